@@ -1,0 +1,147 @@
+/* uecrt.h -- C ABI of the B200-native path-tracing hot path (libuecrt.so).
+ *
+ * The reference (yaito3014/UECRayTracing) has no plugin / FFI interface: it is one
+ * translation unit whose main() calls yk::render() (source.cpp:98-178, 221).  This header
+ * is the thin extern "C" layer the re-hosted yk::render() binds instead; every entry point
+ * names the reference code it replaces.  Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary.  No CPU fallback exists behind it: every compute entry point
+ * returns UECRT_ERR_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Conventions: return 0 = OK, non-zero = failure (uecrt_last_error() gives the text).
+ * The caller owns every buffer it passes.  "host" entry points copy to/from the device
+ * inside the call; "_device" entry points take device pointers and a cudaStream_t (as
+ * void*), so a host runtime that already owns device memory (torch, in bench.py) can keep
+ * the data resident.
+ */
+#ifndef UECRT_H
+#define UECRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UECRT_VERSION 1
+
+enum {
+  UECRT_OK = 0,
+  UECRT_ERR_INVALID = 1,   /* bad argument */
+  UECRT_ERR_NO_DEVICE = 2, /* no CUDA device / not sm_100 */
+  UECRT_ERR_CUDA = 3,      /* a CUDA call failed */
+  UECRT_ERR_NCCL = 4       /* a NCCL call failed (multi-GPU render) */
+};
+
+/* material kinds; 0 and 1 are the reference's (yk/material.hpp:44-76), 2 is the RTIOW
+ * dielectric named by north_star (absent from the reference). */
+enum { UECRT_MAT_LAMBERTIAN = 0, UECRT_MAT_METAL = 1, UECRT_MAT_DIELECTRIC = 2 };
+
+typedef struct { float x, y, z, w; } uecrt_float4;
+
+/* Flattened hittable_list (yk/hittable_list.hpp:18-30) of spheres (yk/sphere.hpp:16-23).
+ * Index order == insertion order == hit_record::id (hittable_list.hpp:41); the closest-hit
+ * tie rule "later index wins" depends on it.  Host pointers. */
+typedef struct {
+  uint32_t n;
+  const uecrt_float4* geom;      /* {cx, cy, cz, radius}                    */
+  const uint32_t* mat_type;      /* UECRT_MAT_*                             */
+  const uecrt_float4* mat_param; /* {albedo r,g,b, fuzz (metal) | ior (dielectric)} */
+} uecrt_scene;
+
+/* yk::camera (yk/camera.hpp:14-38) extended with the RTIOW look-at / defocus fields.
+ * get_ray(s,t) = { origin + off, lower_left + s*horizontal + t*vertical - origin - off },
+ * off = lens_radius * (rd.x*u + rd.y*v).  The reference camera is origin 0,
+ * lower_left (-16/9,-1,-1), horizontal (32/9,0,0), vertical (0,2,0), lens_radius 0. */
+typedef struct {
+  float origin[3], lower_left[3], horizontal[3], vertical[3], u[3], v[3];
+  float lens_radius;
+} uecrt_camera;
+
+typedef struct {
+  uint32_t width, height; /* height = uint32(width / (16/9)) in the reference (source.cpp:59-62) */
+  uint32_t spp;           /* YK_SPP, source.cpp:47-49       */
+  uint32_t max_depth;     /* YK_MAX_DEPTH, source.cpp:51-53 */
+  uint64_t seed;          /* Philox key                     */
+  uint32_t sample_begin;  /* this call renders sample ids [sample_begin, sample_begin+sample_count) */
+  uint32_t sample_count;  /*   of every pixel; 0 means "all spp" (sample_begin ignored)            */
+  int32_t num_gpus;       /* uecrt_render only: spp-shard over this many devices (>=1)             */
+  uint32_t flags;         /* UECRT_FLAG_*                   */
+} uecrt_params;
+
+enum {
+  UECRT_FLAG_EXACT_HITS = 1u, /* resolve every closest hit in FP64 (reference-exact index) inside K1 */
+  UECRT_FLAG_NO_COUNTERS = 2u /* do not count rays/sphere tests (saves two atomics per CTA)          */
+};
+
+typedef struct {
+  uint64_t rays_traced;  /* closest-hit scans executed (one per path segment)          */
+  uint64_t sphere_tests; /* rays_traced * n                                            */
+  uint64_t paths;        /* (pixel,sample) paths finished                              */
+  double kernel_ms;      /* K1 render_paths, CUDA events on the launch stream          */
+  double reduce_ms;      /* NCCL reduce (uecrt_render with num_gpus>1), else 0         */
+  double resolve_ms;     /* K3 resolve                                                 */
+  double h2d_ms, d2h_ms; /* host entry points only                                     */
+  int32_t sm_count, sm_clock_khz;
+  int32_t k1_blocks, k1_threads, k1_smem_bytes, k1_regs;
+} uecrt_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+const char* uecrt_last_error(void);
+int uecrt_version(void);
+/* number of usable sm_100 devices (0 when none; never fails) */
+int uecrt_device_count(void);
+
+/* ---- host-buffer entry points (what the re-hosted yk::render() calls) ---------------
+ * uecrt_render replaces yk::render<T>() (source.cpp:98-178): pixel x spp loop, ray_color
+ * (raytracer.hpp:19-37), hittable_list::hit_impl/scatter (hittable_list.hpp:32-73),
+ * sphere::hit_impl (sphere.hpp:25-48), lambertian/metal scatter (material.hpp:50-75) and
+ * to_color3b (source.cpp:73-83).  rgb_out: W*H*3 bytes, top row first (source.cpp:170-171).
+ * accum_out_or_null: W*H*4 floats, linear radiance SUM over the rendered samples in
+ * .xyz and the sample count in .w.  With num_gpus > 1 the samples are split over the
+ * devices of this process and summed by one NCCL reduce. */
+int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_params* params,
+                 uint8_t* rgb_out, float* accum_out_or_null, uecrt_stats* stats_or_null);
+
+/* uecrt_primary_hits replaces hittable_list::hit_impl (hittable_list.hpp:32-58) on caller
+ * rays: closest hit in the CLOSED interval [t_min, t_max], later index wins ties.
+ * o_xyz/d_xyz: n_rays*3 floats (direction need not be unit; t is in units of |d| as in
+ * sphere.hpp:35).  Outputs: t (double, or -1 on miss), n_xyz (3 doubles), id (-1 on miss),
+ * front_face.  exact != 0 uses the FP64-resolved path (reference-exact index); exact == 0
+ * is the FP32 fast path K1 uses by default. */
+int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz,
+                       const float* d_xyz, double t_min, double t_max, int exact, double* t,
+                       double* n_xyz, int32_t* id, uint8_t* front_face);
+
+/* uecrt_scatter replaces lambertian::scatter / metal::scatter (material.hpp:50-75) and the
+ * RTIOW dielectric, with the random numbers supplied by the caller (uniforms in [0,1), 4
+ * per call) so the result can be compared with the oracle fed the same numbers.
+ * Per call i: mat_type[i], mat_param[i], incoming direction, hit point, unit normal,
+ * front_face -> scattered (0/1), attenuation rgb, scattered ray origin+direction. */
+int uecrt_scatter(uint64_t n, const uint32_t* mat_type, const uecrt_float4* mat_param,
+                  const float* d_in_xyz, const float* p_xyz, const float* normal_xyz,
+                  const uint8_t* front_face, const float* uniforms4, uint8_t* scattered,
+                  float* attenuation_rgb, float* o_out_xyz, float* d_out_xyz);
+
+/* Philox4x32-10 block for (key = seed, counter = {c0,c1,c2,c3}), computed on the device. */
+int uecrt_philox(uint64_t n, uint64_t seed, const uint32_t* counters4, uint32_t* out4);
+
+/* ---- device-resident entry points (one process per GPU; bench.py / torch.distributed) --
+ * A uecrt_ctx owns the device copy of one scene (+camera) on the current CUDA device. */
+typedef struct uecrt_ctx uecrt_ctx;
+int uecrt_ctx_create(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ctx** out);
+void uecrt_ctx_destroy(uecrt_ctx* ctx);
+/* K1: accumulate samples [sample_begin, +sample_count) of every pixel into d_accum
+ * (device, W*H float4, must be zeroed by the caller before the first call of a frame). */
+int uecrt_accumulate_device(uecrt_ctx* ctx, const uecrt_params* params, float* d_accum,
+                            void* cuda_stream, uecrt_stats* stats_or_null);
+/* K3: to_color3b (source.cpp:73-83): d_accum (sum, any .w) / spp -> sqrt -> clamp -> *256 */
+int uecrt_resolve_device(const float* d_accum, uint32_t width, uint32_t height, uint32_t spp,
+                         uint8_t* d_rgb, void* cuda_stream);
+/* statistics of the last uecrt_accumulate_device on ctx (blocks on the stream's events) */
+int uecrt_ctx_stats(uecrt_ctx* ctx, uecrt_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UECRT_H */

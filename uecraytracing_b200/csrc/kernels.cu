@@ -1,0 +1,441 @@
+// kernels.cu -- hand-written sm_100a kernels of the path-tracing hot path.
+//
+//   K1 k_render_paths   render<T>() pixel x spp loop (source.cpp:122-172) + ray_color
+//                       (raytracer.hpp:19-37) + hittable_list hit/scatter (hittable_list.hpp:32-73)
+//                       + sphere::hit_impl (sphere.hpp:25-48) + materials (material.hpp:44-76)
+//   K2 k_primary_hits   hittable_list::hit_impl on caller rays (parity kernel)
+//   K3 k_resolve        to_color3b (source.cpp:73-83)
+//   probes              scatter_material / philox on caller inputs (unit parity)
+//
+// K1 design (B200: 148 SMs, 4 sub-partitions each, FP32 128 lanes/clk/SM):
+//  * persistent CTAs; every thread owns one live path; the reference's recursion is an
+//    iterative loop carrying the throughput product (exact up to FP reassociation);
+//  * the packed scene (32 B per sphere pair) is staged ONCE per CTA into shared memory with
+//    cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier; the scan reads it with
+//    warp-broadcast LDS.128, so there is no bank conflict and no global traffic in the loop;
+//  * work items are (pixel, chunk of samples); a lane whose path ended starts its next sample
+//    at once, and lanes that finished an item refill together with ONE atomicAdd per warp
+//    (__ballot_sync/__popc/__shfl_sync), so all 32 lanes run the scan on every iteration until
+//    the queue is empty -- no lane idles while its neighbours finish long paths;
+//  * a lane accumulates its item's samples in registers and publishes one float4
+//    red.global.add.v4.f32 per item (16 B vector atomic into the W*H float4 accumulation
+//    buffer; consecutive lanes own consecutive pixels);
+//  * RNG: Philox4x32-10 keyed by seed, counter (pixel, sample, bounce, sub) -- see philox.cuh.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "closest_hit.cuh"
+#include "kernels.cuh"
+#include "materials.cuh"
+#include "philox.cuh"
+
+namespace uecrt {
+
+// ---------------------------------------------------------------------------------------
+// TMA bulk staging of the packed scene: global -> shared, completion on an mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_scene_tma(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    const uint32_t kChunk = 32768;   // bytes per bulk copy (multiple of 16)
+    for (uint32_t off = 0; off < bytes; off += kChunk) {
+      const uint32_t sz = bytes - off < kChunk ? bytes - off : kChunk;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32((char*)dst + off)),
+                   "l"((const char*)src + off), "r"(sz), "r"(smem_u32(bar))
+                   : "memory");
+    }
+  }
+  // every thread waits for phase 0 of the barrier (HW sleep, not a spin on memory)
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar))
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// rare path of the scan: the candidate list is full -> fold it into the running best
+__device__ __noinline__ void fold_full_fast(const float4* geom, uint16_t* base, int stride, int cnt, float ox, float oy,
+                                            float oz, float dx, float dy, float dz, float tmin, int self_id,
+                                            FastBest* best) {
+  CandList L{base, stride};
+  resolve_fast(geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, *best);
+}
+__device__ __noinline__ void fold_full_exact(const float4* geom, uint16_t* base, int stride, int cnt, double ox,
+                                             double oy, double oz, double dx, double dy, double dz, double a,
+                                             double tmin, ExactBest* best) {
+  CandList L{base, stride};
+  resolve_exact(geom, L, cnt, ox, oy, oz, dx, dy, dz, a, tmin, *best);
+}
+
+// One closest-hit query for the renderer: unit direction, t in world units.
+template <bool EXACT>
+__device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulonglong2* s_pairs, const CandList& L,
+                                                float ox, float oy, float oz, float dx, float dy, float dz,
+                                                float tmin, int self_id) {
+  const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
+  Hit h;
+  h.id = -1;
+  if (!EXACT) {
+    FastBest best{CUDART_INF_F, -1};
+    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
+      fold_full_fast(sc.geom, L.base, L.stride, c, ox, oy, oz, dx, dy, dz, tmin, self_id, &best);
+    });
+    resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, best);
+    if (best.id >= 0) {
+      h.id = best.id;
+      h.t = best.t;
+      finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+    }
+  } else {
+    const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
+    const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
+    ExactBest best{(double)CUDART_INF, -1};
+    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
+      fold_full_exact(sc.geom, L.base, L.stride, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, &best);
+    });
+    resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, best);
+    if (best.id >= 0) {
+      const float4 g = __ldg(&sc.geom[best.id]);
+      const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
+      const double r = g.w;
+      double nx = (px - (double)g.x) / r, ny = (py - (double)g.y) / r, nz = (pz - (double)g.z) / r;   // sphere.hpp:44
+      const bool front = (Dx * nx + Dy * ny + Dz * nz) < 0;                                   // hittable.hpp:25
+      if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+      h.id = best.id; h.t = (float)best.t; h.front = front;
+      h.px = (float)px; h.py = (float)py; h.pz = (float)pz;
+      h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
+    }
+  }
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1
+template <bool EXACT>
+__global__ void __launch_bounds__(kRenderThreads, 2) k_render_paths(const RenderArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
+  const uint32_t pair_bytes = (uint32_t)a.sc.npairs * 32u;
+  uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + 16 + pair_bytes);
+  stage_scene_tma(bar, s_pairs, a.sc.pairs, pair_bytes);
+
+  const CandList L{s_lists + threadIdx.x, (int)blockDim.x};
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long n_pixels = (unsigned long long)a.width * a.height;
+  const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
+
+  bool active = false, done = false;
+  uint32_t pixel = 0, s_next = 0, s_end = 0, sample = 0, bounce = 0;
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_n = 0.f;
+  float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, dlen = 1.f;
+  float thr_r = 1.f, thr_g = 1.f, thr_b = 1.f;
+  uint32_t depth_left = 0;
+  int self_id = -1;
+  unsigned n_rays = 0, n_paths = 0;
+
+  for (;;) {
+    // ---- refill: lanes that finished an item publish it and pull the next one together
+    const bool need_item = !active && !done && (s_next == s_end);
+    const unsigned need_mask = __ballot_sync(0xffffffffu, need_item);
+    if (need_mask) {
+      if (need_item && acc_n > 0.f) {
+        red_add_v4(a.accum + pixel, acc_r, acc_g, acc_b, acc_n);
+        acc_r = acc_g = acc_b = acc_n = 0.f;
+      }
+      const int leader = __ffs(need_mask) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(need_mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need_item) {
+        const unsigned long long w = base + __popc(need_mask & ((1u << lane) - 1u));
+        if (w < a.total_items) {
+          const unsigned long long q = w / n_pixels;
+          pixel = (uint32_t)(w - q * n_pixels);
+          s_next = a.sample_begin + (uint32_t)q * a.chunk;
+          const uint32_t lim = a.sample_begin + a.sample_count;
+          s_end = s_next + a.chunk < lim ? s_next + a.chunk : lim;
+        } else {
+          done = true;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+
+    // ---- start the next sample of this lane's item: camera ray (source.cpp:154-165, camera.hpp:29-32)
+    if (!active && !done) {
+      sample = s_next++;
+      const uint32_t py = pixel / a.width, px = pixel - py * a.width;
+      philox_out r = philox4x32_10(pixel, sample, 0u, 0u, a.key0, a.key1);
+      const float u = ((float)px + uecrt_u01(r.x)) * inv_w;
+      const float v = ((float)(a.height - py - 1u) + uecrt_u01(r.y)) * inv_h;
+      float tx = fmaf(v, a.cam.ver[0], fmaf(u, a.cam.hor[0], a.cam.ll[0]));
+      float ty = fmaf(v, a.cam.ver[1], fmaf(u, a.cam.hor[1], a.cam.ll[1]));
+      float tz = fmaf(v, a.cam.ver[2], fmaf(u, a.cam.hor[2], a.cam.ll[2]));
+      ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
+      if (a.cam.lens > 0.f) {
+        // RTIOW random_in_unit_disk: rejection on successive Philox blocks (sub = 1, 2, ...)
+        float rx = fmaf(2.f, uecrt_u01(r.z), -1.f), ry = fmaf(2.f, uecrt_u01(r.w), -1.f);
+        uint32_t sub = 1;
+        while (rx * rx + ry * ry >= 1.f) {
+          philox_out q = philox4x32_10(pixel, sample, 0u, sub++, a.key0, a.key1);
+          rx = fmaf(2.f, uecrt_u01(q.x), -1.f); ry = fmaf(2.f, uecrt_u01(q.y), -1.f);
+          if (rx * rx + ry * ry >= 1.f) { rx = fmaf(2.f, uecrt_u01(q.z), -1.f); ry = fmaf(2.f, uecrt_u01(q.w), -1.f); }
+        }
+        const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;
+        const float offx = fmaf(ly, a.cam.v[0], lx * a.cam.u[0]);
+        const float offy = fmaf(ly, a.cam.v[1], lx * a.cam.u[1]);
+        const float offz = fmaf(ly, a.cam.v[2], lx * a.cam.u[2]);
+        tx = tx - ox - offx; ty = ty - oy - offy; tz = tz - oz - offz;
+        ox += offx; oy += offy; oz += offz;
+      } else if (!a.cam.origin_is_zero) {
+        tx -= ox; ty -= oy; tz -= oz;
+      }
+      const float len2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+      dlen = sqrtf(len2);
+      const float inv = 1.0f / dlen;
+      dx = tx * inv; dy = ty * inv; dz = tz * inv;
+      thr_r = thr_g = thr_b = 1.f;
+      depth_left = a.max_depth;
+      self_id = -1;
+      bounce = 0;
+      active = depth_left > 0;
+      if (!active) { acc_n += 1.f; ++n_paths; }   // depth 0: black (raytracer.hpp:26)
+    }
+
+    // ---- one path segment: closest hit + scatter (raytracer.hpp:27-36)
+    if (active) {
+      ++n_rays;
+      const Hit h = closest_hit_unit<EXACT>(a.sc, s_pairs, L, ox, oy, oz, dx, dy, dz, 0.001f * dlen, self_id);
+      float rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
+      bool ended = true;
+      if (h.id < 0) {
+        const float t = 0.5f * (dy + 1.0f);                       // raytracer.hpp:35
+        const float w0 = 1.0f - t;
+        rad_r = thr_r * fmaf(t, 0.5f, w0); rad_g = thr_g * fmaf(t, 0.7f, w0); rad_b = thr_b * (w0 + t);
+      } else {
+        ++bounce;
+        const uint32_t mt = __ldg(&a.sc.mat_type[h.id]);
+        const float4 mp = __ldg(&a.sc.mat_param[h.id]);
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+        if (mt != UECRT_MAT_METAL || mp.w > 0.f) {
+          const philox_out r = philox4x32_10(pixel, sample, bounce, 0u, a.key0, a.key1);
+          u0 = uecrt_u01(r.x); u1 = uecrt_u01(r.y); u2 = uecrt_u01(r.z); u3 = uecrt_u01(r.w);
+        }
+        const ScatterOut s = scatter_material(mt, mp, dx, dy, dz, h.nx, h.ny, h.nz, h.front, u0, u1, u2, u3);
+        if (s.ok && depth_left > 1u) {                             // depth-1 == 0 returns black (raytracer.hpp:26)
+          thr_r *= s.ar; thr_g *= s.ag; thr_b *= s.ab;
+          ox = h.px; oy = h.py; oz = h.pz;
+          const float len2 = fmaf(s.dz, s.dz, fmaf(s.dy, s.dy, s.dx * s.dx));
+          dlen = sqrtf(len2);
+          const float inv = 1.0f / dlen;
+          dx = s.dx * inv; dy = s.dy * inv; dz = s.dz * inv;
+          self_id = h.id;
+          --depth_left;
+          ended = false;
+        }
+      }
+      if (ended) {
+        // a NaN radiance would hang the reference's math::sqrt (math.hpp:14); it contributes 0 here
+        acc_r += (rad_r == rad_r) ? rad_r : 0.f;
+        acc_g += (rad_g == rad_g) ? rad_g : 0.f;
+        acc_b += (rad_b == rad_b) ? rad_b : 0.f;
+        acc_n += 1.f;
+        ++n_paths;
+        active = false;
+      }
+    }
+  }
+
+  if (a.count_stats) {
+    unsigned r = n_rays, p = n_paths;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+    if (lane == 0) {
+      atomicAdd(a.counters + 1, (unsigned long long)r);
+      atomicAdd(a.counters + 2, (unsigned long long)p);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: closest hit on caller rays.  One thread per ray, same scan + resolve as K1.
+template <bool EXACT>
+__global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene sc, unsigned long long n_rays,
+                                                               const float* __restrict__ o, const float* __restrict__ d,
+                                                               double tmin, double tmax, double* __restrict__ t_out,
+                                                               double* __restrict__ n_out, int32_t* __restrict__ id_out,
+                                                               uint8_t* __restrict__ ff_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
+  const uint32_t pair_bytes = (uint32_t)sc.npairs * 32u;
+  uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + 16 + pair_bytes);
+  stage_scene_tma(bar, s_pairs, sc.pairs, pair_bytes);
+  const CandList L{s_lists + threadIdx.x, (int)blockDim.x};
+
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float ox = o[3 * i], oy = o[3 * i + 1], oz = o[3 * i + 2];
+    const float rx = d[3 * i], ry = d[3 * i + 1], rz = d[3 * i + 2];
+    const float dlen = sqrtf(fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
+    const float inv = 1.0f / dlen;
+    const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
+    const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
+    double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
+    int id = -1;
+    bool front = false;
+    if (!EXACT) {
+      const float tmin_w = (float)tmin * dlen;
+      FastBest best{(float)tmax * dlen, -1};
+      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
+        fold_full_fast(sc.geom, L.base, L.stride, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
+      });
+      resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
+      if (best.id >= 0) {
+        Hit h; h.id = best.id; h.t = best.t;
+        finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+        id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
+      }
+    } else {
+      const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
+      const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
+      ExactBest best{tmax, -1};
+      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
+        fold_full_exact(sc.geom, L.base, L.stride, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
+      });
+      resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
+      if (best.id >= 0) {
+        const float4 g = __ldg(&sc.geom[best.id]);
+        const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
+                     pz = __dadd_rn(Oz, __dmul_rn(Dz, best.t));                                   // ray.hpp:16-19
+        const double r = g.w;
+        nx = __ddiv_rn(__dsub_rn(px, (double)g.x), r);                                             // sphere.hpp:44
+        ny = __ddiv_rn(__dsub_rn(py, (double)g.y), r);
+        nz = __ddiv_rn(__dsub_rn(pz, (double)g.z), r);
+        front = __dadd_rn(__dadd_rn(__dmul_rn(Dx, nx), __dmul_rn(Dy, ny)), __dmul_rn(Dz, nz)) < 0;  // hittable.hpp:25
+        if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+        id = best.id; t = best.t;
+      }
+    }
+    t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
+    id_out[i] = id; ff_out[i] = front ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: to_color3b (source.cpp:73-83): sum / spp -> sqrt -> clamp [0, 0.999] -> * 256 -> truncate.
+// Done in double like the reference (the input is an FP32 sum); NaN / negative -> 0.
+__global__ void k_resolve(const float4* __restrict__ accum, uint32_t n_pixels, uint32_t spp, uint8_t* __restrict__ rgb) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pixels) return;
+  const float4 a = accum[i];
+  const double inv = 1.0 / (double)spp;
+  auto q = [&](float c) -> uint8_t {
+    double v = (double)c * inv;
+    v = (v == v && v > 0.0) ? sqrt(v) : 0.0;
+    v = v > 0.999 ? 0.999 : v;
+    return (uint8_t)(v * 256.0);
+  };
+  rgb[3 * i] = q(a.x); rgb[3 * i + 1] = q(a.y); rgb[3 * i + 2] = q(a.z);
+}
+
+// ---------------------------------------------------------------------------------------
+// probes
+__global__ void k_scatter(unsigned long long n, const uint32_t* __restrict__ mat_type, const float4* __restrict__ mat_param,
+                          const float* __restrict__ d_in, const float* __restrict__ p, const float* __restrict__ nrm,
+                          const uint8_t* __restrict__ ff, const float* __restrict__ un, uint8_t* __restrict__ scattered,
+                          float* __restrict__ att, float* __restrict__ o_out, float* __restrict__ d_out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float dx = d_in[3 * i], dy = d_in[3 * i + 1], dz = d_in[3 * i + 2];
+  const float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));   // material.hpp:70 normalises d_in
+  dx *= inv; dy *= inv; dz *= inv;
+  const ScatterOut s = scatter_material(mat_type[i], mat_param[i], dx, dy, dz, nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2],
+                                        ff[i] != 0, un[4 * i], un[4 * i + 1], un[4 * i + 2], un[4 * i + 3]);
+  scattered[i] = s.ok ? 1 : 0;
+  att[3 * i] = s.ar; att[3 * i + 1] = s.ag; att[3 * i + 2] = s.ab;
+  o_out[3 * i] = p[3 * i]; o_out[3 * i + 1] = p[3 * i + 1]; o_out[3 * i + 2] = p[3 * i + 2];
+  d_out[3 * i] = s.dx; d_out[3 * i + 1] = s.dy; d_out[3 * i + 2] = s.dz;
+}
+
+__global__ void k_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* __restrict__ c, uint32_t* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const philox_out r = philox4x32_10(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], k0, k1);
+  out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+size_t render_smem_bytes(int npairs, int threads) {
+  return 16 + (size_t)npairs * 32 + (size_t)kListCap * threads * sizeof(uint16_t);
+}
+
+cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render) {
+  cudaError_t e;
+  const int optin = 232448;
+  if ((e = cudaFuncSetAttribute(k_render_paths<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_render_paths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_primary_hits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_primary_hits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, k_render_paths<false>)) != cudaSuccess) return e;
+  if (regs_render) *regs_render = fa.numRegs;
+  int nb = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_paths<false>, kRenderThreads, smem_render)) != cudaSuccess) return e;
+  if (max_blocks_per_sm) *max_blocks_per_sm = nb;
+  return cudaSuccess;
+}
+
+void launch_render_paths(const RenderArgs& a, bool exact, int blocks, int threads, size_t smem, cudaStream_t st) {
+  if (exact)
+    k_render_paths<true><<<blocks, threads, smem, st>>>(a);
+  else
+    k_render_paths<false><<<blocks, threads, smem, st>>>(a);
+}
+
+void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
+                         double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, cudaStream_t st) {
+  const size_t smem = render_smem_bytes(sc.npairs, kHitsThreads);
+  unsigned long long want = (n_rays + kHitsThreads - 1) / kHitsThreads;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148ull * 16 ? 148ull * 16 : want));
+  if (exact)
+    k_primary_hits<true><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  else
+    k_primary_hits<false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+}
+
+void launch_resolve(const float4* accum, uint32_t n_pixels, uint32_t spp, uint8_t* rgb, cudaStream_t st) {
+  k_resolve<<<(n_pixels + 255) / 256, 256, 0, st>>>(accum, n_pixels, spp, rgb);
+}
+
+void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4* mat_param, const float* d_in,
+                    const float* p, const float* nrm, const uint8_t* ff, const float* uniforms4, uint8_t* scattered,
+                    float* att, float* o_out, float* d_out, cudaStream_t st) {
+  k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, mat_type, mat_param, d_in, p, nrm, ff, uniforms4, scattered,
+                                                        att, o_out, d_out);
+}
+
+void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st) {
+  k_philox<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, k0, k1, ctr4, out4);
+}
+
+}  // namespace uecrt

@@ -1,0 +1,53 @@
+// kernels.cuh -- kernel argument blocks shared by kernels.cu (device) and uecrt_api.cu (host).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uecrt {
+
+struct DeviceScene {
+  const ulonglong2* pairs;   // global copy of the packed pairs (2 x 16 B per pair), staged to smem by TMA
+  int npairs;                // padded, multiple of 4
+  int n;                     // spheres
+  const float4* geom;        // {cx,cy,cz,r}
+  const uint32_t* mat_type;
+  const float4* mat_param;
+};
+
+struct DeviceCamera {
+  float origin[3], ll[3], hor[3], ver[3], u[3], v[3];
+  float lens;
+  int origin_is_zero;        // the reference never subtracts its zero origin (camera.hpp:29-32)
+};
+
+// counters[0] work-queue head, [1] rays traced, [2] paths finished
+struct RenderArgs {
+  DeviceScene sc;
+  DeviceCamera cam;
+  uint32_t width, height;
+  uint32_t sample_begin, sample_count, chunk;   // chunk = samples per work item
+  uint32_t max_depth;
+  uint32_t key0, key1;                          // Philox key (seed)
+  unsigned long long total_items;               // pixels * ceil(sample_count / chunk)
+  float4* accum;
+  unsigned long long* counters;
+  int count_stats;
+};
+
+constexpr int kRenderThreads = 256;
+constexpr int kHitsThreads = 128;
+
+size_t render_smem_bytes(int npairs, int threads);
+
+void launch_render_paths(const RenderArgs& a, bool exact, int blocks, int threads, size_t smem, cudaStream_t st);
+void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,
+                         double tmin, double tmax, bool exact, double* t, double* nrm, int32_t* id,
+                         uint8_t* ff, cudaStream_t st);
+void launch_resolve(const float4* accum, uint32_t n_pixels, uint32_t spp, uint8_t* rgb, cudaStream_t st);
+void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4* mat_param, const float* d_in,
+                    const float* p, const float* nrm, const uint8_t* ff, const float* uniforms4,
+                    uint8_t* scattered, float* att, float* o_out, float* d_out, cudaStream_t st);
+void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st);
+cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render);
+
+}  // namespace uecrt

@@ -1,0 +1,540 @@
+// uecrt_api.cu -- implementation of the C ABI declared in include/uecrt.h.
+//
+// Host side of the boundary: packs the flattened hittable_list (scene_pack.hpp), owns device
+// memory and CUDA events, launches K1/K2/K3 (kernels.cu) and, for uecrt_render with
+// num_gpus > 1, shards samples-per-pixel over the devices of this process (one host thread per
+// GPU) and sums the float4 accumulation buffers with ONE ncclReduce over NVLink.
+// There is no CPU fallback: without an sm_100 device every compute entry point fails with
+// UECRT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/uecrt.h"
+#include "kernels.cuh"
+#include "scene_pack.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_err_mutex;
+std::string g_last_err_any;   // last error from any thread (worker threads of uecrt_render)
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_err_any = buf;
+  }
+  return code;
+}
+
+#define CUDA_TRY(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(UECRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+bool device_is_sm100(int dev) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+  return major == 10;
+}
+
+int usable_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d)
+    if (device_is_sm100(d)) ++ok; else break;
+  return ok;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(UECRT_ERR_NO_DEVICE, "no CUDA device (%s); libuecrt has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!device_is_sm100(dev)) return fail(UECRT_ERR_NO_DEVICE, "device %d is not sm_100 (B200); kernels are built for sm_100a only", dev);
+  return UECRT_OK;
+}
+
+int validate_scene(const uecrt_scene* s) {
+  if (!s) return fail(UECRT_ERR_INVALID, "scene is null");
+  if (s->n > 65534u) return fail(UECRT_ERR_INVALID, "scene has %u spheres; the candidate lists hold 16-bit indices (max 65534)", s->n);
+  if (s->n && (!s->geom || !s->mat_type || !s->mat_param)) return fail(UECRT_ERR_INVALID, "scene arrays are null");
+  for (uint32_t i = 0; i < s->n; ++i)
+    if (s->mat_type[i] > UECRT_MAT_DIELECTRIC) return fail(UECRT_ERR_INVALID, "sphere %u: unknown material type %u", i, s->mat_type[i]);
+  return UECRT_OK;
+}
+
+}  // namespace
+
+struct uecrt_ctx {
+  int device = 0;
+  uecrt::DeviceScene sc{};
+  uecrt::DeviceCamera cam{};
+  void* d_pairs = nullptr;
+  void* d_geom = nullptr;
+  void* d_mat_type = nullptr;
+  void* d_mat_param = nullptr;
+  unsigned long long* d_counters = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int sm_count = 0, sm_clock_khz = 0, regs = 0, blocks_per_sm = 0;
+  int last_blocks = 0;
+  size_t smem = 0;
+  uint32_t n = 0;
+};
+
+namespace {
+
+int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
+  const uecrt::PackedScene ps = uecrt::pack_scene(*scene);
+  const size_t pair_bytes = (size_t)ps.npairs * 32;
+  const size_t smem_need = uecrt::render_smem_bytes((int)ps.npairs, uecrt::kRenderThreads);
+  if (smem_need > 232448)
+    return fail(UECRT_ERR_INVALID, "scene of %u spheres needs %zu B of shared memory per CTA (max 232448)", scene->n, smem_need);
+  const uint32_t n_alloc = std::max<uint32_t>(scene->n, 1);
+  CUDA_TRY(cudaMalloc(&c->d_pairs, pair_bytes));
+  CUDA_TRY(cudaMalloc(&c->d_geom, (size_t)n_alloc * sizeof(uecrt_float4)));
+  CUDA_TRY(cudaMalloc(&c->d_mat_type, (size_t)n_alloc * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->d_mat_param, (size_t)n_alloc * sizeof(uecrt_float4)));
+  CUDA_TRY(cudaMemcpy(c->d_pairs, ps.pairs.data(), pair_bytes, cudaMemcpyHostToDevice));
+  if (scene->n) {
+    CUDA_TRY(cudaMemcpy(c->d_geom, scene->geom, (size_t)scene->n * sizeof(uecrt_float4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_mat_type, scene->mat_type, (size_t)scene->n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_mat_param, scene->mat_param, (size_t)scene->n * sizeof(uecrt_float4), cudaMemcpyHostToDevice));
+  }
+  c->n = scene->n;
+  c->sc.pairs = static_cast<const ulonglong2*>(c->d_pairs);
+  c->sc.npairs = (int)ps.npairs;
+  c->sc.n = (int)scene->n;
+  c->sc.geom = static_cast<const float4*>(c->d_geom);
+  c->sc.mat_type = static_cast<const uint32_t*>(c->d_mat_type);
+  c->sc.mat_param = static_cast<const float4*>(c->d_mat_param);
+  c->smem = smem_need;
+  return UECRT_OK;
+}
+
+void ctx_free(uecrt_ctx* c) {
+  if (!c) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  cudaSetDevice(prev);
+  delete c;
+}
+
+int ctx_create_on_current_device(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ctx** out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = validate_scene(scene))) return rc;
+  uecrt_ctx* c = new uecrt_ctx();
+  cudaGetDevice(&c->device);
+  rc = ctx_upload_scene(c, scene);
+  if (rc) { ctx_free(c); return rc; }
+  if (cam) {
+    for (int i = 0; i < 3; ++i) {
+      c->cam.origin[i] = cam->origin[i]; c->cam.ll[i] = cam->lower_left[i]; c->cam.hor[i] = cam->horizontal[i];
+      c->cam.ver[i] = cam->vertical[i]; c->cam.u[i] = cam->u[i]; c->cam.v[i] = cam->v[i];
+    }
+    c->cam.lens = cam->lens_radius;
+    c->cam.origin_is_zero = (cam->origin[0] == 0.f && cam->origin[1] == 0.f && cam->origin[2] == 0.f) ? 1 : 0;
+  }
+  cudaError_t e;
+  if ((e = cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+      (e = uecrt::configure_kernels(&c->regs, &c->blocks_per_sm, c->smem)) != cudaSuccess) {
+    ctx_free(c);
+    return fail(UECRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+  }
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+  cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, c->device);
+  if (c->blocks_per_sm < 1) { ctx_free(c); return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem); }
+  *out = c;
+  return UECRT_OK;
+}
+
+int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream_t st) {
+  if (!ctx || !p || !d_accum) return fail(UECRT_ERR_INVALID, "null argument");
+  if (p->width == 0 || p->height == 0) return fail(UECRT_ERR_INVALID, "empty image");
+  uint32_t begin = p->sample_begin, count = p->sample_count;
+  if (count == 0) { begin = 0; count = p->spp; }
+  uecrt::RenderArgs a{};
+  a.sc = ctx->sc; a.cam = ctx->cam;
+  a.width = p->width; a.height = p->height;
+  a.sample_begin = begin; a.sample_count = count;
+  a.chunk = std::max<uint32_t>(1, std::min<uint32_t>(count, 16));
+  a.max_depth = p->max_depth;
+  a.key0 = (uint32_t)(p->seed & 0xffffffffull); a.key1 = (uint32_t)(p->seed >> 32);
+  const unsigned long long chunks = count ? (count + a.chunk - 1) / a.chunk : 0;
+  a.total_items = (unsigned long long)p->width * p->height * chunks;
+  a.accum = reinterpret_cast<float4*>(d_accum);
+  a.counters = ctx->d_counters;
+  a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
+  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  const int blocks = ctx->sm_count * ctx->blocks_per_sm;
+  ctx->last_blocks = blocks;
+  CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+  uecrt::launch_render_paths(a, (p->flags & UECRT_FLAG_EXACT_HITS) != 0, blocks, uecrt::kRenderThreads, ctx->smem, st);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+  ctx->timed = true;
+  return UECRT_OK;
+}
+
+int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
+  if (!ctx || !out) return fail(UECRT_ERR_INVALID, "null argument");
+  std::memset(out, 0, sizeof *out);
+  out->sm_count = ctx->sm_count; out->sm_clock_khz = ctx->sm_clock_khz;
+  out->k1_blocks = ctx->last_blocks; out->k1_threads = uecrt::kRenderThreads;
+  out->k1_smem_bytes = (int32_t)ctx->smem; out->k1_regs = ctx->regs;
+  if (!ctx->timed) return UECRT_OK;
+  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  out->kernel_ms = ms;
+  unsigned long long h[4];
+  CUDA_TRY(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+  out->rays_traced = h[1]; out->paths = h[2]; out->sphere_tests = h[1] * (unsigned long long)ctx->n;
+  return UECRT_OK;
+}
+
+// ---- NCCL through dlopen: only uecrt_render(num_gpus > 1) needs it ---------------------
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(void** comms, int ndev, const int* devlist) = nullptr;
+  int (*CommDestroy)(void* comm) = nullptr;
+  int (*Reduce)(const void* send, void* recv, size_t count, int dtype, int op, int root, void* comm, cudaStream_t st) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclFloat = 7, kNcclSum = 0;   // ncclFloat32, ncclSum (nccl.h enums, stable since 2.0)
+
+int load_nccl(NcclApi& n) {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (n.lib) break;
+  }
+  if (!n.lib) return fail(UECRT_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  n.CommInitAll = reinterpret_cast<decltype(n.CommInitAll)>(dlsym(n.lib, "ncclCommInitAll"));
+  n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(n.lib, "ncclCommDestroy"));
+  n.Reduce = reinterpret_cast<decltype(n.Reduce)>(dlsym(n.lib, "ncclReduce"));
+  n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(dlsym(n.lib, "ncclGroupStart"));
+  n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(dlsym(n.lib, "ncclGroupEnd"));
+  n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(n.lib, "ncclGetErrorString"));
+  if (!n.CommInitAll || !n.CommDestroy || !n.Reduce || !n.GroupStart || !n.GroupEnd)
+    return fail(UECRT_ERR_NCCL, "libnccl lacks a required symbol");
+  return UECRT_OK;
+}
+
+// process-global communicator cache (communicator creation is excluded from frame timing)
+struct CommCache {
+  std::mutex m;
+  NcclApi api;
+  int ndev = 0;
+  std::vector<void*> comms;
+} g_comms;
+
+int get_comms(int ndev, std::vector<void*>& out, NcclApi*& api) {
+  std::lock_guard<std::mutex> lk(g_comms.m);
+  if (!g_comms.api.lib) {
+    int rc = load_nccl(g_comms.api);
+    if (rc) return rc;
+  }
+  if (g_comms.ndev != ndev) {
+    for (void* c : g_comms.comms) g_comms.api.CommDestroy(c);
+    g_comms.comms.assign(ndev, nullptr);
+    std::vector<int> devs(ndev);
+    for (int i = 0; i < ndev; ++i) devs[i] = i;
+    int r = g_comms.api.CommInitAll(g_comms.comms.data(), ndev, devs.data());
+    if (r != 0) {
+      g_comms.comms.clear(); g_comms.ndev = 0;
+      return fail(UECRT_ERR_NCCL, "ncclCommInitAll(%d) failed: %s", ndev, g_comms.api.GetErrorString ? g_comms.api.GetErrorString(r) : "?");
+    }
+    g_comms.ndev = ndev;
+  }
+  out = g_comms.comms;
+  api = &g_comms.api;
+  return UECRT_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* uecrt_last_error(void) {
+  if (!g_err.empty()) return g_err.c_str();
+  std::lock_guard<std::mutex> lk(g_err_mutex);
+  g_err = g_last_err_any;
+  return g_err.c_str();
+}
+int uecrt_version(void) { return UECRT_VERSION; }
+int uecrt_device_count(void) { return usable_device_count(); }
+
+int uecrt_ctx_create(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ctx** out) {
+  if (!out) return fail(UECRT_ERR_INVALID, "out is null");
+  *out = nullptr;
+  return ctx_create_on_current_device(scene, cam, out);
+}
+void uecrt_ctx_destroy(uecrt_ctx* ctx) { ctx_free(ctx); }
+
+int uecrt_accumulate_device(uecrt_ctx* ctx, const uecrt_params* params, float* d_accum, void* cuda_stream,
+                            uecrt_stats* stats_or_null) {
+  int rc = accumulate(ctx, params, d_accum, static_cast<cudaStream_t>(cuda_stream));
+  if (rc) return rc;
+  if (stats_or_null) return ctx_stats(ctx, stats_or_null);
+  return UECRT_OK;
+}
+
+int uecrt_resolve_device(const float* d_accum, uint32_t width, uint32_t height, uint32_t spp, uint8_t* d_rgb,
+                         void* cuda_stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!d_accum || !d_rgb || spp == 0) return fail(UECRT_ERR_INVALID, "bad argument");
+  uecrt::launch_resolve(reinterpret_cast<const float4*>(d_accum), width * height, spp, d_rgb, static_cast<cudaStream_t>(cuda_stream));
+  CUDA_TRY(cudaGetLastError());
+  return UECRT_OK;
+}
+
+int uecrt_ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) { return ctx_stats(ctx, out); }
+
+int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_params* params, uint8_t* rgb_out,
+                 float* accum_out_or_null, uecrt_stats* stats_or_null) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!scene || !cam || !params || !rgb_out) return fail(UECRT_ERR_INVALID, "null argument");
+  if (params->spp == 0) return fail(UECRT_ERR_INVALID, "spp must be > 0");
+  const int avail = usable_device_count();
+  int ndev = params->num_gpus <= 0 ? 1 : params->num_gpus;
+  if (ndev > avail) return fail(UECRT_ERR_INVALID, "num_gpus=%d but only %d sm_100 device(s) are visible", ndev, avail);
+  uint32_t begin = params->sample_begin, count = params->sample_count;
+  if (count == 0) { begin = 0; count = params->spp; }
+  ndev = (int)std::min<uint32_t>((uint32_t)ndev, count);
+  const size_t npx = (size_t)params->width * params->height;
+
+  int dev0 = 0;
+  CUDA_TRY(cudaGetDevice(&dev0));
+  std::vector<void*> comms;
+  NcclApi* nccl = nullptr;
+  if (ndev > 1 && (rc = get_comms(ndev, comms, nccl))) return rc;
+
+  struct PerDev {
+    uecrt_ctx* ctx = nullptr; float* accum = nullptr; cudaStream_t st = nullptr; int rc = 0; uecrt_stats stats{};
+    cudaEvent_t r0 = nullptr, r1 = nullptr;
+  };
+  std::vector<PerDev> pd(ndev);
+  std::vector<std::thread> th;
+  uint8_t* d_rgb = nullptr;
+  double resolve_ms = 0, d2h_ms = 0, reduce_ms = 0;
+
+  auto worker = [&](int g) {
+    PerDev& w = pd[g];
+    auto body = [&]() -> int {
+      const int dev = ndev > 1 ? g : dev0;
+      CUDA_TRY(cudaSetDevice(dev));
+      int r = ctx_create_on_current_device(scene, cam, &w.ctx);
+      if (r) return r;
+      CUDA_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
+      CUDA_TRY(cudaMalloc(&w.accum, npx * 4 * sizeof(float)));
+      CUDA_TRY(cudaMemsetAsync(w.accum, 0, npx * 4 * sizeof(float), w.st));
+      uecrt_params p = *params;
+      // spp shard g of ndev: global sample ids, so the image does not depend on ndev
+      const uint32_t lo = begin + (uint32_t)((uint64_t)count * g / ndev), hi = begin + (uint32_t)((uint64_t)count * (g + 1) / ndev);
+      p.sample_begin = lo; p.sample_count = hi - lo;
+      if (p.sample_count) {
+        r = accumulate(w.ctx, &p, w.accum, w.st);
+        if (r) return r;
+      }
+      CUDA_TRY(cudaEventCreate(&w.r0)); CUDA_TRY(cudaEventCreate(&w.r1));
+      return UECRT_OK;
+    };
+    w.rc = body();
+  };
+  if (ndev == 1) worker(0);
+  else {
+    for (int g = 0; g < ndev; ++g) th.emplace_back(worker, g);
+    for (auto& t : th) t.join();
+  }
+  auto cleanup = [&]() {
+    for (int g = 0; g < ndev; ++g) {
+      cudaSetDevice(ndev > 1 ? g : dev0);
+      if (pd[g].accum) cudaFree(pd[g].accum);
+      if (pd[g].st) { cudaStreamSynchronize(pd[g].st); cudaStreamDestroy(pd[g].st); }
+      if (pd[g].r0) cudaEventDestroy(pd[g].r0);
+      if (pd[g].r1) cudaEventDestroy(pd[g].r1);
+      if (pd[g].ctx) ctx_free(pd[g].ctx);
+    }
+    cudaSetDevice(dev0);
+    if (d_rgb) cudaFree(d_rgb);
+  };
+  for (int g = 0; g < ndev; ++g)
+    if (pd[g].rc) { rc = pd[g].rc; cleanup(); return rc; }
+
+  // ---- one NCCL reduce of W*H*4 floats to device 0 (in place on the root)
+  if (ndev > 1) {
+    nccl->GroupStart();
+    for (int g = 0; g < ndev; ++g) {
+      cudaSetDevice(g);
+      cudaEventRecord(pd[g].r0, pd[g].st);
+      int r = nccl->Reduce(pd[g].accum, pd[g].accum, npx * 4, kNcclFloat, kNcclSum, 0, comms[g], pd[g].st);
+      if (r != 0) rc = fail(UECRT_ERR_NCCL, "ncclReduce failed on device %d: %s", g, nccl->GetErrorString ? nccl->GetErrorString(r) : "?");
+    }
+    int r = nccl->GroupEnd();
+    if (r != 0 && !rc) rc = fail(UECRT_ERR_NCCL, "ncclGroupEnd failed: %s", nccl->GetErrorString ? nccl->GetErrorString(r) : "?");
+    for (int g = 0; g < ndev; ++g) { cudaSetDevice(g); cudaEventRecord(pd[g].r1, pd[g].st); }
+    if (rc) { cleanup(); return rc; }
+  }
+
+  // ---- root: K3 resolve + copies back
+  auto root = [&]() -> int {
+    CUDA_TRY(cudaSetDevice(ndev > 1 ? 0 : dev0));
+    PerDev& w = pd[0];
+    cudaEvent_t e0, e1, e2;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventCreate(&e2));
+    CUDA_TRY(cudaMalloc(&d_rgb, npx * 3));
+    CUDA_TRY(cudaEventRecord(e0, w.st));
+    uecrt::launch_resolve(reinterpret_cast<const float4*>(w.accum), (uint32_t)npx, count, d_rgb, w.st);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e1, w.st));
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, d_rgb, npx * 3, cudaMemcpyDeviceToHost, w.st));
+    if (accum_out_or_null) CUDA_TRY(cudaMemcpyAsync(accum_out_or_null, w.accum, npx * 4 * sizeof(float), cudaMemcpyDeviceToHost, w.st));
+    CUDA_TRY(cudaEventRecord(e2, w.st));
+    CUDA_TRY(cudaStreamSynchronize(w.st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1)); resolve_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e1, e2)); d2h_ms = ms;
+    if (ndev > 1) { CUDA_TRY(cudaEventElapsedTime(&ms, w.r0, w.r1)); reduce_ms = ms; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return UECRT_OK;
+  };
+  rc = root();
+  if (!rc && stats_or_null) {
+    uecrt_stats total{};
+    for (int g = 0; g < ndev && !rc; ++g) {
+      cudaSetDevice(ndev > 1 ? g : dev0);
+      cudaStreamSynchronize(pd[g].st);
+      uecrt_stats s{};
+      rc = ctx_stats(pd[g].ctx, &s);
+      if (g == 0) total = s;
+      else {
+        total.rays_traced += s.rays_traced; total.sphere_tests += s.sphere_tests; total.paths += s.paths;
+        total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms);
+      }
+    }
+    total.reduce_ms = reduce_ms; total.resolve_ms = resolve_ms; total.d2h_ms = d2h_ms;
+    *stats_or_null = total;
+  }
+  cleanup();
+  return rc;
+}
+
+int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
+                       double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (n_rays == 0) return UECRT_OK;
+  if (!o_xyz || !d_xyz || !t || !n_xyz || !id || !front_face) return fail(UECRT_ERR_INVALID, "null argument");
+  uecrt_ctx* c = nullptr;
+  if ((rc = ctx_create_on_current_device(scene, nullptr, &c))) return rc;
+  float *d_o = nullptr, *d_d = nullptr;
+  double *d_t = nullptr, *d_n = nullptr;
+  int32_t* d_id = nullptr;
+  uint8_t* d_ff = nullptr;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_o, n_rays * 3 * sizeof(float))); CUDA_TRY(cudaMalloc(&d_d, n_rays * 3 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&d_t, n_rays * sizeof(double))); CUDA_TRY(cudaMalloc(&d_n, n_rays * 3 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_id, n_rays * sizeof(int32_t))); CUDA_TRY(cudaMalloc(&d_ff, n_rays));
+    CUDA_TRY(cudaMemcpy(d_o, o_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_d, d_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    uecrt::launch_primary_hits(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(t, d_t, n_rays * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(n_xyz, d_n, n_rays * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(id, d_id, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(front_face, d_ff, n_rays, cudaMemcpyDeviceToHost));
+    return UECRT_OK;
+  };
+  rc = body();
+  cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_n); cudaFree(d_id); cudaFree(d_ff);
+  ctx_free(c);
+  return rc;
+}
+
+int uecrt_scatter(uint64_t n, const uint32_t* mat_type, const uecrt_float4* mat_param, const float* d_in_xyz,
+                  const float* p_xyz, const float* normal_xyz, const uint8_t* front_face, const float* uniforms4,
+                  uint8_t* scattered, float* attenuation_rgb, float* o_out_xyz, float* d_out_xyz) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (n == 0) return UECRT_OK;
+  void* bufs[12] = {};
+  const size_t sz[12] = {n * 4, n * 16, n * 12, n * 12, n * 12, n, n * 16, n, n * 12, n * 12, n * 12, 0};
+  const void* src[7] = {mat_type, mat_param, d_in_xyz, p_xyz, normal_xyz, front_face, uniforms4};
+  auto body = [&]() -> int {
+    for (int i = 0; i < 11; ++i) CUDA_TRY(cudaMalloc(&bufs[i], sz[i]));
+    for (int i = 0; i < 7; ++i) CUDA_TRY(cudaMemcpy(bufs[i], src[i], sz[i], cudaMemcpyHostToDevice));
+    uecrt::launch_scatter(n, (const uint32_t*)bufs[0], (const float4*)bufs[1], (const float*)bufs[2], (const float*)bufs[3],
+                          (const float*)bufs[4], (const uint8_t*)bufs[5], (const float*)bufs[6], (uint8_t*)bufs[7],
+                          (float*)bufs[8], (float*)bufs[9], (float*)bufs[10], 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(scattered, bufs[7], sz[7], cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(attenuation_rgb, bufs[8], sz[8], cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(o_out_xyz, bufs[9], sz[9], cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(d_out_xyz, bufs[10], sz[10], cudaMemcpyDeviceToHost));
+    return UECRT_OK;
+  };
+  rc = body();
+  for (void* b : bufs) cudaFree(b);
+  return rc;
+}
+
+int uecrt_philox(uint64_t n, uint64_t seed, const uint32_t* counters4, uint32_t* out4) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (n == 0) return UECRT_OK;
+  uint32_t *d_c = nullptr, *d_o = nullptr;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_c, n * 16)); CUDA_TRY(cudaMalloc(&d_o, n * 16));
+    CUDA_TRY(cudaMemcpy(d_c, counters4, n * 16, cudaMemcpyHostToDevice));
+    uecrt::launch_philox(n, (uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32), d_c, d_o, 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out4, d_o, n * 16, cudaMemcpyDeviceToHost));
+    return UECRT_OK;
+  };
+  rc = body();
+  cudaFree(d_c); cudaFree(d_o);
+  return rc;
+}
+
+}  // extern "C"

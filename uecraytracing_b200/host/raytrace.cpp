@@ -1,0 +1,94 @@
+// raytrace.cpp -- the drop-in binary: same CLI contract as the reference's main()
+// (source.cpp:190-231): raytrace [-h] [-v] [-l N] [-o FILE | FILE]; no output -> help, exit 0;
+// stdout lines "rendering...", "rendering finished", "write to file : <f>", "success";
+// a failed write prints "error" and exits 1; an unknown option aborts (uncaught exception).
+// New, additive flags (north_star): --width --spp --depth --seed, plus --gpus --scene --dense-n
+// --exact-hits --dump-accum.  Defaults equal the reference's macros (400 / 100 / 50).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <random>
+#include <string>
+
+#include "cli_options.hpp"
+#include "png_writer.hpp"
+#include "yk/render.hpp"
+#include "yk/scenes.hpp"
+
+int main(int argc, char* argv[]) {
+  std::ios::sync_with_stdio(false);
+  std::cout.tie(nullptr);
+
+  uecrt_host::options options("raytrace", "raytracing program");
+  options.add('h', "help", "print usage", false)
+      .add('v', "verbose", "verbose output", false)
+      .add('o', "output", "filename of output", true)
+      .add('l', "verbose-level", "set verbose level", true)
+      .add(0, "width", "image width (default 400; height = width*9/16)", true)
+      .add(0, "spp", "samples per pixel (default 100)", true)
+      .add(0, "depth", "maximum bounce depth (default 50)", true)
+      .add(0, "seed", "Philox seed (default: random)", true)
+      .add(0, "gpus", "number of B200s to shard samples over (default 1)", true)
+      .add(0, "scene", "ref4 | ref4d | final | dense (default ref4)", true)
+      .add(0, "scene-seed", "seed of the random scene generator (default 1)", true)
+      .add(0, "dense-n", "sphere count of --scene dense (default 10000)", true)
+      .add(0, "exact-hits", "resolve every closest hit in FP64", false)
+      .add(0, "dump-accum", "also write the linear float accumulation buffer (raw W*H*4 f32)", true);
+  options.positional("output");
+  options.parse(argc, argv);
+  if (options.count("help") || !options.count("output")) {
+    std::cout << options.help() << std::endl;
+    std::exit(EXIT_SUCCESS);
+  }
+  if (options.count("verbose") && !yk::verbose) ++yk::verbose;
+  if (options.count("verbose-level")) yk::verbose = options.as<std::uint32_t>("verbose-level");
+
+  const std::string filename = options.last("output");
+
+  yk::render_config cfg;
+  if (options.count("width")) cfg.width = options.as<std::uint32_t>("width");
+  if (options.count("spp")) cfg.spp = options.as<std::uint32_t>("spp");
+  if (options.count("depth")) cfg.max_depth = options.as<std::uint32_t>("depth");
+  cfg.seed = options.count("seed") ? options.as<std::uint64_t>("seed")
+                                   : (std::uint64_t(std::random_device{}()) << 32) ^ std::random_device{}();   // source.cpp:159
+  if (options.count("gpus")) cfg.gpus = options.as<int>("gpus");
+  cfg.exact_hits = options.count("exact-hits") != 0;
+  const std::string scene = options.count("scene") ? options.last("scene") : "ref4";
+  const std::uint32_t scene_seed = options.count("scene-seed") ? options.as<std::uint32_t>("scene-seed") : 1u;
+  const std::uint32_t dense_n = options.count("dense-n") ? options.as<std::uint32_t>("dense-n") : 10000u;
+
+  yk::hittable_list<double> world;
+  yk::camera<double> cam;
+  if (scene == "ref4") { world = yk::scenes::reference_scene(); cam = yk::scenes::reference_camera(); }
+  else if (scene == "ref4d") { world = yk::scenes::reference_scene_dielectric(); cam = yk::scenes::reference_camera(); }
+  else if (scene == "final") { world = yk::scenes::final_scene(scene_seed); cam = yk::scenes::final_camera(); }
+  else if (scene == "dense") { world = yk::scenes::dense_scene(dense_n, scene_seed); cam = yk::scenes::dense_camera(); }
+  else { std::cout << "unknown scene : " << scene << std::endl; std::exit(EXIT_FAILURE); }
+
+  // rendering
+  const bool dump = options.count("dump-accum") != 0;
+  yk::image_t image;
+  try {
+    image = yk::render(world, cam, cfg, dump);
+  } catch (const std::exception& e) {
+    std::cout << "error" << std::endl;
+    std::cerr << e.what() << std::endl;
+    std::exit(EXIT_FAILURE);
+  }
+
+  std::cout << "write to file : " << filename << std::endl;
+  if (!uecrt_host::write_png(filename.c_str(), (int)image.width, (int)image.height, 3, image.data(), (int)(3 * image.width))) {
+    std::cout << "error" << std::endl;
+    std::exit(EXIT_FAILURE);
+  }
+  if (dump) {
+    std::FILE* f = std::fopen(options.last("dump-accum").c_str(), "wb");
+    if (!f || std::fwrite(image.accum.data(), sizeof(float), image.accum.size(), f) != image.accum.size()) {
+      std::cout << "error" << std::endl;
+      std::exit(EXIT_FAILURE);
+    }
+    std::fclose(f);
+  }
+  std::cout << "success" << std::endl;
+}

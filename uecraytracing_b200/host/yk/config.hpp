@@ -1,0 +1,6 @@
+// yk/config.hpp -- the reference's global verbosity switch (yk/config.hpp:28-30).
+#pragma once
+#include <cstdint>
+namespace yk {
+inline std::uint32_t verbose = 0;
+}

@@ -1,0 +1,81 @@
+// yk/render.hpp -- re-hosted yk::render() (source.cpp:98-178).  Same role and the same four
+// progress lines; the pixel x spp loop, ray_color, hit and scatter run in libuecrt.so (K1-K3).
+// Width / spp / depth default to the reference's compile-time macros YK_IMAGE_WIDTH / YK_SPP /
+// YK_MAX_DEPTH (source.cpp:43-53) and become runtime values, so image_t is a heap vector
+// instead of a stack std::array (source.cpp:70-71 overflows the stack at 3840x2160).
+#pragma once
+#include <cstdint>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/uecrt.h"
+#include "camera.hpp"
+#include "color.hpp"
+#include "config.hpp"
+#include "hittable_list.hpp"
+
+#ifndef YK_IMAGE_WIDTH
+#define YK_IMAGE_WIDTH 400
+#endif
+#ifndef YK_SPP
+#define YK_SPP 100
+#endif
+#ifndef YK_MAX_DEPTH
+#define YK_MAX_DEPTH 50
+#endif
+
+namespace yk {
+
+namespace constants {
+constexpr double aspect_ratio = 16.0 / 9.0;                      // source.cpp:57
+constexpr std::uint32_t image_width = YK_IMAGE_WIDTH;
+constexpr std::uint32_t samples_per_pixel = YK_SPP;
+constexpr std::uint32_t max_depth = YK_MAX_DEPTH;
+constexpr std::uint32_t height_for(std::uint32_t width) { return static_cast<std::uint32_t>(width / aspect_ratio); }  // source.cpp:59-62
+}  // namespace constants
+
+struct render_config {
+  std::uint32_t width = constants::image_width;
+  std::uint32_t spp = constants::samples_per_pixel;
+  std::uint32_t max_depth = constants::max_depth;
+  std::uint64_t seed = 0;
+  int gpus = 1;
+  bool exact_hits = false;
+};
+
+struct image_t {
+  std::uint32_t width = 0, height = 0;
+  std::vector<color3b> pixels;          // row-major, top row first (source.cpp:170-171)
+  std::vector<float> accum;             // optional W*H*4 linear sums
+  uecrt_stats stats{};
+  const std::uint8_t* data() const { return reinterpret_cast<const std::uint8_t*>(pixels.data()); }
+};
+
+inline image_t render(const hittable_list<double>& world, const camera<double>& cam, const render_config& cfg, bool keep_accum = false) {
+  image_t img;
+  img.width = cfg.width;
+  img.height = constants::height_for(cfg.width);
+  img.pixels.resize((std::size_t)img.width * img.height);
+  if (keep_accum) img.accum.resize((std::size_t)img.width * img.height * 4);
+  std::cout << "rendering..." << std::endl;                      // source.cpp:114
+  const uecrt_scene sc = world.flatten();
+  const uecrt_camera c = cam.flatten();
+  uecrt_params p{};
+  p.width = img.width; p.height = img.height; p.spp = cfg.spp; p.max_depth = cfg.max_depth;
+  p.seed = cfg.seed; p.num_gpus = cfg.gpus; p.flags = cfg.exact_hits ? UECRT_FLAG_EXACT_HITS : 0;
+  static_assert(sizeof(color3b) == 3, "color3b must be 3 packed bytes");
+  if (uecrt_render(&sc, &c, &p, reinterpret_cast<std::uint8_t*>(img.pixels.data()), keep_accum ? img.accum.data() : nullptr, &img.stats) != UECRT_OK)
+    throw std::runtime_error(std::string("uecrt_render: ") + uecrt_last_error());
+  if (verbose) {
+    const double samples = (double)img.width * img.height * cfg.spp;
+    std::cout << "K1 render_paths " << img.stats.kernel_ms << " ms, reduce " << img.stats.reduce_ms << " ms, K3 resolve "
+              << img.stats.resolve_ms << " ms; " << samples / (img.stats.kernel_ms * 1e-3) << " samples/s; rays "
+              << img.stats.rays_traced << ", sphere tests " << img.stats.sphere_tests << std::endl;
+  }
+  std::cout << "rendering finished" << std::endl;                 // source.cpp:175
+  return img;
+}
+
+}  // namespace yk
