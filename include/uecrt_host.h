@@ -31,6 +31,9 @@ uint32_t uecrt_host_image_height(uint32_t width);
  * stbi_write_png).  Returns 0 on success. */
 int uecrt_host_write_png(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb);
 
+/* Philox4x32-10 on the host (same code as the device, csrc/philox.cuh), for known-answer tests */
+void uecrt_host_philox(uint64_t seed, const uint32_t counter[4], uint32_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif

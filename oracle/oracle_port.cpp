@@ -161,10 +161,13 @@ inline V3 random_unit_vector(Rng& g) {
   v.z = g.uniform(-1, 1);
   return divs(v, length(v));                     // vec3.hpp:131 normalize(): *this /= length()
 }
-// material.hpp:27-31 (unused upstream; the fuzz extension uses its distribution)
+// material.hpp:27-31 (never called upstream; the fuzz extension uses its distribution).  Upstream
+// writes normalize(random) * dist(gen): both operands draw, in an order C++ leaves unspecified;
+// fixed here (and in ref_harness.cpp) as direction x,y,z first, then the radius.
 inline V3 random_in_unit_sphere(Rng& g) {
   V3 v = random_unit_vector(g);
-  return mul(v, g.uniform(0.01, 0.99));
+  double radius = g.uniform(0.01, 0.99);
+  return mul(v, radius);
 }
 
 // [EXTERNAL, RTIOW book; SURVEY.md App. D] -- not in the reference

@@ -78,7 +78,12 @@ std::optional<std::pair<C, R>> scatter_one(const mat_desc& m, const R& r_in, con
     case UECRT_MAT_METAL: {
       if (!(m.param > 0)) return yk::metal<double>(m.albedo).scatter(r_in, rec, gen);  // upstream code
       V reflected = yk::reflect(r_in.direction.normalized(), rec.normal);
-      reflected = reflected + yk::random_in_unit_sphere<double>(gen) * m.param;
+      // same distribution as the upstream helper random_in_unit_sphere (material.hpp:27-31), which is
+      // never called upstream and whose two operands of `*` both draw from gen (evaluation order
+      // unspecified in C++): the order is fixed here as direction (x,y,z) first, then the radius.
+      V unit = yk::random_unit_vector<double>(gen);
+      double radius = yk::uniform_real_distribution<double>(0.01, 0.99)(gen);
+      reflected = reflected + (unit * radius) * m.param;
       auto scattered = yk::ray(rec.p, reflected);
       if (yk::dot(scattered.direction, rec.normal) > 0) return std::make_pair(m.albedo, scattered);
       return std::nullopt;

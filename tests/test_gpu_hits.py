@@ -1,0 +1,124 @@
+"""-m gpu: closest-hit parity of the CUDA path (K2, the same scan + resolve K1 runs) against the
+oracle on identical rays.  north_star's bar: indices bit-exact, floats <= 1e-5 relative; the
+FP64-resolved path is held to 1e-12 here.  The FP32 fast path (K1's default) is reported against
+the same rays with its own, looser, stated tolerance."""
+import numpy as np
+import pytest
+
+from conftest import golden, primary_rays, unhex
+
+pytestmark = pytest.mark.gpu
+
+T_REL_EXACT = 1e-12    # FP64 resolve follows the reference's operation order
+T_REL_BAR = 1e-5       # north_star tolerance
+
+
+def _check_exact(got, want, what):
+    t, n, i, f = got
+    to, no, io, fo = want
+    assert np.array_equal(i, io), f"{what}: {(i != io).sum()} index mismatches"
+    assert np.array_equal(f, fo), f"{what}: front_face mismatches"
+    hit = io >= 0
+    assert np.all(t[~hit] == -1)
+    if hit.any():
+        rel = np.abs(t[hit] - to[hit]) / np.abs(to[hit])
+        assert rel.max() <= T_REL_EXACT, f"{what}: t rel err {rel.max():.3e}"
+        assert np.abs(n[hit] - no[hit]).max() <= 1e-9, what
+
+
+@pytest.mark.parametrize("name,cam,W", [("ref4", "ref", 400), ("ref4d", "ref", 400), ("final", "final", 1200)])
+def test_primary_rays_exact(u, oracle, name, cam, W):
+    """Every primary (pixel-centre) ray of BASELINE configs 0 and 1."""
+    sc, c = u.Scene.named(name, seed=1), u.Camera.named(cam)
+    o, d = primary_rays(c, W, u.image_height(W))
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, name)
+    assert (want[2] >= 0).mean() > 0.5
+
+
+def test_primary_rays_exact_dense_10k(u, oracle):
+    """Config 3's 10k-sphere scene (160 KB of packed geometry in shared memory), sampled rays."""
+    sc, c = u.Scene.named("dense", seed=1, n=10000), u.Camera.named("dense")
+    o, d = primary_rays(c, 1920, 1080)
+    pick = np.random.default_rng(3).choice(len(o), 60000, replace=False)
+    o, d = o[pick], d[pick]
+    _check_exact(u.primary_hits(sc, o, d, exact=True), oracle.hits(sc, o.astype(np.float64), d.astype(np.float64)), "dense")
+
+
+@pytest.mark.parametrize("name,span", [("ref4", 3.0), ("final", 14.0)])
+def test_random_rays_exact_and_golden(u, oracle, name, span):
+    sc = u.Scene.named(name, seed=1)
+    g = golden("random_ray_hits.json")[name]
+    o = np.array(g["o"], np.float32).reshape(-1, 3); d = np.array(g["d"], np.float32).reshape(-1, 3)
+    want = (unhex(g["t"]), unhex(g["n"], (-1, 3)), np.array(g["id"], np.int32), np.array(g["ff"], np.uint8))
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, name + " golden")
+    rng = np.random.default_rng(11)
+    o = rng.uniform(-span, span, (200000, 3)).astype(np.float32)
+    d = (rng.normal(size=(200000, 3)) * rng.uniform(0.05, 5, (200000, 1))).astype(np.float32)
+    _check_exact(u.primary_hits(sc, o, d, exact=True), oracle.hits(sc, o.astype(np.float64), d.astype(np.float64)), name)
+
+
+def test_secondary_rays_from_surfaces_exact(u, oracle):
+    """Bounce-like rays: origins ON sphere surfaces (incl. the r=1000 ground), random directions."""
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    o, d = primary_rays(c, 400, 225)
+    t, n, i, f = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    hit = i >= 0
+    p = (o[hit].astype(np.float64) + d[hit].astype(np.float64) * t[hit][:, None]).astype(np.float32)
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=p.shape); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    d2 = (n[hit] + v).astype(np.float32)                         # lambertian-style, unnormalised
+    want = oracle.hits(sc, p.astype(np.float64), d2.astype(np.float64))
+    _check_exact(u.primary_hits(sc, p, d2, exact=True), want, "secondary")
+    assert (want[2] >= 0).mean() > 0.2
+
+
+def test_edge_cases_golden(u):
+    for c in golden("hit_edge_cases.json")["cases"]:
+        g = np.array(c["spheres"], np.float32)
+        sc = u.Scene(g, np.zeros(len(g), np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (len(g), 1)))
+        tmax = float("inf") if c["tmax"] == "inf" else float.fromhex(c["tmax"])
+        for exact in (True, False):
+            t, n, i, f = u.primary_hits(sc, [c["o"]], [c["d"]], float.fromhex(c["tmin"]), tmax, exact=exact)
+            if not exact and "just above" in c["name"]:
+                continue                                       # a 1e-7 margin is below FP32 resolution
+            assert int(i[0]) == c["id"], (c["name"], exact)
+            if c["id"] >= 0:
+                assert int(f[0]) == c["ff"], (c["name"], exact)
+                tol = T_REL_EXACT if exact else 1e-5
+                assert abs(t[0] - unhex(c["t"])[0]) <= tol * abs(unhex(c["t"])[0]), (c["name"], exact)
+                assert np.abs(n.ravel() - unhex(c["n"])).max() <= (1e-12 if exact else 1e-5), (c["name"], exact)
+
+
+def test_empty_ragged_and_interval(u, oracle):
+    cam = u.Camera.named("ref")
+    o, d = primary_rays(cam, 40, 22)
+    empty = u.Scene(np.zeros((0, 4)), np.zeros(0), np.zeros((0, 4)))
+    t, n, i, f = u.primary_hits(empty, o, d)
+    assert np.all(i == -1) and np.all(t == -1)
+    one = u.Scene(np.array([[0, 0, -1, .5]]), [0], [[.5, .5, .5, 0]])        # odd count -> padded pair
+    for k in (1, 31, 33, 127, 129):
+        _check_exact(u.primary_hits(one, o[:k], d[:k]), oracle.hits(one, o[:k].astype(np.float64), d[:k].astype(np.float64)), f"n_rays={k}")
+    t, n, i, f = u.primary_hits(one, o[:0], d[:0])
+    assert len(t) == 0
+    sc = u.Scene.named("final", seed=1)
+    o, d = primary_rays(u.Camera.named("final"), 200, 112)
+    for tmin, tmax in ((0.001, 1.2), (1.0, 1.5), (0.5, float("inf"))):
+        _check_exact(u.primary_hits(sc, o, d, tmin, tmax), oracle.hits(sc, o.astype(np.float64), d.astype(np.float64), tmin, tmax), f"[{tmin},{tmax}]")
+    with pytest.raises(u.UecrtError):
+        u.primary_hits(u.Scene(np.zeros((70000, 4)), np.zeros(70000), np.zeros((70000, 4))), o, d)
+
+
+@pytest.mark.parametrize("name,cam,W", [("ref4", "ref", 400), ("final", "final", 1200)])
+def test_fast_path_statistics(u, oracle, name, cam, W):
+    """K1's default FP32 resolve on the same rays: not bit-exact by design; stated tolerance."""
+    sc, c = u.Scene.named(name, seed=1), u.Camera.named(cam)
+    o, d = primary_rays(c, W, u.image_height(W))
+    to, no, io, fo = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    t, n, i, f = u.primary_hits(sc, o, d, exact=False)
+    assert (i != io).mean() <= 2e-4, f"{(i != io).sum()} of {len(i)} indices differ"
+    both = (io >= 0) & (i == io)
+    rel = np.abs(t[both] - to[both]) / np.abs(to[both])
+    assert np.percentile(rel, 99) <= 1e-4 and rel.max() <= 5e-3
+    assert np.percentile(np.abs(n[both] - no[both]).max(axis=1), 99) <= 1e-4
+    assert (f[both] != fo[both]).mean() <= 1e-4

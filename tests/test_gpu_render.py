@@ -1,0 +1,152 @@
+"""-m gpu: image-level parity of K1 + K3 against the oracle.  The RNG streams differ (Philox vs the
+reference's per-sample mt19937), so images are compared statistically, against the oracle's own
+seed-to-seed noise floor, plus exact structural properties that hold at any size."""
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import golden, psnr8
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,cam,W,spp", [("ref4", "ref", 200, 64), ("ref4d", "ref", 160, 32), ("final", "final", 240, 48)])
+def test_render_matches_oracle_at_noise_floor(u, oracle, name, cam, W, spp):
+    """PSNR(gpu, oracle) must be within 0.5 dB of PSNR(oracle seed A, oracle seed B) at the same spp,
+    and the linear image means must agree to 0.5%."""
+    sc, c = u.Scene.named(name, seed=1), u.Camera.named(cam)
+    H = u.image_height(W)
+    rgb, acc, st = u.render(sc, c, W, spp, 50, seed=7, return_accum=True)
+    a, rays_a = oracle.render(sc, c, W, H, spp, 50, 1)
+    b, _ = oracle.render(sc, c, W, H, spp, 50, 1000003)
+    a8, b8 = oracle.to_color3b(a, spp), oracle.to_color3b(b, spp)
+    floor = psnr8(a8, b8)
+    got = min(psnr8(rgb, a8), psnr8(rgb, b8))
+    assert got >= floor - 0.5, f"{name}: gpu-vs-oracle {got:.2f} dB, oracle-vs-oracle floor {floor:.2f} dB"
+    lin = acc[..., :3] / spp
+    floor_lin = np.mean((a / spp - b / spp) ** 2)
+    assert np.mean((lin - a / spp) ** 2) <= 1.15 * floor_lin
+    assert abs(lin.mean() - (a.mean() + b.mean()) / (2 * spp)) <= 0.005 * a.mean() / spp
+    assert abs(st["rays_traced"] / (W * H * spp) - rays_a / (W * H * spp)) < 0.02
+    assert st["paths"] == W * H * spp and st["sphere_tests"] == st["rays_traced"] * sc.n
+
+
+@pytest.mark.parametrize("name", ["ref4", "final"])
+def test_converged_against_committed_oracle_image(u, name):
+    """The committed 2048-spp oracle image (tests/golden/converged_*.json, made from the reference
+    headers).  With N_gpu = N_oracle the expected MSE is the MSE between the oracle's two halves / 2;
+    a systematic error larger than ~30% of that noise fails."""
+    g = golden(f"converged_{name}_64.json")
+    W, H, N = g["w"], g["h"], g["spp_total"]
+    want = np.array(g["mean_rgb_f32"], np.float32).reshape(H, W, 3)
+    sc, c = u.Scene.named(name, seed=1), u.Camera.named(g["camera"])
+    rgb, acc, st = u.render(sc, c, W, N, g["depth"], seed=99, return_accum=True)
+    lin = acc[..., :3] / N
+    expected = g["mse_between_halves"] / 2
+    mse = float(np.mean((lin - want) ** 2))
+    assert mse <= 1.3 * expected, f"{name}: mse {mse:.3e} vs expected noise {expected:.3e}"
+    psnr_lin = 10 * np.log10(1.0 / mse)
+    assert psnr_lin >= 40.0 or name == "final", psnr_lin
+    assert abs(lin.mean() / want.mean() - 1) < 0.003
+    assert abs(st["rays_traced"] / (W * H * N) - g["rays_per_sample"]) < 0.01
+
+
+def test_resolve_matches_to_color3b(u, oracle):
+    """K3 == to_color3b (source.cpp:73-83) on the very sums K1 produced, plus the clamp / zero cases."""
+    sc, c = u.Scene.named("ref4"), u.Camera.named("ref")
+    rgb, acc, _ = u.render(sc, c, 160, 16, 50, seed=3, return_accum=True)
+    want = oracle.to_color3b(acc[..., :3].astype(np.float64), 16)
+    assert (rgb != want).mean() <= 1e-5
+    assert np.abs(rgb.astype(int) - want.astype(int)).max() <= 1
+    assert rgb.max() <= 255 and rgb[0].min() > 100          # top row is sky
+
+
+def test_sample_shards_add_up(u):
+    """spp-sharding invariant: Philox counters use the GLOBAL sample id, so rendering
+    [0,S) equals the sum of any partition of it, up to FP32 summation order."""
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    W, S = 128, 24
+    _, full, _ = u.render(sc, c, W, S, 50, seed=5, return_accum=True)
+    parts = np.zeros_like(full)
+    for lo, n in ((0, 5), (5, 3), (8, 16)):
+        _, a, _ = u.render(sc, c, W, S, 50, seed=5, return_accum=True, sample_begin=lo, sample_count=n)
+        assert np.all(a[..., 3] == n)
+        parts += a
+    assert np.all(full[..., 3] == S)
+    np.testing.assert_allclose(parts[..., :3], full[..., :3], rtol=2e-5, atol=1e-5)
+    _, other, _ = u.render(sc, c, W, S, 50, seed=6, return_accum=True)
+    assert np.abs(other[..., :3] - full[..., :3]).mean() > 1e-3     # a different seed is a different image
+
+
+def test_depth_semantics(u):
+    """raytracer.hpp:26: depth 0 -> black.  With max_depth 1 a hit's scattered ray gets depth 0, so
+    the image is sky where primary rays miss and black elsewhere."""
+    sc, c = u.Scene.named("ref4"), u.Camera.named("ref")
+    W, H, S = 64, 36, 8
+    _, acc, st = u.render(sc, c, W, S, 1, seed=1, return_accum=True)
+    assert st["rays_traced"] == W * H * S
+    lin = acc[..., :3] / S
+    assert np.all(lin[H // 2, W // 2] == 0)                  # centre pixel hits sphere 0 on every sample
+    t = lin[0, :, 2]
+    assert np.all(t == 1.0)                                   # sky: blue channel is (1-t)+t = 1 exactly
+    assert np.all((lin[0, :, 0] >= 0.5) & (lin[0, :, 0] <= 1.0))
+    _, acc0, st0 = u.render(sc, c, W, S, 0, seed=1, return_accum=True)
+    assert st0["rays_traced"] == 0 and np.all(acc0[..., :3] == 0) and np.all(acc0[..., 3] == S)
+
+
+def test_exact_hits_flag_is_statistically_identical(u):
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    a8, a, _ = u.render(sc, c, 200, 32, 50, seed=11, return_accum=True)
+    b8, b, _ = u.render(sc, c, 200, 32, 50, seed=11, return_accum=True, exact=True)
+    # same Philox streams: paths differ only where FP32 and FP64 resolve pick different spheres
+    same = np.isclose(a[..., :3], b[..., :3], rtol=1e-3, atol=1e-3).all(axis=-1).mean()
+    assert same > 0.90, same
+    assert abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
+
+
+def test_full_size_config1_properties(u):
+    """BASELINE configs[1] at full size (1200x675, 500 spp, depth 50): size-independent properties."""
+    g = golden("converged_final_64.json")
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    rgb, acc, st = u.render(sc, c, 1200, 500, 50, seed=2026, return_accum=True)
+    assert rgb.shape == (675, 1200, 3)
+    assert np.all(acc[..., 3] == 500)                                          # every pixel got every sample once
+    assert st["paths"] == 1200 * 675 * 500
+    assert abs(st["rays_traced"] / st["paths"] - g["rays_per_sample"]) < 0.01
+    assert np.isfinite(acc).all() and acc[..., :3].min() >= 0
+    want = np.array(g["mean_rgb_f32"], np.float32).reshape(g["h"], g["w"], 3)
+    assert abs(acc[..., :3].mean() / 500 / want.mean() - 1) < 0.01
+    assert rgb[:40].mean() > 200                                               # sky at the top
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")), reason="binary not built")
+def test_cli_renders_reference_default(u, oracle, tmp_path):
+    """The drop-in binary at the reference's defaults (400x225, 100 spp, depth 50; source.cpp:43-53)."""
+    out = tmp_path / "image.png"
+    r = subprocess.run([os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace"), str(out), "--seed", "5"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split("\n")[:4] == ["rendering...", "rendering finished", f"write to file : {out}", "success"]
+    raw = out.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n" and int.from_bytes(raw[16:20], "big") == 400 and int.from_bytes(raw[20:24], "big") == 225
+    n = int.from_bytes(raw[33:37], "big")
+    img = np.frombuffer(zlib.decompress(raw[41:41 + n]), np.uint8).reshape(225, 1 + 1200)[:, 1:].reshape(225, 400, 3)
+    rgb, _, _ = u.render(u.Scene.named("ref4"), u.Camera.named("ref"), 400, 100, 50, seed=5)
+    assert psnr8(img, rgb) > 45          # same seed through the CLI and the API: equal up to FP32 sum order
+    a, _ = oracle.render(u.Scene.named("ref4"), u.Camera.named("ref"), 400, 225, 25, 50, 1)
+    assert psnr8(img, oracle.to_color3b(a, 25)) > 30
+
+
+def test_multi_gpu_single_process(u):
+    if u.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    _, a, _ = u.render(sc, c, 256, 32, 50, seed=4, return_accum=True, gpus=1)
+    _, b, st = u.render(sc, c, 256, 32, 50, seed=4, return_accum=True, gpus=2)
+    assert np.all(b[..., 3] == 32)
+    np.testing.assert_allclose(a[..., :3], b[..., :3], rtol=2e-5, atol=1e-5)
+    assert st["reduce_ms"] > 0

@@ -43,7 +43,7 @@ EXPORTS = [
     "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_primary_hits", "uecrt_scatter",
     "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_accumulate_device", "uecrt_resolve_device",
     "uecrt_ctx_stats", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
-    "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png",
+    "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox",
 ]
 
 
@@ -74,6 +74,8 @@ def _load():
     L.uecrt_host_image_height.argtypes = [u32]
     L.uecrt_host_image_height.restype = u32
     L.uecrt_host_write_png.argtypes = [C.c_char_p, u32, u32, vp]
+    L.uecrt_host_philox.argtypes = [u64, vp, vp]
+    L.uecrt_host_philox.restype = None
     for name in ("uecrt_render", "uecrt_primary_hits", "uecrt_scatter", "uecrt_philox", "uecrt_ctx_create",
                  "uecrt_accumulate_device", "uecrt_resolve_device", "uecrt_ctx_stats", "uecrt_host_scene_fill",
                  "uecrt_host_camera", "uecrt_host_camera_lookat", "uecrt_host_write_png"):

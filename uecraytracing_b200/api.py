@@ -167,3 +167,10 @@ def write_png(path, rgb):
     rgb = np.ascontiguousarray(rgb, np.uint8)
     h, w, _ = rgb.shape
     check(lib.uecrt_host_write_png(str(path).encode(), w, h, _ptr(rgb)), "uecrt_host_write_png")
+
+
+def philox_host(seed, counter4):
+    """Philox4x32-10 block computed by the host build of csrc/philox.cuh (no GPU needed)."""
+    c = (C.c_uint32 * 4)(*[int(x) for x in counter4]); out = (C.c_uint32 * 4)()
+    lib.uecrt_host_philox(seed, c, out)
+    return [int(x) for x in out]

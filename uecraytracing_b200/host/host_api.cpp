@@ -3,6 +3,7 @@
 #include <string>
 
 #include "../../include/uecrt_host.h"
+#include "../csrc/philox.cuh"
 #include "png_writer.hpp"
 #include "yk/render.hpp"
 #include "yk/scenes.hpp"
@@ -50,6 +51,10 @@ int uecrt_host_camera_lookat(const double from[3], const double at[3], const dou
   *out = yk::camera<double>(P(from[0], from[1], from[2]), P(at[0], at[1], at[2]), yk::vec3<double>(vup[0], vup[1], vup[2]),
                             vfov_deg, aspect, aperture, focus_dist).flatten();
   return UECRT_OK;
+}
+void uecrt_host_philox(uint64_t seed, const uint32_t c[4], uint32_t out[4]) {
+  const philox_out r = philox4x32_10(c[0], c[1], c[2], c[3], (uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32));
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 uint32_t uecrt_host_image_height(uint32_t width) { return yk::constants::height_for(width); }
 int uecrt_host_write_png(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb) {
