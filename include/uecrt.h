@@ -103,6 +103,9 @@ int uecrt_device_count(void);
 int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_params* params,
                  uint8_t* rgb_out, float* accum_out_or_null, uecrt_stats* stats_or_null);
 
+/* Frees the per-device workspaces (stream, events, buffers) uecrt_render caches between calls. */
+void uecrt_release(void);
+
 /* uecrt_primary_hits replaces hittable_list::hit_impl (hittable_list.hpp:32-58) on caller
  * rays: closest hit in the CLOSED interval [t_min, t_max], later index wins ties.
  * o_xyz/d_xyz: n_rays*3 floats (direction need not be unit; t is in units of |d| as in

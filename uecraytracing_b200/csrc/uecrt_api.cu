@@ -108,6 +108,9 @@ struct uecrt_ctx {
   int last_blocks = 0;
   size_t smem = 0;
   uint32_t n = 0;
+  size_t cap_pairs = 0;    // bytes allocated for d_pairs
+  uint32_t cap_n = 0;      // spheres allocated for geom / materials
+  bool configured = false;
 };
 
 namespace {
@@ -119,10 +122,19 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
   if (smem_need > 232448)
     return fail(UECRT_ERR_INVALID, "scene of %u spheres needs %zu B of shared memory per CTA (max 232448)", scene->n, smem_need);
   const uint32_t n_alloc = std::max<uint32_t>(scene->n, 1);
-  CUDA_TRY(cudaMalloc(&c->d_pairs, pair_bytes));
-  CUDA_TRY(cudaMalloc(&c->d_geom, (size_t)n_alloc * sizeof(uecrt_float4)));
-  CUDA_TRY(cudaMalloc(&c->d_mat_type, (size_t)n_alloc * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&c->d_mat_param, (size_t)n_alloc * sizeof(uecrt_float4)));
+  if (pair_bytes > c->cap_pairs) {             // grow-only: a reused context re-uploads without cudaMalloc
+    cudaFree(c->d_pairs); c->d_pairs = nullptr; c->cap_pairs = 0;
+    CUDA_TRY(cudaMalloc(&c->d_pairs, pair_bytes));
+    c->cap_pairs = pair_bytes;
+  }
+  if (n_alloc > c->cap_n) {
+    cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param);
+    c->d_geom = c->d_mat_type = c->d_mat_param = nullptr; c->cap_n = 0;
+    CUDA_TRY(cudaMalloc(&c->d_geom, (size_t)n_alloc * sizeof(uecrt_float4)));
+    CUDA_TRY(cudaMalloc(&c->d_mat_type, (size_t)n_alloc * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c->d_mat_param, (size_t)n_alloc * sizeof(uecrt_float4)));
+    c->cap_n = n_alloc;
+  }
   CUDA_TRY(cudaMemcpy(c->d_pairs, ps.pairs.data(), pair_bytes, cudaMemcpyHostToDevice));
   if (scene->n) {
     CUDA_TRY(cudaMemcpy(c->d_geom, scene->geom, (size_t)scene->n * sizeof(uecrt_float4), cudaMemcpyHostToDevice));
@@ -152,14 +164,11 @@ void ctx_free(uecrt_ctx* c) {
   delete c;
 }
 
-int ctx_create_on_current_device(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ctx** out) {
-  int rc = require_device();
+// (re)load a scene + camera into a context on the current device; buffers are reused when they fit
+int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* cam) {
+  int rc = validate_scene(scene);
   if (rc) return rc;
-  if ((rc = validate_scene(scene))) return rc;
-  uecrt_ctx* c = new uecrt_ctx();
-  cudaGetDevice(&c->device);
-  rc = ctx_upload_scene(c, scene);
-  if (rc) { ctx_free(c); return rc; }
+  if ((rc = ctx_upload_scene(c, scene))) return rc;
   if (cam) {
     for (int i = 0; i < 3; ++i) {
       c->cam.origin[i] = cam->origin[i]; c->cam.ll[i] = cam->lower_left[i]; c->cam.hor[i] = cam->horizontal[i];
@@ -169,18 +178,87 @@ int ctx_create_on_current_device(const uecrt_scene* scene, const uecrt_camera* c
     c->cam.origin_is_zero = (cam->origin[0] == 0.f && cam->origin[1] == 0.f && cam->origin[2] == 0.f) ? 1 : 0;
   }
   cudaError_t e;
-  if ((e = cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-      (e = uecrt::configure_kernels(&c->regs, &c->blocks_per_sm, c->smem)) != cudaSuccess) {
-    ctx_free(c);
-    return fail(UECRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+  if (!c->configured) {
+    if ((e = cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess)
+      return fail(UECRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, c->device);
+    c->configured = true;
   }
-  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
-  cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, c->device);
-  if (c->blocks_per_sm < 1) { ctx_free(c); return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem); }
+  if ((e = uecrt::configure_kernels(&c->regs, &c->blocks_per_sm, c->smem)) != cudaSuccess)
+    return fail(UECRT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e));
+  if (c->blocks_per_sm < 1) return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem);
+  c->timed = false;
+  return UECRT_OK;
+}
+
+int ctx_create_on_current_device(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ctx** out) {
+  int rc = require_device();
+  if (rc) return rc;
+  uecrt_ctx* c = new uecrt_ctx();
+  cudaGetDevice(&c->device);
+  rc = ctx_set_scene(c, scene, cam);
+  if (rc) { ctx_free(c); return rc; }
   *out = c;
   return UECRT_OK;
+}
+
+// ---- per-device workspace of the host-buffer entry point uecrt_render: stream, events, the
+// accumulation / RGB buffers and a scene context are created once per process and reused, so a
+// frame costs the scene H2D, K1 (+ reduce), K3 and the D2H -- no cudaMalloc/cudaFree per call.
+struct Workspace {
+  int device = -1;
+  uecrt_ctx* ctx = nullptr;
+  cudaStream_t st = nullptr;
+  float* accum = nullptr; size_t accum_cap = 0;
+  uint8_t* rgb = nullptr; size_t rgb_cap = 0;
+  cudaEvent_t r0 = nullptr, r1 = nullptr, e0 = nullptr, e1 = nullptr, e2 = nullptr;
+};
+std::mutex g_ws_mutex;
+std::vector<Workspace*> g_ws;
+
+int get_workspace(int dev, size_t accum_bytes, size_t rgb_bytes, Workspace** out) {
+  Workspace* w = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    for (Workspace* x : g_ws) if (x->device == dev) w = x;
+    if (!w) { w = new Workspace(); w->device = dev; g_ws.push_back(w); }
+  }
+  CUDA_TRY(cudaSetDevice(dev));
+  if (!w->st) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&w->r0)); CUDA_TRY(cudaEventCreate(&w->r1));
+    CUDA_TRY(cudaEventCreate(&w->e0)); CUDA_TRY(cudaEventCreate(&w->e1)); CUDA_TRY(cudaEventCreate(&w->e2));
+  }
+  if (!w->ctx) { w->ctx = new uecrt_ctx(); w->ctx->device = dev; }
+  if (accum_bytes > w->accum_cap) {
+    cudaFree(w->accum); w->accum = nullptr; w->accum_cap = 0;
+    CUDA_TRY(cudaMalloc(&w->accum, accum_bytes)); w->accum_cap = accum_bytes;
+  }
+  if (rgb_bytes > w->rgb_cap) {
+    cudaFree(w->rgb); w->rgb = nullptr; w->rgb_cap = 0;
+    CUDA_TRY(cudaMalloc(&w->rgb, rgb_bytes)); w->rgb_cap = rgb_bytes;
+  }
+  *out = w;
+  return UECRT_OK;
+}
+
+void release_workspaces() {
+  std::lock_guard<std::mutex> lk(g_ws_mutex);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (Workspace* w : g_ws) {
+    cudaSetDevice(w->device);
+    if (w->st) { cudaStreamSynchronize(w->st); cudaStreamDestroy(w->st); }
+    cudaFree(w->accum); cudaFree(w->rgb);
+    for (cudaEvent_t e : {w->r0, w->r1, w->e0, w->e1, w->e2}) if (e) cudaEventDestroy(e);
+    if (w->ctx) ctx_free(w->ctx);
+    delete w;
+  }
+  g_ws.clear();
+  cudaSetDevice(prev);
 }
 
 int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream_t st) {
@@ -332,10 +410,14 @@ int uecrt_ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) { return ctx_stats(ctx, ou
 
 int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_params* params, uint8_t* rgb_out,
                  float* accum_out_or_null, uecrt_stats* stats_or_null) {
+  static std::mutex render_mutex;                 // one frame at a time per process
+  std::lock_guard<std::mutex> render_lock(render_mutex);
   int rc = require_device();
   if (rc) return rc;
   if (!scene || !cam || !params || !rgb_out) return fail(UECRT_ERR_INVALID, "null argument");
   if (params->spp == 0) return fail(UECRT_ERR_INVALID, "spp must be > 0");
+  if (params->width == 0 || params->height == 0) return fail(UECRT_ERR_INVALID, "empty image");
+  if ((rc = validate_scene(scene))) return rc;
   const int avail = usable_device_count();
   int ndev = params->num_gpus <= 0 ? 1 : params->num_gpus;
   if (ndev > avail) return fail(UECRT_ERR_INVALID, "num_gpus=%d but only %d sm_100 device(s) are visible", ndev, avail);
@@ -350,103 +432,79 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
   NcclApi* nccl = nullptr;
   if (ndev > 1 && (rc = get_comms(ndev, comms, nccl))) return rc;
 
-  struct PerDev {
-    uecrt_ctx* ctx = nullptr; float* accum = nullptr; cudaStream_t st = nullptr; int rc = 0; uecrt_stats stats{};
-    cudaEvent_t r0 = nullptr, r1 = nullptr;
-  };
-  std::vector<PerDev> pd(ndev);
-  std::vector<std::thread> th;
-  uint8_t* d_rgb = nullptr;
-  double resolve_ms = 0, d2h_ms = 0, reduce_ms = 0;
-
+  std::vector<Workspace*> ws(ndev, nullptr);
+  std::vector<int> wrc(ndev, 0);
+  // per device: scene H2D, zero the accumulation buffer, launch K1 on this device's spp shard
   auto worker = [&](int g) {
-    PerDev& w = pd[g];
     auto body = [&]() -> int {
       const int dev = ndev > 1 ? g : dev0;
-      CUDA_TRY(cudaSetDevice(dev));
-      int r = ctx_create_on_current_device(scene, cam, &w.ctx);
+      int r = get_workspace(dev, npx * 4 * sizeof(float), g == 0 ? npx * 3 : 0, &ws[g]);
       if (r) return r;
-      CUDA_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
-      CUDA_TRY(cudaMalloc(&w.accum, npx * 4 * sizeof(float)));
+      Workspace& w = *ws[g];
+      if ((r = ctx_set_scene(w.ctx, scene, cam))) return r;
       CUDA_TRY(cudaMemsetAsync(w.accum, 0, npx * 4 * sizeof(float), w.st));
       uecrt_params p = *params;
-      // spp shard g of ndev: global sample ids, so the image does not depend on ndev
+      // spp shard g of ndev: GLOBAL sample ids, so the image does not depend on ndev
       const uint32_t lo = begin + (uint32_t)((uint64_t)count * g / ndev), hi = begin + (uint32_t)((uint64_t)count * (g + 1) / ndev);
       p.sample_begin = lo; p.sample_count = hi - lo;
-      if (p.sample_count) {
-        r = accumulate(w.ctx, &p, w.accum, w.st);
-        if (r) return r;
-      }
-      CUDA_TRY(cudaEventCreate(&w.r0)); CUDA_TRY(cudaEventCreate(&w.r1));
+      w.ctx->timed = false;
+      if (p.sample_count && (r = accumulate(w.ctx, &p, w.accum, w.st))) return r;
       return UECRT_OK;
     };
-    w.rc = body();
+    wrc[g] = body();
   };
   if (ndev == 1) worker(0);
   else {
+    std::vector<std::thread> th;
     for (int g = 0; g < ndev; ++g) th.emplace_back(worker, g);
     for (auto& t : th) t.join();
   }
-  auto cleanup = [&]() {
-    for (int g = 0; g < ndev; ++g) {
-      cudaSetDevice(ndev > 1 ? g : dev0);
-      if (pd[g].accum) cudaFree(pd[g].accum);
-      if (pd[g].st) { cudaStreamSynchronize(pd[g].st); cudaStreamDestroy(pd[g].st); }
-      if (pd[g].r0) cudaEventDestroy(pd[g].r0);
-      if (pd[g].r1) cudaEventDestroy(pd[g].r1);
-      if (pd[g].ctx) ctx_free(pd[g].ctx);
-    }
-    cudaSetDevice(dev0);
-    if (d_rgb) cudaFree(d_rgb);
-  };
+  auto restore = [&]() { cudaSetDevice(dev0); };
   for (int g = 0; g < ndev; ++g)
-    if (pd[g].rc) { rc = pd[g].rc; cleanup(); return rc; }
+    if (wrc[g]) { restore(); return wrc[g]; }
 
-  // ---- one NCCL reduce of W*H*4 floats to device 0 (in place on the root)
+  // ---- one NCCL reduce of W*H*4 floats to device 0 (in place on the root) over NVLink
+  double resolve_ms = 0, d2h_ms = 0, reduce_ms = 0;
   if (ndev > 1) {
     nccl->GroupStart();
     for (int g = 0; g < ndev; ++g) {
       cudaSetDevice(g);
-      cudaEventRecord(pd[g].r0, pd[g].st);
-      int r = nccl->Reduce(pd[g].accum, pd[g].accum, npx * 4, kNcclFloat, kNcclSum, 0, comms[g], pd[g].st);
+      cudaEventRecord(ws[g]->r0, ws[g]->st);
+      int r = nccl->Reduce(ws[g]->accum, ws[g]->accum, npx * 4, kNcclFloat, kNcclSum, 0, comms[g], ws[g]->st);
       if (r != 0) rc = fail(UECRT_ERR_NCCL, "ncclReduce failed on device %d: %s", g, nccl->GetErrorString ? nccl->GetErrorString(r) : "?");
     }
     int r = nccl->GroupEnd();
     if (r != 0 && !rc) rc = fail(UECRT_ERR_NCCL, "ncclGroupEnd failed: %s", nccl->GetErrorString ? nccl->GetErrorString(r) : "?");
-    for (int g = 0; g < ndev; ++g) { cudaSetDevice(g); cudaEventRecord(pd[g].r1, pd[g].st); }
-    if (rc) { cleanup(); return rc; }
+    for (int g = 0; g < ndev; ++g) { cudaSetDevice(g); cudaEventRecord(ws[g]->r1, ws[g]->st); }
+    if (rc) { restore(); return rc; }
   }
 
   // ---- root: K3 resolve + copies back
   auto root = [&]() -> int {
     CUDA_TRY(cudaSetDevice(ndev > 1 ? 0 : dev0));
-    PerDev& w = pd[0];
-    cudaEvent_t e0, e1, e2;
-    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventCreate(&e2));
-    CUDA_TRY(cudaMalloc(&d_rgb, npx * 3));
-    CUDA_TRY(cudaEventRecord(e0, w.st));
-    uecrt::launch_resolve(reinterpret_cast<const float4*>(w.accum), (uint32_t)npx, count, d_rgb, w.st);
+    Workspace& w = *ws[0];
+    CUDA_TRY(cudaEventRecord(w.e0, w.st));
+    uecrt::launch_resolve(reinterpret_cast<const float4*>(w.accum), (uint32_t)npx, count, w.rgb, w.st);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(e1, w.st));
-    CUDA_TRY(cudaMemcpyAsync(rgb_out, d_rgb, npx * 3, cudaMemcpyDeviceToHost, w.st));
+    CUDA_TRY(cudaEventRecord(w.e1, w.st));
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, w.rgb, npx * 3, cudaMemcpyDeviceToHost, w.st));
     if (accum_out_or_null) CUDA_TRY(cudaMemcpyAsync(accum_out_or_null, w.accum, npx * 4 * sizeof(float), cudaMemcpyDeviceToHost, w.st));
-    CUDA_TRY(cudaEventRecord(e2, w.st));
+    CUDA_TRY(cudaEventRecord(w.e2, w.st));
     CUDA_TRY(cudaStreamSynchronize(w.st));
     float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1)); resolve_ms = ms;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e1, e2)); d2h_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, w.e0, w.e1)); resolve_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, w.e1, w.e2)); d2h_ms = ms;
     if (ndev > 1) { CUDA_TRY(cudaEventElapsedTime(&ms, w.r0, w.r1)); reduce_ms = ms; }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return UECRT_OK;
   };
   rc = root();
+  for (int g = 1; g < ndev; ++g) { cudaSetDevice(g); cudaStreamSynchronize(ws[g]->st); }
   if (!rc && stats_or_null) {
     uecrt_stats total{};
     for (int g = 0; g < ndev && !rc; ++g) {
       cudaSetDevice(ndev > 1 ? g : dev0);
-      cudaStreamSynchronize(pd[g].st);
       uecrt_stats s{};
-      rc = ctx_stats(pd[g].ctx, &s);
+      rc = ctx_stats(ws[g]->ctx, &s);
       if (g == 0) total = s;
       else {
         total.rays_traced += s.rays_traced; total.sphere_tests += s.sphere_tests; total.paths += s.paths;
@@ -456,9 +514,11 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
     total.reduce_ms = reduce_ms; total.resolve_ms = resolve_ms; total.d2h_ms = d2h_ms;
     *stats_or_null = total;
   }
-  cleanup();
+  restore();
   return rc;
 }
+
+void uecrt_release(void) { release_workspaces(); }
 
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
                        double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
