@@ -36,7 +36,8 @@ class StatsStruct(C.Structure):
                 ("k1_blocks", C.c_int32), ("k1_threads", C.c_int32), ("k1_smem_bytes", C.c_int32), ("k1_regs", C.c_int32)]
 
 
-lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libuecrt.so")
+# UECRT_LIB selects an alternative build of the same ABI (kernel tuning experiments only)
+lib_path = os.environ.get("UECRT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libuecrt.so")
 
 # every symbol include/uecrt.h and include/uecrt_host.h declare
 EXPORTS = [

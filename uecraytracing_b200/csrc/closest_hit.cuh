@@ -4,19 +4,22 @@
 // with a shrinking CLOSED interval, later index wins exact ties) over sphere::hit_impl
 // (yk/sphere.hpp:25-48).  Two phases per ray:
 //
-//  1. SCAN (the roofline loop, FP32, packed f32x2 -> SASS FFMA2/FADD2): for every sphere PAIR
-//     read two broadcast LDS.128 from shared memory and evaluate, with the ray direction
-//     normalised (a = 1),
-//         hb   = o.d - c.d                      (3 FFMA2, chain starts at the per-ray o.d)
-//         -cc  = -(|o|^2 - 2 o.c + |c|^2 - r^2) (3 FFMA2 + 1 FADD2; |c|^2-r^2 is per-sphere)
-//         disc = hb^2 - cc                      (1 FFMA2)
-//     i.e. 8 packed FP32 instructions per 2 tests.  The per-sphere constant is stored
-//     RAISED and |o|^2 LOWERED by a rigorous bound on the FP32 rounding error of this
-//     expression (scene_pack.hpp), so "disc_fp32 >= 0" is a SUPERSET of the reference's
-//     "discriminant >= 0" (sphere.hpp:32).  Sign bits of the two discriminants are combined
-//     with one LOP3; a taken branch only appends the sphere index to a per-thread candidate
-//     list in shared memory.  Nothing else happens in the loop: every non-FP32 instruction
-//     costs an FP32 issue slot on sm_100 (tools/microbench, profiles/ubench_r1.log).
+//  1. SCAN (the roofline loop, FP32, packed f32x2 -> SASS FMUL2/FFMA2): with the ray direction
+//     normalised (a = 1) the reference discriminant half_b^2 - a*c (sphere.hpp:27-31) is
+//         disc = (c.d)^2 + q.c - k - P,   q = 2(o - (o.d)d),  k = |c|^2 - r^2,  P = |o|^2 - (o.d)^2
+//     q and P depend on the ray only, k on the sphere only, so per sphere PAIR the loop reads
+//     two broadcast LDS.128 from shared memory and evaluates
+//         cd = c.d                 (FMUL2 + 2 FFMA2)
+//         e  = q.c - k             (3 FFMA2, the chain starts at the per-sphere -k)
+//         f  = cd^2 + e            (1 FFMA2)
+//     i.e. 7 packed FP32 instructions per 2 tests, and a sphere is a candidate iff f >= P.
+//     -k is stored RAISED and P LOWERED by a rigorous bound on the FP32 rounding error of this
+//     expression (scene_pack.hpp), so {f >= P} is a SUPERSET of the reference's
+//     "discriminant >= 0" (sphere.hpp:32).  P > 0, so f >= P is an INTEGER compare of the float
+//     bit patterns: eight f are reduced with 3-input integer max and one branch per 8 spheres
+//     guards the code that appends sphere indices to a per-thread candidate list in shared
+//     memory.  Nothing else happens in the loop: every non-FP32 instruction costs an FP32 issue
+//     slot on sm_100 (tools/microbench, profiles/ubench_r1.log).
 //  2. RESOLVE (once per ray, a few candidates): walk the candidate list in index order and
 //     apply the reference's root selection and closed-interval update
 //       FAST : FP32, cancellation-free form  l = oc - (oc.d)d, disc = r^2 - |l|^2
@@ -41,37 +44,59 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
   unsigned long long d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 
+// 1/sqrt(x): MUFU.RSQ plus one Newton step (~1 ulp), instead of the multi-instruction IEEE
+// sqrtf + divide; the scan's error bound budgets 3u for the normalised direction.
+__device__ __forceinline__ float rsqrt_nr(float x) {
+  const float y = rsqrtf(x);
+  return y * fmaf(-0.5f * x, y * y, 1.5f);
+}
+// sqrt(x) for x >= 0 through MUFU.SQRT (sqrt.approx, <= 2 ulp); exact 0 stays 0
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Per-ray constants of the scan (unit direction).
 struct ScanRay {
-  float dx, dy, dz;     // unit direction
-  float m2ox, m2oy, m2oz;  // -2 * origin
-  float od;             // origin . direction
-  float noo;            // -(|origin|^2 * (1 - kRayBound))   (lowered |o|^2, negated)
+  float dx, dy, dz;        // unit direction
+  float nqx, nqy, nqz;     // -q = 2((o.d)d - o)
+  int thr;                 // bit pattern of P lowered by the ray part of the error bound, clamped to >= +0
 };
 
-// Fraction of |o|^2 by which the ray part of the discriminant bound lowers cc (scene_pack.hpp).
+// Fraction of |o|^2 by which the ray part of the discriminant bound lowers P (scene_pack.hpp).
 constexpr float kRayBound = 80.0f * 5.9604644775390625e-8f;   // 80 * 2^-24
 
 __device__ __forceinline__ ScanRay make_scan_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
   ScanRay s;
   s.dx = dx; s.dy = dy; s.dz = dz;
-  s.m2ox = -2.0f * ox; s.m2oy = -2.0f * oy; s.m2oz = -2.0f * oz;
-  s.od = fmaf(oz, dz, fmaf(oy, dy, ox * dx));
+  const float od = fmaf(oz, dz, fmaf(oy, dy, ox * dx));
+  s.nqx = 2.0f * fmaf(od, dx, -ox); s.nqy = 2.0f * fmaf(od, dy, -oy); s.nqz = 2.0f * fmaf(od, dz, -oz);
   const float oo = fmaf(oz, oz, fmaf(oy, oy, ox * ox));
-  s.noo = -(oo - oo * kRayBound);
+  const float P = fmaf(-od, od, oo) - oo * kRayBound;
+  // f >= P as a signed-integer compare needs P >= +0: a lowered P below zero becomes +0, which only
+  // adds candidates (every f with a clear sign bit), never drops one
+  s.thr = __float_as_int(fmaxf(P, 0.0f));
   return s;
 }
 
-// Candidate list: entry e of thread t lives at list[e * stride] (list already offset by t).
+// Candidate list: entry e of thread t lives at base[e * STRIDE] (base already offset by t);
+// STRIDE = threads per block, so the 32 lanes of a warp write 32 consecutive uint16.
+template <int STRIDE>
 struct CandList {
   uint16_t* base;
-  int stride;   // in uint16 units (= threads per block)
+  static constexpr int stride = STRIDE;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -79,11 +104,12 @@ struct CandList {
 // t is the distance along the UNIT direction; tmin is 0.001*|d| in those units.
 struct FastBest { float t; int id; };
 
-__device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, const CandList& L, int cnt,
+template <int STRIDE>
+__device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, const CandList<STRIDE>& L, int cnt,
                                              float ox, float oy, float oz, float dx, float dy, float dz,
                                              float tmin, int self_id, FastBest& best) {
   for (int e = 0; e < cnt; ++e) {
-    const int j = L.base[e * L.stride];
+    const int j = L.base[e * STRIDE];
     const float4 g = __ldg(&geom[j]);
     const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
     const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
@@ -97,7 +123,7 @@ __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, co
       const float lx = fmaf(-hb, dx, ocx), ly = fmaf(-hb, dy, ocy), lz = fmaf(-hb, dz, ocz);
       const float disc = fmaf(g.w, g.w, -fmaf(lz, lz, fmaf(ly, ly, lx * lx)));
       if (disc < 0.0f) continue;                       // sphere.hpp:32
-      const float s = sqrtf(disc);
+      const float s = sqrt_fast(disc);
       t = -hb - s;                                      // sphere.hpp:35
       if (t < tmin) {                                   // sphere.hpp:36-39 (t_max test below)
         t = -hb + s;
@@ -114,11 +140,12 @@ __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, co
 // reference's root; the unit direction inside K1).
 struct ExactBest { double t; int id; };
 
-__device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, const CandList& L, int cnt,
+template <int STRIDE>
+__device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, const CandList<STRIDE>& L, int cnt,
                                               double ox, double oy, double oz, double dx, double dy, double dz,
                                               double a, double tmin, ExactBest& best) {
   for (int e = 0; e < cnt; ++e) {
-    const int j = L.base[e * L.stride];
+    const int j = L.base[e * STRIDE];
     const float4 g = __ldg(&geom[j]);
     const double cx = g.x, cy = g.y, cz = g.z, r = g.w;
     const double ocx = __dsub_rn(ox, cx), ocy = __dsub_rn(oy, cy), ocz = __dsub_rn(oz, cz);     // sphere.hpp:27
@@ -140,43 +167,76 @@ __device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, c
 
 // ---------------------------------------------------------------------------------------
 // Phase 1: the scan.  pairs: shared memory, 2 x 16 B per sphere pair
-//   A = {-cx0, -cx1, -cy0, -cy1},  B = {-cz0, -cz1, nk0, nk1},  nk = -(|c|^2 - r^2 - bound)
-// npairs is a multiple of 4 (host pads with never-hit pairs).  `index_base` is added to
-// stored indices (tile offset when the scene is swept in tiles).
-// On list overflow the FULL callback folds the list into the running best and empties it.
-template <class OnFull>
+//   A = {-cx0, -cx1, -cy0, -cy1},  B = {-cz0, -cz1, nk0, nk1},  nk = -(|c|^2 - r^2) + bound
+// Two pairs (4 spheres) form a GROUP; npairs is a multiple of 4 and the host appends one more
+// never-hit group so the loop can prefetch group g+1 unconditionally.  Per group the loop issues
+// 4 LDS.128 for the NEXT group (software pipelining: the loads are in flight across this
+// group's math), 14 packed FP32 ops in two interleaved dependency chains and two 3-input integer
+// max; every second group ends with the compare + branch.  `index_base` is added to stored
+// indices (tile offset when the scene is swept in tiles).  When the list is nearly full the FULL
+// callback folds it into the running best and the list restarts.
+template <int STRIDE, class OnFull>
 __device__ __forceinline__ int scan_pairs(const ulonglong2* __restrict__ pairs, int npairs, int index_base,
-                                          const ScanRay& r, const CandList& L, int cnt, OnFull&& on_full) {
+                                          const ScanRay& r, const CandList<STRIDE>& L, OnFull&& on_full) {
   const unsigned long long dx2 = pk2(r.dx, r.dx), dy2 = pk2(r.dy, r.dy), dz2 = pk2(r.dz, r.dz);
-  const unsigned long long ox2 = pk2(r.m2ox, r.m2ox), oy2 = pk2(r.m2oy, r.m2oy), oz2 = pk2(r.m2oz, r.m2oz);
-  const unsigned long long od2 = pk2(r.od, r.od), noo2 = pk2(r.noo, r.noo);
-#pragma unroll 4
-  for (int j = 0; j < npairs; ++j) {
-    const ulonglong2 A = pairs[2 * j];
-    const ulonglong2 B = pairs[2 * j + 1];
-    unsigned long long hb = fma2(A.x, dx2, od2);
-    unsigned long long ncc = fma2(A.x, ox2, noo2);
-    hb = fma2(A.y, dy2, hb);
-    ncc = fma2(A.y, oy2, ncc);
-    hb = fma2(B.x, dz2, hb);
-    ncc = fma2(B.x, oz2, ncc);
-    ncc = add2(ncc, B.y);
-    const unsigned long long disc = fma2(hb, hb, ncc);
-    const uint32_t d0 = (uint32_t)disc, d1 = (uint32_t)(disc >> 32);
-    if ((int)(d0 & d1) >= 0) {              // at least one sign bit clear: a candidate
-      if ((int)d0 >= 0) {
-        if (cnt == kListCap) { on_full(cnt); cnt = 0; }
-        L.base[cnt * L.stride] = (uint16_t)(index_base + 2 * j);
-        ++cnt;
+  const unsigned long long qx2 = pk2(r.nqx, r.nqx), qy2 = pk2(r.nqy, r.nqy), qz2 = pk2(r.nqz, r.nqz);
+  const int thr = r.thr;
+  // byte offset of the next free list entry (32-bit shared-memory arithmetic only)
+  constexpr uint32_t kEntryBytes = (uint32_t)STRIDE * (uint32_t)sizeof(uint16_t);
+  constexpr uint32_t kFullAt = (uint32_t)(kListCap - 8) * kEntryBytes;   // < 8 free entries left
+  unsigned char* const lbase = reinterpret_cast<unsigned char*>(L.base);
+  uint32_t ofs = 0;
+
+  // f for the four spheres of one group: two interleaved chains of 7 packed ops
+#define UECRT_GROUP_MATH(A0, B0, A1, B1, f0, f1, f2, f3)                                   \
+  {                                                                                        \
+    unsigned long long cd0 = mul2(A0.x, dx2);                                              \
+    unsigned long long cd1 = mul2(A1.x, dx2);                                              \
+    unsigned long long e0 = fma2(A0.x, qx2, B0.y);                                         \
+    unsigned long long e1 = fma2(A1.x, qx2, B1.y);                                         \
+    cd0 = fma2(A0.y, dy2, cd0);                                                            \
+    cd1 = fma2(A1.y, dy2, cd1);                                                            \
+    e0 = fma2(A0.y, qy2, e0);                                                              \
+    e1 = fma2(A1.y, qy2, e1);                                                              \
+    cd0 = fma2(B0.x, dz2, cd0);                                                            \
+    cd1 = fma2(B1.x, dz2, cd1);                                                            \
+    e0 = fma2(B0.x, qz2, e0);                                                              \
+    e1 = fma2(B1.x, qz2, e1);                                                              \
+    const unsigned long long g0 = fma2(cd0, cd0, e0);                                      \
+    const unsigned long long g1 = fma2(cd1, cd1, e1);                                      \
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(f0), "=r"(f1) : "l"(g0));                           \
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(f2), "=r"(f3) : "l"(g1));                           \
+  }
+#define UECRT_PUSH(f, idx)                                                                 \
+  if (f >= thr) { *reinterpret_cast<uint16_t*>(lbase + ofs) = (uint16_t)(idx); ofs += kEntryBytes; }
+
+  const ulonglong2* p = pairs;
+  ulonglong2 A0 = p[0], B0 = p[1], A1 = p[2], B1 = p[3];
+  const int niter = npairs >> 2;          // 8 spheres per iteration
+#pragma unroll 1
+  for (int it = 0; it < niter; ++it) {
+    int f0, f1, f2, f3, f4, f5, f6, f7;
+    const ulonglong2 A2 = p[4], B2 = p[5], A3 = p[6], B3 = p[7];          // second group of this iteration
+    UECRT_GROUP_MATH(A0, B0, A1, B1, f0, f1, f2, f3)
+    p += 8;
+    A0 = p[0]; B0 = p[1]; A1 = p[2]; B1 = p[3];                            // first group of the next (padded)
+    UECRT_GROUP_MATH(A2, B2, A3, B3, f4, f5, f6, f7)
+    const int mlo = max(max(f0, f1), max(f2, f3));
+    const int mhi = max(max(f4, f5), max(f6, f7));
+    if (max(mlo, mhi) >= thr) {           // at least one of the 8 spheres is a candidate
+      if (ofs > kFullAt) { on_full((int)(ofs / kEntryBytes)); ofs = 0; }
+      const int i0 = index_base + 8 * it;
+      if (mlo >= thr) {
+        UECRT_PUSH(f0, i0) UECRT_PUSH(f1, i0 + 1) UECRT_PUSH(f2, i0 + 2) UECRT_PUSH(f3, i0 + 3)
       }
-      if ((int)d1 >= 0) {
-        if (cnt == kListCap) { on_full(cnt); cnt = 0; }
-        L.base[cnt * L.stride] = (uint16_t)(index_base + 2 * j + 1);
-        ++cnt;
+      if (mhi >= thr) {
+        UECRT_PUSH(f4, i0 + 4) UECRT_PUSH(f5, i0 + 5) UECRT_PUSH(f6, i0 + 6) UECRT_PUSH(f7, i0 + 7)
       }
     }
   }
-  return cnt;
+#undef UECRT_GROUP_MATH
+#undef UECRT_PUSH
+  return (int)(ofs / kEntryBytes);
 }
 
 // Hit record in FP32 (yk/hittable.hpp:16-28; id is the OBJECT index as in hittable_list.hpp:41)

@@ -71,22 +71,24 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float
 }
 
 // rare path of the scan: the candidate list is full -> fold it into the running best
-__device__ __noinline__ void fold_full_fast(const float4* geom, uint16_t* base, int stride, int cnt, float ox, float oy,
+template <int STRIDE>
+__device__ __noinline__ void fold_full_fast(const float4* geom, uint16_t* base, int cnt, float ox, float oy,
                                             float oz, float dx, float dy, float dz, float tmin, int self_id,
                                             FastBest* best) {
-  CandList L{base, stride};
+  CandList<STRIDE> L{base};
   resolve_fast(geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, *best);
 }
-__device__ __noinline__ void fold_full_exact(const float4* geom, uint16_t* base, int stride, int cnt, double ox,
+template <int STRIDE>
+__device__ __noinline__ void fold_full_exact(const float4* geom, uint16_t* base, int cnt, double ox,
                                              double oy, double oz, double dx, double dy, double dz, double a,
                                              double tmin, ExactBest* best) {
-  CandList L{base, stride};
+  CandList<STRIDE> L{base};
   resolve_exact(geom, L, cnt, ox, oy, oz, dx, dy, dz, a, tmin, *best);
 }
 
 // One closest-hit query for the renderer: unit direction, t in world units.
-template <bool EXACT>
-__device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulonglong2* s_pairs, const CandList& L,
+template <bool EXACT, int STRIDE>
+__device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulonglong2* s_pairs, const CandList<STRIDE>& L,
                                                 float ox, float oy, float oz, float dx, float dy, float dz,
                                                 float tmin, int self_id) {
   const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
@@ -94,8 +96,8 @@ __device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulo
   h.id = -1;
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
-      fold_full_fast(sc.geom, L.base, L.stride, c, ox, oy, oz, dx, dy, dz, tmin, self_id, &best);
+    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+      fold_full_fast<STRIDE>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin, self_id, &best);
     });
     resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, best);
     if (best.id >= 0) {
@@ -107,8 +109,8 @@ __device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulo
     const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
     ExactBest best{(double)CUDART_INF, -1};
-    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
-      fold_full_exact(sc.geom, L.base, L.stride, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, &best);
+    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+      fold_full_exact<STRIDE>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, &best);
     });
     resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, best);
     if (best.id >= 0) {
@@ -129,15 +131,18 @@ __device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulo
 // ---------------------------------------------------------------------------------------
 // K1
 template <bool EXACT>
-__global__ void __launch_bounds__(kRenderThreads, 2) k_render_paths(const RenderArgs a) {
+#ifndef UECRT_K1_MINB
+#define UECRT_K1_MINB 3          // CTAs per SM the register allocator must allow (tuning knob; 3 measured best)
+#endif
+__global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(const RenderArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
-  const uint32_t pair_bytes = (uint32_t)a.sc.npairs * 32u;
+  const uint32_t pair_bytes = (uint32_t)(a.sc.npairs + 2) * 32u;   // + the prefetch pad group
   uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + 16 + pair_bytes);
   stage_scene_tma(bar, s_pairs, a.sc.pairs, pair_bytes);
 
-  const CandList L{s_lists + threadIdx.x, (int)blockDim.x};
+  const CandList<kRenderThreads> L{s_lists + threadIdx.x};
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long n_pixels = (unsigned long long)a.width * a.height;
   const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
@@ -209,8 +214,8 @@ __global__ void __launch_bounds__(kRenderThreads, 2) k_render_paths(const Render
         tx -= ox; ty -= oy; tz -= oz;
       }
       const float len2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-      dlen = sqrtf(len2);
-      const float inv = 1.0f / dlen;
+      const float inv = rsqrt_nr(len2);
+      dlen = len2 * inv;
       dx = tx * inv; dy = ty * inv; dz = tz * inv;
       thr_r = thr_g = thr_b = 1.f;
       depth_left = a.max_depth;
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(kRenderThreads, 2) k_render_paths(const Render
     // ---- one path segment: closest hit + scatter (raytracer.hpp:27-36)
     if (active) {
       ++n_rays;
-      const Hit h = closest_hit_unit<EXACT>(a.sc, s_pairs, L, ox, oy, oz, dx, dy, dz, 0.001f * dlen, self_id);
+      const Hit h = closest_hit_unit<EXACT, kRenderThreads>(a.sc, s_pairs, L, ox, oy, oz, dx, dy, dz, 0.001f * dlen, self_id);
       float rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
       bool ended = true;
       if (h.id < 0) {
@@ -244,8 +249,8 @@ __global__ void __launch_bounds__(kRenderThreads, 2) k_render_paths(const Render
           thr_r *= s.ar; thr_g *= s.ag; thr_b *= s.ab;
           ox = h.px; oy = h.py; oz = h.pz;
           const float len2 = fmaf(s.dz, s.dz, fmaf(s.dy, s.dy, s.dx * s.dx));
-          dlen = sqrtf(len2);
-          const float inv = 1.0f / dlen;
+          const float inv = rsqrt_nr(len2);
+          dlen = len2 * inv;
           dx = s.dx * inv; dy = s.dy * inv; dz = s.dz * inv;
           self_id = h.id;
           --depth_left;
@@ -286,10 +291,10 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
-  const uint32_t pair_bytes = (uint32_t)sc.npairs * 32u;
+  const uint32_t pair_bytes = (uint32_t)(sc.npairs + 2) * 32u;     // + the prefetch pad group
   uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + 16 + pair_bytes);
   stage_scene_tma(bar, s_pairs, sc.pairs, pair_bytes);
-  const CandList L{s_lists + threadIdx.x, (int)blockDim.x};
+  const CandList<kHitsThreads> L{s_lists + threadIdx.x};
 
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays;
        i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -305,8 +310,8 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
     if (!EXACT) {
       const float tmin_w = (float)tmin * dlen;
       FastBest best{(float)tmax * dlen, -1};
-      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
-        fold_full_fast(sc.geom, L.base, L.stride, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
+      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+        fold_full_fast<kHitsThreads>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
       });
       resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
       if (best.id >= 0) {
@@ -318,8 +323,8 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
       const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
       const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
       ExactBest best{tmax, -1};
-      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, [&](int c) {
-        fold_full_exact(sc.geom, L.base, L.stride, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
+      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+        fold_full_exact<kHitsThreads>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
       });
       resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
       if (best.id >= 0) {
@@ -386,7 +391,7 @@ __global__ void k_philox(unsigned long long n, uint32_t k0, uint32_t k1, const u
 // ---------------------------------------------------------------------------------------
 // host launchers
 size_t render_smem_bytes(int npairs, int threads) {
-  return 16 + (size_t)npairs * 32 + (size_t)kListCap * threads * sizeof(uint16_t);
+  return 16 + (size_t)(npairs + 2) * 32 + (size_t)kListCap * threads * sizeof(uint16_t);
 }
 
 cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render) {

@@ -8,6 +8,7 @@
 // switch on the per-sphere material type.
 #pragma once
 #include "../../include/uecrt.h"
+#include "closest_hit.cuh"
 #include "philox.cuh"
 
 namespace uecrt {
@@ -56,7 +57,7 @@ __device__ __forceinline__ ScatterOut scatter_material(uint32_t type, float4 par
       s.dx = fmaf(-dn, nx, dx); s.dy = fmaf(-dn, ny, dy); s.dz = fmaf(-dn, nz, dz);
     } else {
       const float px = eta * fmaf(cos_theta, nx, dx), py = eta * fmaf(cos_theta, ny, dy), pz = eta * fmaf(cos_theta, nz, dz);
-      const float k = -sqrtf(fabsf(1.0f - fmaf(pz, pz, fmaf(py, py, px * px))));
+      const float k = -sqrt_fast(fabsf(1.0f - fmaf(pz, pz, fmaf(py, py, px * px))));
       s.dx = fmaf(k, nx, px); s.dy = fmaf(k, ny, py); s.dz = fmaf(k, nz, pz);
     }
   }

@@ -23,12 +23,14 @@
 
 namespace uecrt {
 
-constexpr int kPairUnroll = 4;   // scan loop unroll; npairs is padded to a multiple of it
+constexpr int kPairUnroll = 4;   // pairs per unrolled scan iteration (2 groups of 2 pairs); npairs is padded to a multiple
+constexpr int kPairPad = 2;      // one extra never-hit group after the last, read by the scan's prefetch
 
 struct PackedScene {
   uint32_t n = 0;        // spheres
-  uint32_t npairs = 0;   // padded pair count (multiple of kPairUnroll)
-  std::vector<float> pairs;   // npairs * 8 floats
+  uint32_t npairs = 0;   // padded pair count (multiple of kPairUnroll) the scan loops over
+  std::vector<float> pairs;   // (npairs + kPairPad) * 8 floats
+  size_t bytes() const { return pairs.size() * sizeof(float); }
 };
 
 inline float round_up_to_float(double v) {
@@ -44,9 +46,9 @@ inline PackedScene pack_scene(const uecrt_scene& sc) {
   np = (np + kPairUnroll - 1) / kPairUnroll * kPairUnroll;
   if (np == 0) np = kPairUnroll;
   p.npairs = np;
-  p.pairs.assign((size_t)np * 8, 0.0f);
+  p.pairs.assign((size_t)(np + kPairPad) * 8, 0.0f);
   const double u = 5.9604644775390625e-8;   // 2^-24
-  for (uint32_t i = 0; i < np * 2; ++i) {
+  for (uint32_t i = 0; i < (np + kPairPad) * 2; ++i) {
     float ncx = 0.f, ncy = 0.f, ncz = 0.f, nk = -1e30f;   // padding: cc = +1e30 -> never a candidate
     if (i < sc.n) {
       const double cx = sc.geom[i].x, cy = sc.geom[i].y, cz = sc.geom[i].z, r = sc.geom[i].w;

@@ -117,7 +117,7 @@ namespace {
 
 int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
   const uecrt::PackedScene ps = uecrt::pack_scene(*scene);
-  const size_t pair_bytes = (size_t)ps.npairs * 32;
+  const size_t pair_bytes = ps.bytes();
   const size_t smem_need = uecrt::render_smem_bytes((int)ps.npairs, uecrt::kRenderThreads);
   if (smem_need > 232448)
     return fail(UECRT_ERR_INVALID, "scene of %u spheres needs %zu B of shared memory per CTA (max 232448)", scene->n, smem_need);
