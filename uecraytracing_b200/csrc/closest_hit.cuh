@@ -168,7 +168,7 @@ __device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, c
 // ---------------------------------------------------------------------------------------
 // Phase 1: the scan.  pairs: shared memory, 2 x 16 B per sphere pair
 //   A = {-cx0, -cx1, -cy0, -cy1},  B = {-cz0, -cz1, nk0, nk1},  nk = -(|c|^2 - r^2) + bound
-// Two pairs (4 spheres) form a GROUP; npairs is a multiple of 4 and the host appends one more
+// Two pairs (4 spheres) form a GROUP; npairs is a multiple of 8 and the host appends one more
 // never-hit group so the loop can prefetch group g+1 unconditionally.  Per group the loop issues
 // 4 LDS.128 for the NEXT group (software pipelining: the loads are in flight across this
 // group's math), 14 packed FP32 ops in two interleaved dependency chains and two 3-input integer
@@ -212,8 +212,8 @@ __device__ __forceinline__ int scan_pairs(const ulonglong2* __restrict__ pairs, 
 
   const ulonglong2* p = pairs;
   ulonglong2 A0 = p[0], B0 = p[1], A1 = p[2], B1 = p[3];
-  const int niter = npairs >> 2;          // 8 spheres per iteration
-#pragma unroll 1
+  const int niter = npairs >> 2;          // 8 spheres per iteration; npairs is a multiple of 8
+#pragma unroll 2
   for (int it = 0; it < niter; ++it) {
     int f0, f1, f2, f3, f4, f5, f6, f7;
     const ulonglong2 A2 = p[4], B2 = p[5], A3 = p[6], B3 = p[7];          // second group of this iteration

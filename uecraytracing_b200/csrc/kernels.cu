@@ -196,14 +196,11 @@ __global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(
       float tz = fmaf(v, a.cam.ver[2], fmaf(u, a.cam.hor[2], a.cam.ll[2]));
       ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
       if (a.cam.lens > 0.f) {
-        // RTIOW random_in_unit_disk: rejection on successive Philox blocks (sub = 1, 2, ...)
-        float rx = fmaf(2.f, uecrt_u01(r.z), -1.f), ry = fmaf(2.f, uecrt_u01(r.w), -1.f);
-        uint32_t sub = 1;
-        while (rx * rx + ry * ry >= 1.f) {
-          philox_out q = philox4x32_10(pixel, sample, 0u, sub++, a.key0, a.key1);
-          rx = fmaf(2.f, uecrt_u01(q.x), -1.f); ry = fmaf(2.f, uecrt_u01(q.y), -1.f);
-          if (rx * rx + ry * ry >= 1.f) { rx = fmaf(2.f, uecrt_u01(q.z), -1.f); ry = fmaf(2.f, uecrt_u01(q.w), -1.f); }
-        }
+        // uniform point in the unit disk from the block's last two uniforms (polar map: r = sqrt(u),
+        // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop the oracle
+        // runs, but exactly two uniforms and no divergent retry loop.
+        const float rr = sqrt_fast(uecrt_u01(r.z)), phi = 6.28318530717958647692f * uecrt_u01(r.w);
+        const float rx = rr * __cosf(phi), ry = rr * __sinf(phi);
         const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;
         const float offx = fmaf(ly, a.cam.v[0], lx * a.cam.u[0]);
         const float offy = fmaf(ly, a.cam.v[1], lx * a.cam.u[1]);

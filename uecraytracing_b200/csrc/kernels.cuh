@@ -7,7 +7,7 @@ namespace uecrt {
 
 struct DeviceScene {
   const ulonglong2* pairs;   // global copy of the packed pairs (2 x 16 B per pair), staged to smem by TMA
-  int npairs;                // padded, multiple of 4; the buffer holds npairs + 2 (prefetch pad)
+  int npairs;                // padded, multiple of 8; the buffer holds npairs + 2 (prefetch pad)
   int n;                     // spheres
   const float4* geom;        // {cx,cy,cz,r}
   const uint32_t* mat_type;

@@ -23,7 +23,7 @@
 
 namespace uecrt {
 
-constexpr int kPairUnroll = 4;   // pairs per unrolled scan iteration (2 groups of 2 pairs); npairs is padded to a multiple
+constexpr int kPairUnroll = 8;   // pairs per unrolled scan trip (2 iterations x 2 groups x 2 pairs); npairs is padded to a multiple
 constexpr int kPairPad = 2;      // one extra never-hit group after the last, read by the scan's prefetch
 
 struct PackedScene {
