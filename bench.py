@@ -254,16 +254,15 @@ def main():
         e2e_s = (time.perf_counter() - t0) / args.steps
     else:
         def e2e_step():
-            c2 = u.Context(scene, cam)                                       # H2D of the scene
+            ctx.set_scene(scene, cam)                                        # H2D of scene + camera (every rank)
             accum.zero_()
             if cnt:
-                c2.accumulate(accum.data_ptr(), W, H, spp, depth, 2026, lo, cnt, stream.cuda_stream, flags)
+                ctx.accumulate(accum.data_ptr(), W, H, spp, depth, 2026, lo, cnt, stream.cuda_stream, flags)
             reduce_accum(accum, 0)
             if rank == 0:
                 u.resolve_device(accum.data_ptr(), W, H, spp, rgb.data_ptr(), stream.cuda_stream)
-                pin_rgb.copy_(rgb, non_blocking=True)                        # D2H of the frame
+                pin_rgb.copy_(rgb, non_blocking=True)                        # D2H of the frame to pinned host memory
             torch.cuda.synchronize()
-            c2.close()
         e2e_step(); barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):

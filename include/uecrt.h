@@ -134,6 +134,9 @@ int uecrt_philox(uint64_t n, uint64_t seed, const uint32_t* counters4, uint32_t*
 typedef struct uecrt_ctx uecrt_ctx;
 int uecrt_ctx_create(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ctx** out);
 void uecrt_ctx_destroy(uecrt_ctx* ctx);
+/* Re-upload a scene (+camera) into an existing context: host->device copies only, device buffers
+ * are reused when they fit (the per-frame H2D of a caller whose scene changes every frame). */
+int uecrt_ctx_set_scene(uecrt_ctx* ctx, const uecrt_scene* scene, const uecrt_camera* cam);
 /* K1: accumulate samples [sample_begin, +sample_count) of every pixel into d_accum
  * (device, W*H float4, must be zeroed by the caller before the first call of a frame). */
 int uecrt_accumulate_device(uecrt_ctx* ctx, const uecrt_params* params, float* d_accum,

@@ -42,7 +42,7 @@ lib_path = os.environ.get("UECRT_LIB") or os.path.join(os.path.dirname(os.path.a
 # every symbol include/uecrt.h and include/uecrt_host.h declare
 EXPORTS = [
     "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_primary_hits", "uecrt_scatter",
-    "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_accumulate_device", "uecrt_resolve_device",
+    "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_ctx_set_scene", "uecrt_accumulate_device", "uecrt_resolve_device",
     "uecrt_ctx_stats", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
     "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox",
 ]
@@ -64,6 +64,8 @@ def _load():
     L.uecrt_philox.argtypes = [u64, u64, vp, vp]
     L.uecrt_ctx_create.argtypes = [vp, vp, C.POINTER(vp)]
     L.uecrt_ctx_destroy.argtypes = [vp]
+    L.uecrt_ctx_set_scene.argtypes = [vp, vp, vp]
+    L.uecrt_ctx_set_scene.restype = C.c_int
     L.uecrt_ctx_destroy.restype = None
     L.uecrt_accumulate_device.argtypes = [vp, vp, vp, vp, vp]
     L.uecrt_resolve_device.argtypes = [vp, u32, u32, u32, vp, vp]

@@ -135,6 +135,11 @@ class Context:
         sc, cam = scene.struct(), camera.struct()
         check(lib.uecrt_ctx_create(C.byref(sc), C.byref(cam), C.byref(self._h)), "uecrt_ctx_create")
 
+    def set_scene(self, scene, camera):
+        """Host->device re-upload of scene and camera into this context (no allocation when it fits)."""
+        sc, cam = scene.struct(), camera.struct()
+        check(lib.uecrt_ctx_set_scene(self._h, C.byref(sc), C.byref(cam)), "uecrt_ctx_set_scene")
+
     def accumulate(self, d_accum_ptr, width, height, spp, max_depth, seed, sample_begin=0, sample_count=0, stream=0,
                    flags=0):
         p = _params(width, height, spp, max_depth, seed, sample_begin, sample_count, 1, flags)

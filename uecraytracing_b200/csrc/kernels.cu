@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(
       ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
       if (a.cam.lens > 0.f) {
         // uniform point in the unit disk from the block's last two uniforms (polar map: r = sqrt(u),
-        // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop the oracle
-        // runs, but exactly two uniforms and no divergent retry loop.
+        // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop of the
+        // book (and of the CPU checker), but exactly two uniforms and no divergent retry loop.
         const float rr = sqrt_fast(uecrt_u01(r.z)), phi = 6.28318530717958647692f * uecrt_u01(r.w);
         const float rx = rr * __cosf(phi), ry = rr * __sinf(phi);
         const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;

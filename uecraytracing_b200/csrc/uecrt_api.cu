@@ -387,6 +387,13 @@ int uecrt_ctx_create(const uecrt_scene* scene, const uecrt_camera* cam, uecrt_ct
   return ctx_create_on_current_device(scene, cam, out);
 }
 void uecrt_ctx_destroy(uecrt_ctx* ctx) { ctx_free(ctx); }
+int uecrt_ctx_set_scene(uecrt_ctx* ctx, const uecrt_scene* scene, const uecrt_camera* cam) {
+  if (!ctx) return fail(UECRT_ERR_INVALID, "ctx is null");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != ctx->device) return fail(UECRT_ERR_INVALID, "context lives on device %d, current device is %d", ctx->device, dev);
+  return ctx_set_scene(ctx, scene, cam);
+}
 
 int uecrt_accumulate_device(uecrt_ctx* ctx, const uecrt_params* params, float* d_accum, void* cuda_stream,
                             uecrt_stats* stats_or_null) {
