@@ -84,6 +84,7 @@ typedef struct {
   double h2d_ms, d2h_ms; /* host entry points only                                     */
   int32_t sm_count, sm_clock_khz;
   int32_t k1_blocks, k1_threads, k1_smem_bytes, k1_regs;
+  int32_t tiles, tile_spheres; /* 1 tile = scene resident in shared memory */
 } uecrt_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
@@ -105,6 +106,12 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 
 /* Frees the per-device workspaces (stream, events, buffers) uecrt_render caches between calls. */
 void uecrt_release(void);
+
+/* Shared-memory tiling of the scene.  0 (default) = automatic: the whole packed scene (16 B per
+ * sphere) stays resident in each CTA's shared memory while three CTAs still fit on an SM (up to
+ * ~4000 spheres), otherwise it is swept in tiles of 2048 spheres through a two-buffer TMA ring.  A non-zero value forces tiles of that many
+ * spheres for every scene loaded afterwards (tests use tiny tiles to exercise the ring). */
+void uecrt_set_tile_spheres(uint32_t spheres_per_tile);
 
 /* uecrt_primary_hits replaces hittable_list::hit_impl (hittable_list.hpp:32-58) on caller
  * rays: closest hit in the CLOSED interval [t_min, t_max], later index wins ties.

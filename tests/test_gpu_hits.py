@@ -40,7 +40,7 @@ def test_primary_rays_exact(u, oracle, name, cam, W):
 
 
 def test_primary_rays_exact_dense_10k(u, oracle):
-    """Config 3's 10k-sphere scene (160 KB of packed geometry in shared memory), sampled rays."""
+    """Config 3's 10k-sphere scene (160 KB packed: swept through the shared-memory tile ring), sampled rays."""
     sc, c = u.Scene.named("dense", seed=1, n=10000), u.Camera.named("dense")
     o, d = primary_rays(c, 1920, 1080)
     pick = np.random.default_rng(3).choice(len(o), 60000, replace=False)

@@ -179,3 +179,8 @@ def philox_host(seed, counter4):
     c = (C.c_uint32 * 4)(*[int(x) for x in counter4]); out = (C.c_uint32 * 4)()
     lib.uecrt_host_philox(seed, c, out)
     return [int(x) for x in out]
+
+
+def set_tile_spheres(n):
+    """0 = automatic residency/tiling; n > 0 forces shared-memory tiles of n spheres (see include/uecrt.h)."""
+    lib.uecrt_set_tile_spheres(int(n))

@@ -173,11 +173,12 @@ __device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, c
 // 4 LDS.128 for the NEXT group (software pipelining: the loads are in flight across this
 // group's math), 14 packed FP32 ops in two interleaved dependency chains and two 3-input integer
 // max; every second group ends with the compare + branch.  `index_base` is added to stored
-// indices (tile offset when the scene is swept in tiles).  When the list is nearly full the FULL
-// callback folds it into the running best and the list restarts.
+// indices (tile offset when the scene is swept in tiles) and `cnt_in` is the number of candidates
+// already in the list.  When the list is nearly full the FULL callback folds it into the running
+// best and the list restarts.
 template <int STRIDE, class OnFull>
 __device__ __forceinline__ int scan_pairs(const ulonglong2* __restrict__ pairs, int npairs, int index_base,
-                                          const ScanRay& r, const CandList<STRIDE>& L, OnFull&& on_full) {
+                                          const ScanRay& r, const CandList<STRIDE>& L, int cnt_in, OnFull&& on_full) {
   const unsigned long long dx2 = pk2(r.dx, r.dx), dy2 = pk2(r.dy, r.dy), dz2 = pk2(r.dz, r.dz);
   const unsigned long long qx2 = pk2(r.nqx, r.nqx), qy2 = pk2(r.nqy, r.nqy), qz2 = pk2(r.nqz, r.nqz);
   const int thr = r.thr;
@@ -185,7 +186,7 @@ __device__ __forceinline__ int scan_pairs(const ulonglong2* __restrict__ pairs, 
   constexpr uint32_t kEntryBytes = (uint32_t)STRIDE * (uint32_t)sizeof(uint16_t);
   constexpr uint32_t kFullAt = (uint32_t)(kListCap - 8) * kEntryBytes;   // < 8 free entries left
   unsigned char* const lbase = reinterpret_cast<unsigned char*>(L.base);
-  uint32_t ofs = 0;
+  uint32_t ofs = (uint32_t)cnt_in * kEntryBytes;   // candidates carried over from earlier tiles
 
   // f for the four spheres of one group: two interleaved chains of 7 packed ops
 #define UECRT_GROUP_MATH(A0, B0, A1, B1, f0, f1, f2, f3)                                   \

@@ -10,8 +10,10 @@
 // K1 design (B200: 148 SMs, 4 sub-partitions each, FP32 128 lanes/clk/SM):
 //  * persistent CTAs; every thread owns one live path; the reference's recursion is an
 //    iterative loop carrying the throughput product (exact up to FP reassociation);
-//  * the packed scene (32 B per sphere pair) is staged ONCE per CTA into shared memory with
-//    cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier; the scan reads it with
+//  * the packed scene (32 B per sphere pair) is staged into shared memory with cp.async.bulk (TMA,
+//    SASS UBLKCP) completing on an mbarrier -- ONCE per CTA when it fits (RESIDENT), else TILED:
+//    the CTA sweeps the scene through a two-buffer ring, every live ray of the block testing tile
+//    k while the TMA fills the other buffer with tile k+1; the scan reads shared memory with
 //    warp-broadcast LDS.128, so there is no bank conflict and no global traffic in the loop;
 //  * work items are (pixel, chunk of samples); a lane whose path ended starts its next sample
 //    at once, and lanes that finished an item refill together with ONE atomicAdd per warp
@@ -66,6 +68,61 @@ __device__ __forceinline__ void stage_scene_tma(uint64_t* bar, void* dst, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Tile ring for scenes that do not fit in one CTA's shared memory.  Tiles are consumed in a fixed
+// global order s = 0, 1, 2, ... (tile s % ntiles into buffer s & 1); the k-th fill of a buffer
+// completes phase k of its full-barrier.  A buffer is refilled only after a __syncthreads() that
+// follows every thread's scan of it.  `seq` is identical in all threads of the CTA.
+struct TileRing {
+  uint64_t* full;          // 2 mbarriers
+  unsigned char* buf;      // 2 buffers of tile_bytes
+  uint32_t tile_bytes;
+  uint32_t seq;            // tiles consumed so far
+};
+
+__device__ __forceinline__ void ring_issue(const TileRing& r, const DeviceScene& sc, uint32_t s) {   // one thread
+  const uint32_t b = s & 1u, tile = s % (uint32_t)sc.ntiles;
+  const char* src = reinterpret_cast<const char*>(sc.pairs) + (size_t)tile * r.tile_bytes;
+  const uint32_t bar = smem_u32(r.full + b);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(r.tile_bytes) : "memory");
+  const uint32_t kChunk = 32768;
+  for (uint32_t off = 0; off < r.tile_bytes; off += kChunk) {
+    const uint32_t sz = r.tile_bytes - off < kChunk ? r.tile_bytes - off : kChunk;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(r.buf + (size_t)b * r.tile_bytes + off)),
+                 "l"(src + off), "r"(sz), "r"(bar)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void ring_wait(const TileRing& r, uint32_t s) {   // every thread
+  const uint32_t bar = smem_u32(r.full + (s & 1u)), parity = (s >> 1) & 1u;
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void ring_init(TileRing& r, const DeviceScene& sc, unsigned char* smem_raw) {
+  r.full = reinterpret_cast<uint64_t*>(smem_raw);
+  r.buf = smem_raw + 32;
+  r.tile_bytes = (uint32_t)(sc.npairs + 2) * 32u;
+  r.seq = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(r.full)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(r.full + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { ring_issue(r, sc, 0); ring_issue(r, sc, 1); }
+}
+// before the CTA exits: the two fills that are always in flight ahead of `seq` must land
+__device__ __forceinline__ void ring_drain(const TileRing& r) { ring_wait(r, r.seq); ring_wait(r, r.seq + 1); }
+
 __device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z, float w) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
@@ -86,34 +143,58 @@ __device__ __noinline__ void fold_full_exact(const float4* geom, uint16_t* base,
   resolve_exact(geom, L, cnt, ox, oy, oz, dx, dy, dz, a, tmin, *best);
 }
 
+// Candidate collection over the whole scene.  RESIDENT: one call of the scan on the resident
+// tile, no synchronisation.  TILED: block-synchronous sweep; EVERY thread of the CTA must call
+// this (has_ray = false for threads without a live ray: they only take part in the barriers).
+template <bool TILED, int STRIDE, class OnFull>
+__device__ __forceinline__ int collect_candidates(const DeviceScene& sc, const ulonglong2* s_pairs, TileRing& ring,
+                                                  const CandList<STRIDE>& L, bool has_ray, const ScanRay& sr,
+                                                  OnFull&& on_full) {
+  if (!TILED) return scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, on_full);
+  int cnt = 0;
+  for (int t = 0; t < sc.ntiles; ++t) {
+    const uint32_t sq = ring.seq;
+    ring_wait(ring, sq);
+    if (has_ray)
+      cnt = scan_pairs(reinterpret_cast<const ulonglong2*>(ring.buf + (size_t)(sq & 1u) * ring.tile_bytes), sc.npairs,
+                       t * sc.npairs * 2, sr, L, cnt, on_full);
+    __syncthreads();                                   // every thread is done with this buffer
+    if (threadIdx.x == 0) ring_issue(ring, sc, sq + 2);   // refill it with the tile after next
+    ring.seq = sq + 1;
+  }
+  return cnt;
+}
+
 // One closest-hit query for the renderer: unit direction, t in world units.
-template <bool EXACT, int STRIDE>
-__device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulonglong2* s_pairs, const CandList<STRIDE>& L,
-                                                float ox, float oy, float oz, float dx, float dy, float dz,
-                                                float tmin, int self_id) {
+template <bool EXACT, bool TILED, int STRIDE>
+__device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulonglong2* s_pairs, TileRing& ring,
+                                                const CandList<STRIDE>& L, bool has_ray, float ox, float oy, float oz,
+                                                float dx, float dy, float dz, float tmin, int self_id) {
   const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
   Hit h;
   h.id = -1;
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+    const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
       fold_full_fast<STRIDE>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin, self_id, &best);
     });
-    resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, best);
-    if (best.id >= 0) {
-      h.id = best.id;
-      h.t = best.t;
-      finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+    if (has_ray) {
+      resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, best);
+      if (best.id >= 0) {
+        h.id = best.id;
+        h.t = best.t;
+        finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+      }
     }
   } else {
     const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
     ExactBest best{(double)CUDART_INF, -1};
-    int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+    const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
       fold_full_exact<STRIDE>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, &best);
     });
-    resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, best);
-    if (best.id >= 0) {
+    if (has_ray) resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, best);
+    if (has_ray && best.id >= 0) {
       const float4 g = __ldg(&sc.geom[best.id]);
       const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
       const double r = g.w;
@@ -130,17 +211,19 @@ __device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulo
 
 // ---------------------------------------------------------------------------------------
 // K1
-template <bool EXACT>
 #ifndef UECRT_K1_MINB
 #define UECRT_K1_MINB 3          // CTAs per SM the register allocator must allow (tuning knob; 3 measured best)
 #endif
-__global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(const RenderArgs a) {
+// shared memory: RESIDENT [16 B mbarrier][(npairs+2)*32 B pairs][lists]; TILED [32 B: 2 mbarriers][2 tile buffers][lists]
+template <bool EXACT, bool TILED>
+__global__ void __launch_bounds__(kRenderThreads, EXACT ? 2 : UECRT_K1_MINB) k_render_paths(const RenderArgs a) {   // FP64 resolve needs the registers
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  const uint32_t pair_bytes = (uint32_t)(a.sc.npairs + 2) * 32u;   // one tile + its prefetch pad group
   ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
-  const uint32_t pair_bytes = (uint32_t)(a.sc.npairs + 2) * 32u;   // + the prefetch pad group
-  uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + 16 + pair_bytes);
-  stage_scene_tma(bar, s_pairs, a.sc.pairs, pair_bytes);
+  uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + (TILED ? 32u + 2u * pair_bytes : 16u + pair_bytes));
+  TileRing ring{};
+  if (TILED) ring_init(ring, a.sc, smem_raw);
+  else stage_scene_tma(reinterpret_cast<uint64_t*>(smem_raw), s_pairs, a.sc.pairs, pair_bytes);
 
   const CandList<kRenderThreads> L{s_lists + threadIdx.x};
   const unsigned lane = threadIdx.x & 31u;
@@ -182,7 +265,7 @@ __global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(
         }
       }
     }
-    if (__all_sync(0xffffffffu, done)) break;
+    if (TILED ? __syncthreads_and(done) : __all_sync(0xffffffffu, done)) break;   // TILED: the whole CTA sweeps together
 
     // ---- start the next sample of this lane's item: camera ray (source.cpp:154-165, camera.hpp:29-32)
     if (!active && !done) {
@@ -223,9 +306,13 @@ __global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(
     }
 
     // ---- one path segment: closest hit + scatter (raytracer.hpp:27-36)
+    Hit h;
+    h.id = -1;
+    if (TILED || active)
+      h = closest_hit_unit<EXACT, TILED, kRenderThreads>(a.sc, s_pairs, ring, L, active, ox, oy, oz, dx, dy, dz,
+                                                         0.001f * dlen, self_id);
     if (active) {
       ++n_rays;
-      const Hit h = closest_hit_unit<EXACT, kRenderThreads>(a.sc, s_pairs, L, ox, oy, oz, dx, dy, dz, 0.001f * dlen, self_id);
       float rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
       bool ended = true;
       if (h.id < 0) {
@@ -266,6 +353,7 @@ __global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(
     }
   }
 
+  if (TILED) ring_drain(ring);
   if (a.count_stats) {
     unsigned r = n_rays, p = n_paths;
 #pragma unroll
@@ -278,25 +366,33 @@ __global__ void __launch_bounds__(kRenderThreads, UECRT_K1_MINB) k_render_paths(
 }
 
 // ---------------------------------------------------------------------------------------
-// K2: closest hit on caller rays.  One thread per ray, same scan + resolve as K1.
-template <bool EXACT>
+// K2: closest hit on caller rays.  One thread per ray, same scan + resolve as K1.  In TILED mode the
+// CTA sweeps the tile ring once per batch of blockDim rays, so every thread runs the same number of
+// batches (threads past the end of the ray array carry has_ray = false).
+template <bool EXACT, bool TILED>
 __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene sc, unsigned long long n_rays,
                                                                const float* __restrict__ o, const float* __restrict__ d,
                                                                double tmin, double tmax, double* __restrict__ t_out,
                                                                double* __restrict__ n_out, int32_t* __restrict__ id_out,
                                                                uint8_t* __restrict__ ff_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  const uint32_t pair_bytes = (uint32_t)(sc.npairs + 2) * 32u;     // one tile + its prefetch pad group
   ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
-  const uint32_t pair_bytes = (uint32_t)(sc.npairs + 2) * 32u;     // + the prefetch pad group
-  uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + 16 + pair_bytes);
-  stage_scene_tma(bar, s_pairs, sc.pairs, pair_bytes);
+  uint16_t* s_lists = reinterpret_cast<uint16_t*>(smem_raw + (TILED ? 32u + 2u * pair_bytes : 16u + pair_bytes));
+  TileRing ring{};
+  if (TILED) ring_init(ring, sc, smem_raw);
+  else stage_scene_tma(reinterpret_cast<uint64_t*>(smem_raw), s_pairs, sc.pairs, pair_bytes);
   const CandList<kHitsThreads> L{s_lists + threadIdx.x};
 
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    const float ox = o[3 * i], oy = o[3 * i + 1], oz = o[3 * i + 2];
-    const float rx = d[3 * i], ry = d[3 * i + 1], rz = d[3 * i + 2];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long batches = (n_rays + stride - 1) / stride;
+  for (unsigned long long b = 0; b < batches; ++b) {
+    const unsigned long long i = b * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool has_ray = i < n_rays;
+    if (!TILED && !has_ray) break;
+    const unsigned long long j = has_ray ? i : 0;
+    const float ox = o[3 * j], oy = o[3 * j + 1], oz = o[3 * j + 2];
+    const float rx = d[3 * j], ry = d[3 * j + 1], rz = d[3 * j + 2];
     const float dlen = sqrtf(fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
     const float inv = 1.0f / dlen;
     const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
@@ -307,11 +403,11 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
     if (!EXACT) {
       const float tmin_w = (float)tmin * dlen;
       FastBest best{(float)tmax * dlen, -1};
-      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+      const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
         fold_full_fast<kHitsThreads>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
       });
-      resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
-      if (best.id >= 0) {
+      if (has_ray) resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
+      if (has_ray && best.id >= 0) {
         Hit h; h.id = best.id; h.t = best.t;
         finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
         id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
@@ -320,11 +416,11 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
       const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
       const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
       ExactBest best{tmax, -1};
-      int cnt = scan_pairs(s_pairs, sc.npairs, 0, sr, L, [&](int c) {
+      const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
         fold_full_exact<kHitsThreads>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
       });
-      resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
-      if (best.id >= 0) {
+      if (has_ray) resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
+      if (has_ray && best.id >= 0) {
         const float4 g = __ldg(&sc.geom[best.id]);
         const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
                      pz = __dadd_rn(Oz, __dmul_rn(Dz, best.t));                                   // ray.hpp:16-19
@@ -337,9 +433,12 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
         id = best.id; t = best.t;
       }
     }
-    t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
-    id_out[i] = id; ff_out[i] = front ? 1 : 0;
+    if (has_ray) {
+      t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
+      id_out[i] = id; ff_out[i] = front ? 1 : 0;
+    }
   }
+  if (TILED) ring_drain(ring);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -387,42 +486,64 @@ __global__ void k_philox(unsigned long long n, uint32_t k0, uint32_t k1, const u
 
 // ---------------------------------------------------------------------------------------
 // host launchers
-size_t render_smem_bytes(int npairs, int threads) {
-  return 16 + (size_t)(npairs + 2) * 32 + (size_t)kListCap * threads * sizeof(uint16_t);
+size_t render_smem_bytes(int npairs, int ntiles, int threads) {
+  const size_t tile = (size_t)(npairs + 2) * 32, lists = (size_t)kListCap * threads * sizeof(uint16_t);
+  return ntiles > 1 ? 32 + 2 * tile + lists : 16 + tile + lists;
 }
 
-cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render) {
+// max_blocks_per_sm[0] = fast variant, [1] = exact variant
+cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled) {
   cudaError_t e;
   const int optin = 232448;
-  if ((e = cudaFuncSetAttribute(k_render_paths<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_render_paths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_primary_hits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_primary_hits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  static bool attrs_set[16] = {};
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if (dev < 16 && !attrs_set[dev]) {
+#define UECRT_SET(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+    UECRT_SET((k_render_paths<false, false>)) UECRT_SET((k_render_paths<true, false>))
+    UECRT_SET((k_render_paths<false, true>)) UECRT_SET((k_render_paths<true, true>))
+    UECRT_SET((k_primary_hits<false, false>)) UECRT_SET((k_primary_hits<true, false>))
+    UECRT_SET((k_primary_hits<false, true>)) UECRT_SET((k_primary_hits<true, true>))
+#undef UECRT_SET
+    attrs_set[dev] = true;
+  }
   cudaFuncAttributes fa;
-  if ((e = cudaFuncGetAttributes(&fa, k_render_paths<false>)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, tiled ? k_render_paths<false, true> : k_render_paths<false, false>)) != cudaSuccess) return e;
   if (regs_render) *regs_render = fa.numRegs;
-  int nb = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_paths<false>, kRenderThreads, smem_render)) != cudaSuccess) return e;
-  if (max_blocks_per_sm) *max_blocks_per_sm = nb;
+  // CTAs per SM: the minimum over the fast and the exact variant, so one grid size serves both
+  int nb = 1 << 30;
+  for (int exact = 0; exact < 2; ++exact) {
+    int n1 = 0;
+    if (tiled && exact) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<true, true>, kRenderThreads, smem_render);
+    else if (tiled) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<false, true>, kRenderThreads, smem_render);
+    else if (exact) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<true, false>, kRenderThreads, smem_render);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<false, false>, kRenderThreads, smem_render);
+    if (e != cudaSuccess) return e;
+    if (exact == 0 && max_blocks_per_sm) max_blocks_per_sm[0] = n1;
+    if (exact == 1 && max_blocks_per_sm) max_blocks_per_sm[1] = n1;
+    nb = n1 < nb ? n1 : nb;
+  }
   return cudaSuccess;
 }
 
 void launch_render_paths(const RenderArgs& a, bool exact, int blocks, int threads, size_t smem, cudaStream_t st) {
-  if (exact)
-    k_render_paths<true><<<blocks, threads, smem, st>>>(a);
-  else
-    k_render_paths<false><<<blocks, threads, smem, st>>>(a);
+  const bool tiled = a.sc.ntiles > 1;
+  if (exact && tiled) k_render_paths<true, true><<<blocks, threads, smem, st>>>(a);
+  else if (exact) k_render_paths<true, false><<<blocks, threads, smem, st>>>(a);
+  else if (tiled) k_render_paths<false, true><<<blocks, threads, smem, st>>>(a);
+  else k_render_paths<false, false><<<blocks, threads, smem, st>>>(a);
 }
 
 void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
                          double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, cudaStream_t st) {
-  const size_t smem = render_smem_bytes(sc.npairs, kHitsThreads);
+  const size_t smem = render_smem_bytes(sc.npairs, sc.ntiles, kHitsThreads);
   unsigned long long want = (n_rays + kHitsThreads - 1) / kHitsThreads;
   const int blocks = (int)(want < 1 ? 1 : (want > 148ull * 16 ? 148ull * 16 : want));
-  if (exact)
-    k_primary_hits<true><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
-  else
-    k_primary_hits<false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  const bool tiled = sc.ntiles > 1;
+  if (exact && tiled) k_primary_hits<true, true><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  else if (exact) k_primary_hits<true, false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  else if (tiled) k_primary_hits<false, true><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  else k_primary_hits<false, false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
 }
 
 void launch_resolve(const float4* accum, uint32_t n_pixels, uint32_t spp, uint8_t* rgb, cudaStream_t st) {

@@ -7,7 +7,8 @@ namespace uecrt {
 
 struct DeviceScene {
   const ulonglong2* pairs;   // global copy of the packed pairs (2 x 16 B per pair), staged to smem by TMA
-  int npairs;                // padded, multiple of 8; the buffer holds npairs + 2 (prefetch pad)
+  int npairs;                // pairs per TILE (multiple of 8); every tile is stored with npairs + 2 (prefetch pad)
+  int ntiles;                // 1: the whole scene is resident in shared memory; >1: swept through a 2-buffer ring
   int n;                     // spheres
   const float4* geom;        // {cx,cy,cz,r}
   const uint32_t* mat_type;
@@ -37,7 +38,7 @@ struct RenderArgs {
 constexpr int kRenderThreads = 256;
 constexpr int kHitsThreads = 128;
 
-size_t render_smem_bytes(int npairs, int threads);
+size_t render_smem_bytes(int npairs, int ntiles, int threads);
 
 void launch_render_paths(const RenderArgs& a, bool exact, int blocks, int threads, size_t smem, cudaStream_t st);
 void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,
@@ -48,6 +49,6 @@ void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4
                     const float* p, const float* nrm, const uint8_t* ff, const float* uniforms4,
                     uint8_t* scattered, float* att, float* o_out, float* d_out, cudaStream_t st);
 void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st);
-cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render);
+cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled);
 
 }  // namespace uecrt

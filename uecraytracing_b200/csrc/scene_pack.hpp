@@ -1,6 +1,7 @@
 // scene_pack.hpp -- host-side flattening of the sphere list into the scan layout.
 //
-// Per sphere PAIR (2i, 2i+1), 32 bytes, read in the K1/K2 scan as two broadcast LDS.128:
+// Per sphere PAIR (2i, 2i+1), 32 bytes, read in the K1/K2 scan as two broadcast LDS.128
+// (the scene is cut into TILES of tile_pairs pairs; one tile when it fits in shared memory):
 //     A = { -cx0, -cx1, -cy0, -cy1 }      B = { -cz0, -cz1, nk0, nk1 }
 // with  nk = -(|c|^2 - r^2) + bound_sphere   (computed in double, rounded UP to float).
 //
@@ -27,9 +28,11 @@ constexpr int kPairUnroll = 8;   // pairs per unrolled scan trip (2 iterations x
 constexpr int kPairPad = 2;      // one extra never-hit group after the last, read by the scan's prefetch
 
 struct PackedScene {
-  uint32_t n = 0;        // spheres
-  uint32_t npairs = 0;   // padded pair count (multiple of kPairUnroll) the scan loops over
-  std::vector<float> pairs;   // (npairs + kPairPad) * 8 floats
+  uint32_t n = 0;           // spheres
+  uint32_t tile_pairs = 0;  // pairs the scan loops over per tile (multiple of kPairUnroll)
+  uint32_t ntiles = 0;      // 1 = the whole scene is one resident tile
+  std::vector<float> pairs; // ntiles * (tile_pairs + kPairPad) * 8 floats; every tile carries its own prefetch pad
+  size_t tile_bytes() const { return (size_t)(tile_pairs + kPairPad) * 32; }
   size_t bytes() const { return pairs.size() * sizeof(float); }
 };
 
@@ -39,28 +42,38 @@ inline float round_up_to_float(double v) {
   return f;
 }
 
-inline PackedScene pack_scene(const uecrt_scene& sc) {
+// tile_spheres == 0: one tile holding everything.  Otherwise tiles of that many spheres (rounded up
+// to a whole number of unrolled scan trips); sphere i lives in tile i / (2*tile_pairs).
+inline PackedScene pack_scene(const uecrt_scene& sc, uint32_t tile_spheres = 0) {
   PackedScene p;
   p.n = sc.n;
   uint32_t np = (sc.n + 1) / 2;
   np = (np + kPairUnroll - 1) / kPairUnroll * kPairUnroll;
   if (np == 0) np = kPairUnroll;
-  p.npairs = np;
-  p.pairs.assign((size_t)(np + kPairPad) * 8, 0.0f);
+  if (tile_spheres == 0 || (tile_spheres + 1) / 2 >= np) {
+    p.tile_pairs = np;
+    p.ntiles = 1;
+  } else {
+    uint32_t tp = (tile_spheres + 1) / 2;
+    tp = (tp + kPairUnroll - 1) / kPairUnroll * kPairUnroll;
+    p.tile_pairs = tp;
+    p.ntiles = (np + tp - 1) / tp;
+  }
+  const uint32_t stride = p.tile_pairs + kPairPad;
+  p.pairs.assign((size_t)p.ntiles * stride * 8, 0.0f);
+  // default-fill with never-hit pairs: k = +1e30 -> f = -1e30 < P for every ray
+  for (size_t q = 0; q < (size_t)p.ntiles * stride; ++q) { p.pairs[q * 8 + 6] = -1e30f; p.pairs[q * 8 + 7] = -1e30f; }
   const double u = 5.9604644775390625e-8;   // 2^-24
-  for (uint32_t i = 0; i < (np + kPairPad) * 2; ++i) {
-    float ncx = 0.f, ncy = 0.f, ncz = 0.f, nk = -1e30f;   // padding: cc = +1e30 -> never a candidate
-    if (i < sc.n) {
-      const double cx = sc.geom[i].x, cy = sc.geom[i].y, cz = sc.geom[i].z, r = sc.geom[i].w;
-      const double c2 = cx * cx + cy * cy + cz * cz;
-      const double k = c2 - r * r;
-      const double bound = 88.0 * u * c2 + 10.0 * u * r * r;
-      ncx = -sc.geom[i].x; ncy = -sc.geom[i].y; ncz = -sc.geom[i].z;
-      nk = round_up_to_float(-k + bound);
-    }
+  for (uint32_t i = 0; i < sc.n; ++i) {
+    const double cx = sc.geom[i].x, cy = sc.geom[i].y, cz = sc.geom[i].z, r = sc.geom[i].w;
+    const double c2 = cx * cx + cy * cy + cz * cz;
+    const double k = c2 - r * r;
+    const double bound = 88.0 * u * c2 + 10.0 * u * r * r;
     const uint32_t pair = i / 2, half = i & 1;
-    float* q = &p.pairs[(size_t)pair * 8];
-    q[0 + half] = ncx; q[2 + half] = ncy; q[4 + half] = ncz; q[6 + half] = nk;
+    const uint32_t tile = pair / p.tile_pairs, within = pair % p.tile_pairs;
+    float* q = &p.pairs[((size_t)tile * stride + within) * 8];
+    q[0 + half] = -sc.geom[i].x; q[2 + half] = -sc.geom[i].y; q[4 + half] = -sc.geom[i].z;
+    q[6 + half] = round_up_to_float(-k + bound);
   }
   return p;
 }

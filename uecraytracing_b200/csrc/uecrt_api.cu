@@ -104,7 +104,8 @@ struct uecrt_ctx {
   unsigned long long* d_counters = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
-  int sm_count = 0, sm_clock_khz = 0, regs = 0, blocks_per_sm = 0;
+  int sm_count = 0, sm_clock_khz = 0, regs = 0;
+  int blocks_per_sm[2] = {0, 0};   // [0] fast K1, [1] exact K1
   int last_blocks = 0;
   size_t smem = 0;
   uint32_t n = 0;
@@ -115,12 +116,24 @@ struct uecrt_ctx {
 
 namespace {
 
+std::atomic<uint32_t> g_tile_spheres{0};   // 0 = automatic (uecrt_set_tile_spheres)
+constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists = 73 KB -> 3 CTAs per SM
+constexpr size_t kSmemOptin = 232448;
+
 int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
-  const uecrt::PackedScene ps = uecrt::pack_scene(*scene);
+  // resident while 3 CTAs of K1 still fit on an SM (scenes up to ~4000 spheres); beyond that the
+  // scene is swept in 32 KB tiles, which keeps 3 CTAs/SM (measured on the 10k-sphere scene: 66% of
+  // FP32 peak tiled vs 62% resident at 1 CTA/SM) and has no upper bound but the 16-bit list index
+  uint32_t tile = g_tile_spheres.load();
+  if (tile == 0) {
+    const uecrt::PackedScene whole = uecrt::pack_scene(*scene, 0);
+    if (uecrt::render_smem_bytes((int)whole.tile_pairs, 1, uecrt::kRenderThreads) > kSmemOptin / 3 - 1024) tile = kAutoTileSpheres;
+  }
+  const uecrt::PackedScene ps = uecrt::pack_scene(*scene, tile);
   const size_t pair_bytes = ps.bytes();
-  const size_t smem_need = uecrt::render_smem_bytes((int)ps.npairs, uecrt::kRenderThreads);
-  if (smem_need > 232448)
-    return fail(UECRT_ERR_INVALID, "scene of %u spheres needs %zu B of shared memory per CTA (max 232448)", scene->n, smem_need);
+  const size_t smem_need = uecrt::render_smem_bytes((int)ps.tile_pairs, (int)ps.ntiles, uecrt::kRenderThreads);
+  if (smem_need > kSmemOptin)
+    return fail(UECRT_ERR_INVALID, "tile of %u sphere pairs needs %zu B of shared memory per CTA (max %zu)", ps.tile_pairs, smem_need, kSmemOptin);
   const uint32_t n_alloc = std::max<uint32_t>(scene->n, 1);
   if (pair_bytes > c->cap_pairs) {             // grow-only: a reused context re-uploads without cudaMalloc
     cudaFree(c->d_pairs); c->d_pairs = nullptr; c->cap_pairs = 0;
@@ -143,7 +156,8 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
   }
   c->n = scene->n;
   c->sc.pairs = static_cast<const ulonglong2*>(c->d_pairs);
-  c->sc.npairs = (int)ps.npairs;
+  c->sc.npairs = (int)ps.tile_pairs;
+  c->sc.ntiles = (int)ps.ntiles;
   c->sc.n = (int)scene->n;
   c->sc.geom = static_cast<const float4*>(c->d_geom);
   c->sc.mat_type = static_cast<const uint32_t*>(c->d_mat_type);
@@ -187,9 +201,9 @@ int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* ca
     cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, c->device);
     c->configured = true;
   }
-  if ((e = uecrt::configure_kernels(&c->regs, &c->blocks_per_sm, c->smem)) != cudaSuccess)
+  if ((e = uecrt::configure_kernels(&c->regs, c->blocks_per_sm, c->smem, c->sc.ntiles > 1)) != cudaSuccess)
     return fail(UECRT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e));
-  if (c->blocks_per_sm < 1) return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem);
+  if (c->blocks_per_sm[0] < 1 || c->blocks_per_sm[1] < 1) return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem);
   c->timed = false;
   return UECRT_OK;
 }
@@ -279,10 +293,11 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
   CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
-  const int blocks = ctx->sm_count * ctx->blocks_per_sm;
+  const bool exact = (p->flags & UECRT_FLAG_EXACT_HITS) != 0;
+  const int blocks = ctx->sm_count * ctx->blocks_per_sm[exact ? 1 : 0];
   ctx->last_blocks = blocks;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  uecrt::launch_render_paths(a, (p->flags & UECRT_FLAG_EXACT_HITS) != 0, blocks, uecrt::kRenderThreads, ctx->smem, st);
+  uecrt::launch_render_paths(a, exact, blocks, uecrt::kRenderThreads, ctx->smem, st);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->timed = true;
@@ -295,6 +310,7 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   out->sm_count = ctx->sm_count; out->sm_clock_khz = ctx->sm_clock_khz;
   out->k1_blocks = ctx->last_blocks; out->k1_threads = uecrt::kRenderThreads;
   out->k1_smem_bytes = (int32_t)ctx->smem; out->k1_regs = ctx->regs;
+  out->tiles = ctx->sc.ntiles; out->tile_spheres = ctx->sc.npairs * 2;
   if (!ctx->timed) return UECRT_OK;
   CUDA_TRY(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;
@@ -526,6 +542,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 }
 
 void uecrt_release(void) { release_workspaces(); }
+void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
 
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
                        double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
