@@ -274,6 +274,11 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"]          # one ncu --set full capture, per launch
+        except Exception:
+            traffic = None
         sm_max = peaks.get("sm_max_mhz", 1965.0)
         peak = 2 * 128 * st["sm_count"] * sm_max * 1e6 / 1e12
         rays_per_launch = rays / max(args.steps, 1) / max(world, 1)
@@ -284,7 +289,7 @@ def main():
                "e2e": {"value": samples_per_step / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": args.steps * (2 if rank == 0 else 1),
                "roofline": {"bound": "fp32", "kernel": "k_render_paths", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak if peak else None, "traffic": None,
+                            "frac": achieved / peak if peak else None, "traffic": traffic,
                             "peak_source": f"2 FLOP x 128 lanes x {st['sm_count']} SMs x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                            "FFMA microbenchmark measured 73.3 TFLOP/s (profiles/ubench_r1.log)",
                             "algorithmic": "18 FLOP per ray-sphere test x spheres x rays traced (kernel counter)",
