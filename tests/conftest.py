@@ -68,3 +68,20 @@ def primary_rays(cam, W, H, jitter=None):
     d = ll[None] + uu[:, None] * hor[None] + vv[:, None] * ver[None] - org[None]
     o = np.broadcast_to(org, d.shape)
     return np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+
+
+def read_png_rgb(path):
+    """Decode an 8-bit RGB PNG written by uecrt_host_write_png (single IDAT, filter 0 on every row)."""
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h = int.from_bytes(raw[16:20], "big"), int.from_bytes(raw[20:24], "big")
+    pos, idat = 8, b""
+    while pos < len(raw):
+        n = int.from_bytes(raw[pos:pos + 4], "big"); typ = raw[pos + 4:pos + 8]
+        if typ == b"IDAT":
+            idat += raw[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    assert np.all(rows[:, 0] == 0)
+    return rows[:, 1:].reshape(h, w, 3)

@@ -16,6 +16,8 @@ for exact in (True, False):
     t, n, i, f = u.primary_hits(sc, o, d, exact=exact)
     print('exact' if exact else 'fast ', 'idx mismatches', int((i != io).sum()), 'of', len(i))
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+import os
+if os.environ.get("UECRT_RAYS"): u.set_rays_per_thread(int(os.environ["UECRT_RAYS"]))
 for exact in (False, False, True):
     rgb, acc, st = u.render(sc, cam, 1200, spp, 50, seed=3, exact=exact, return_accum=True)
     n = 1200 * 675 * spp

@@ -42,7 +42,7 @@ lib_path = os.environ.get("UECRT_LIB") or os.path.join(os.path.dirname(os.path.a
 
 # every symbol include/uecrt.h and include/uecrt_host.h declare
 EXPORTS = [
-    "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_primary_hits", "uecrt_scatter",
+    "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_primary_hits", "uecrt_scatter",
     "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_ctx_set_scene", "uecrt_accumulate_device", "uecrt_resolve_device",
     "uecrt_ctx_stats", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
     "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox",
@@ -62,6 +62,8 @@ def _load():
     L.uecrt_release.restype = None
     L.uecrt_set_tile_spheres.argtypes = [u32]
     L.uecrt_set_tile_spheres.restype = None
+    L.uecrt_set_rays_per_thread.argtypes = [C.c_int]
+    L.uecrt_set_rays_per_thread.restype = None
     L.uecrt_primary_hits.argtypes = [vp, u64, vp, vp, dbl, dbl, C.c_int, vp, vp, vp, vp]
     L.uecrt_scatter.argtypes = [u64] + [vp] * 11
     L.uecrt_philox.argtypes = [u64, u64, vp, vp]

@@ -184,3 +184,8 @@ def philox_host(seed, counter4):
 def set_tile_spheres(n):
     """0 = automatic residency/tiling; n > 0 forces shared-memory tiles of n spheres (see include/uecrt.h)."""
     lib.uecrt_set_tile_spheres(int(n))
+
+
+def set_rays_per_thread(n):
+    """Paths per K1 thread sharing one scene scan (1 or 2); applies to scenes loaded afterwards."""
+    lib.uecrt_set_rays_per_thread(int(n))

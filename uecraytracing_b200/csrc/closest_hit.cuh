@@ -169,75 +169,97 @@ __device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, c
 // Phase 1: the scan.  pairs: shared memory, 2 x 16 B per sphere pair
 //   A = {-cx0, -cx1, -cy0, -cy1},  B = {-cz0, -cz1, nk0, nk1},  nk = -(|c|^2 - r^2) + bound
 // Two pairs (4 spheres) form a GROUP; npairs is a multiple of 8 and the host appends one more
-// never-hit group so the loop can prefetch group g+1 unconditionally.  Per group the loop issues
-// 4 LDS.128 for the NEXT group (software pipelining: the loads are in flight across this
-// group's math), 14 packed FP32 ops in two interleaved dependency chains and two 3-input integer
-// max; every second group ends with the compare + branch.  `index_base` is added to stored
-// indices (tile offset when the scene is swept in tiles) and `cnt_in` is the number of candidates
-// already in the list.  When the list is nearly full the FULL callback folds it into the running
-// best and the list restarts.
-template <int STRIDE, class OnFull>
-__device__ __forceinline__ int scan_pairs(const ulonglong2* __restrict__ pairs, int npairs, int index_base,
-                                          const ScanRay& r, const CandList<STRIDE>& L, int cnt_in, OnFull&& on_full) {
-  const unsigned long long dx2 = pk2(r.dx, r.dx), dy2 = pk2(r.dy, r.dy), dz2 = pk2(r.dz, r.dz);
-  const unsigned long long qx2 = pk2(r.nqx, r.nqx), qy2 = pk2(r.nqy, r.nqy), qz2 = pk2(r.nqz, r.nqz);
-  const int thr = r.thr;
+// never-hit group so the loop can prefetch group g+1 unconditionally.  A thread scans R rays at
+// once (R = 1 or 2): every sphere load, the loop control and the branch are shared by the R rays,
+// which is what amortises the non-FP32 instructions of the loop (each costs an FP32 issue slot).
+// Per 8 spheres the loop issues 8 LDS.128 for the NEXT iteration (software pipelining: the loads
+// are in flight across this iteration's math), R x 28 packed FP32 ops in 2R interleaved dependency
+// chains, R x 5 integer max, R compares and one branch.  `index_base` is added to stored indices
+// (tile offset when the scene is swept in tiles); cnt[r] carries the candidates already in ray r's
+// list.  When a list is nearly full the FULL callback folds it into that ray's running best and
+// the list restarts.
+template <int R, int STRIDE, class OnFull>
+__device__ __forceinline__ void scan_pairs(const ulonglong2* __restrict__ pairs, int npairs, int index_base,
+                                           const ScanRay (&ray)[R], const CandList<STRIDE> (&L)[R], int (&cnt)[R],
+                                           OnFull&& on_full) {
+  unsigned long long dx2[R], dy2[R], dz2[R], qx2[R], qy2[R], qz2[R];
+  int thr[R];
   // byte offset of the next free list entry (32-bit shared-memory arithmetic only)
   constexpr uint32_t kEntryBytes = (uint32_t)STRIDE * (uint32_t)sizeof(uint16_t);
   constexpr uint32_t kFullAt = (uint32_t)(kListCap - 8) * kEntryBytes;   // < 8 free entries left
-  unsigned char* const lbase = reinterpret_cast<unsigned char*>(L.base);
-  uint32_t ofs = (uint32_t)cnt_in * kEntryBytes;   // candidates carried over from earlier tiles
+  unsigned char* lbase[R];
+  uint32_t ofs[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    dx2[r] = pk2(ray[r].dx, ray[r].dx); dy2[r] = pk2(ray[r].dy, ray[r].dy); dz2[r] = pk2(ray[r].dz, ray[r].dz);
+    qx2[r] = pk2(ray[r].nqx, ray[r].nqx); qy2[r] = pk2(ray[r].nqy, ray[r].nqy); qz2[r] = pk2(ray[r].nqz, ray[r].nqz);
+    thr[r] = ray[r].thr;
+    lbase[r] = reinterpret_cast<unsigned char*>(L[r].base);
+    ofs[r] = (uint32_t)cnt[r] * kEntryBytes;   // candidates carried over from earlier tiles
+  }
 
-  // f for the four spheres of one group: two interleaved chains of 7 packed ops
-#define UECRT_GROUP_MATH(A0, B0, A1, B1, f0, f1, f2, f3)                                   \
+  // f for the four spheres of one group and ray r: two interleaved chains of 7 packed ops
+#define UECRT_GROUP_MATH(r, A0, B0, A1, B1, f0, f1, f2, f3)                                \
   {                                                                                        \
-    unsigned long long cd0 = mul2(A0.x, dx2);                                              \
-    unsigned long long cd1 = mul2(A1.x, dx2);                                              \
-    unsigned long long e0 = fma2(A0.x, qx2, B0.y);                                         \
-    unsigned long long e1 = fma2(A1.x, qx2, B1.y);                                         \
-    cd0 = fma2(A0.y, dy2, cd0);                                                            \
-    cd1 = fma2(A1.y, dy2, cd1);                                                            \
-    e0 = fma2(A0.y, qy2, e0);                                                              \
-    e1 = fma2(A1.y, qy2, e1);                                                              \
-    cd0 = fma2(B0.x, dz2, cd0);                                                            \
-    cd1 = fma2(B1.x, dz2, cd1);                                                            \
-    e0 = fma2(B0.x, qz2, e0);                                                              \
-    e1 = fma2(B1.x, qz2, e1);                                                              \
+    unsigned long long cd0 = mul2(A0.x, dx2[r]);                                           \
+    unsigned long long cd1 = mul2(A1.x, dx2[r]);                                           \
+    unsigned long long e0 = fma2(A0.x, qx2[r], B0.y);                                      \
+    unsigned long long e1 = fma2(A1.x, qx2[r], B1.y);                                      \
+    cd0 = fma2(A0.y, dy2[r], cd0);                                                         \
+    cd1 = fma2(A1.y, dy2[r], cd1);                                                         \
+    e0 = fma2(A0.y, qy2[r], e0);                                                           \
+    e1 = fma2(A1.y, qy2[r], e1);                                                           \
+    cd0 = fma2(B0.x, dz2[r], cd0);                                                         \
+    cd1 = fma2(B1.x, dz2[r], cd1);                                                         \
+    e0 = fma2(B0.x, qz2[r], e0);                                                           \
+    e1 = fma2(B1.x, qz2[r], e1);                                                           \
     const unsigned long long g0 = fma2(cd0, cd0, e0);                                      \
     const unsigned long long g1 = fma2(cd1, cd1, e1);                                      \
     asm("mov.b64 {%0, %1}, %2;" : "=r"(f0), "=r"(f1) : "l"(g0));                           \
     asm("mov.b64 {%0, %1}, %2;" : "=r"(f2), "=r"(f3) : "l"(g1));                           \
   }
-#define UECRT_PUSH(f, idx)                                                                 \
-  if (f >= thr) { *reinterpret_cast<uint16_t*>(lbase + ofs) = (uint16_t)(idx); ofs += kEntryBytes; }
+#define UECRT_PUSH(r, f, idx)                                                              \
+  if (f >= thr[r]) { *reinterpret_cast<uint16_t*>(lbase[r] + ofs[r]) = (uint16_t)(idx); ofs[r] += kEntryBytes; }
 
   const ulonglong2* p = pairs;
   ulonglong2 A0 = p[0], B0 = p[1], A1 = p[2], B1 = p[3];
   const int niter = npairs >> 2;          // 8 spheres per iteration; npairs is a multiple of 8
 #pragma unroll 2
   for (int it = 0; it < niter; ++it) {
-    int f0, f1, f2, f3, f4, f5, f6, f7;
+    int f[R][8], mlo[R], mhi[R];
     const ulonglong2 A2 = p[4], B2 = p[5], A3 = p[6], B3 = p[7];          // second group of this iteration
-    UECRT_GROUP_MATH(A0, B0, A1, B1, f0, f1, f2, f3)
+#pragma unroll
+    for (int r = 0; r < R; ++r) UECRT_GROUP_MATH(r, A0, B0, A1, B1, f[r][0], f[r][1], f[r][2], f[r][3])
     p += 8;
     A0 = p[0]; B0 = p[1]; A1 = p[2]; B1 = p[3];                            // first group of the next (padded)
-    UECRT_GROUP_MATH(A2, B2, A3, B3, f4, f5, f6, f7)
-    const int mlo = max(max(f0, f1), max(f2, f3));
-    const int mhi = max(max(f4, f5), max(f6, f7));
-    if (max(mlo, mhi) >= thr) {           // at least one of the 8 spheres is a candidate
-      if (ofs > kFullAt) { on_full((int)(ofs / kEntryBytes)); ofs = 0; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) UECRT_GROUP_MATH(r, A2, B2, A3, B3, f[r][4], f[r][5], f[r][6], f[r][7])
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mlo[r] = max(max(f[r][0], f[r][1]), max(f[r][2], f[r][3]));
+      mhi[r] = max(max(f[r][4], f[r][5]), max(f[r][6], f[r][7]));
+      any = any || (max(mlo[r], mhi[r]) >= thr[r]);
+    }
+    if (any) {                            // at least one of the 8 spheres is a candidate for one of the rays
       const int i0 = index_base + 8 * it;
-      if (mlo >= thr) {
-        UECRT_PUSH(f0, i0) UECRT_PUSH(f1, i0 + 1) UECRT_PUSH(f2, i0 + 2) UECRT_PUSH(f3, i0 + 3)
-      }
-      if (mhi >= thr) {
-        UECRT_PUSH(f4, i0 + 4) UECRT_PUSH(f5, i0 + 5) UECRT_PUSH(f6, i0 + 6) UECRT_PUSH(f7, i0 + 7)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (R > 1 && max(mlo[r], mhi[r]) < thr[r]) continue;
+        if (ofs[r] > kFullAt) { on_full(r, (int)(ofs[r] / kEntryBytes)); ofs[r] = 0; }
+        if (mlo[r] >= thr[r]) {
+          UECRT_PUSH(r, f[r][0], i0) UECRT_PUSH(r, f[r][1], i0 + 1) UECRT_PUSH(r, f[r][2], i0 + 2) UECRT_PUSH(r, f[r][3], i0 + 3)
+        }
+        if (mhi[r] >= thr[r]) {
+          UECRT_PUSH(r, f[r][4], i0 + 4) UECRT_PUSH(r, f[r][5], i0 + 5) UECRT_PUSH(r, f[r][6], i0 + 6) UECRT_PUSH(r, f[r][7], i0 + 7)
+        }
       }
     }
   }
 #undef UECRT_GROUP_MATH
 #undef UECRT_PUSH
-  return (int)(ofs / kEntryBytes);
+#pragma unroll
+  for (int r = 0; r < R; ++r) cnt[r] = (int)(ofs[r] / kEntryBytes);
 }
 
 // Hit record in FP32 (yk/hittable.hpp:16-28; id is the OBJECT index as in hittable_list.hpp:41)

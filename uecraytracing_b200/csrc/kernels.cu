@@ -143,80 +143,243 @@ __device__ __noinline__ void fold_full_exact(const float4* geom, uint16_t* base,
   resolve_exact(geom, L, cnt, ox, oy, oz, dx, dy, dz, a, tmin, *best);
 }
 
-// Candidate collection over the whole scene.  RESIDENT: one call of the scan on the resident
-// tile, no synchronisation.  TILED: block-synchronous sweep; EVERY thread of the CTA must call
-// this (has_ray = false for threads without a live ray: they only take part in the barriers).
-template <bool TILED, int STRIDE, class OnFull>
-__device__ __forceinline__ int collect_candidates(const DeviceScene& sc, const ulonglong2* s_pairs, TileRing& ring,
-                                                  const CandList<STRIDE>& L, bool has_ray, const ScanRay& sr,
-                                                  OnFull&& on_full) {
-  if (!TILED) return scan_pairs(s_pairs, sc.npairs, 0, sr, L, 0, on_full);
-  int cnt = 0;
+// Candidate collection over the whole scene for the R rays of a thread.  RESIDENT: one call of the
+// scan on the resident tile, no synchronisation.  TILED: block-synchronous sweep; EVERY thread of
+// the CTA must call this (threads without a live ray only take part in the barriers).
+template <bool TILED, int R, int STRIDE, class OnFull>
+__device__ __forceinline__ void collect_candidates(const DeviceScene& sc, const ulonglong2* s_pairs, TileRing& ring,
+                                                   const CandList<STRIDE> (&L)[R], bool any_ray, const ScanRay (&sr)[R],
+                                                   int (&cnt)[R], OnFull&& on_full) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) cnt[r] = 0;
+  if (!TILED) {
+    scan_pairs<R>(s_pairs, sc.npairs, 0, sr, L, cnt, on_full);
+    return;
+  }
   for (int t = 0; t < sc.ntiles; ++t) {
     const uint32_t sq = ring.seq;
     ring_wait(ring, sq);
-    if (has_ray)
-      cnt = scan_pairs(reinterpret_cast<const ulonglong2*>(ring.buf + (size_t)(sq & 1u) * ring.tile_bytes), sc.npairs,
-                       t * sc.npairs * 2, sr, L, cnt, on_full);
-    __syncthreads();                                   // every thread is done with this buffer
+    if (any_ray)
+      scan_pairs<R>(reinterpret_cast<const ulonglong2*>(ring.buf + (size_t)(sq & 1u) * ring.tile_bytes), sc.npairs,
+                    t * sc.npairs * 2, sr, L, cnt, on_full);
+    __syncthreads();                                      // every thread is done with this buffer
     if (threadIdx.x == 0) ring_issue(ring, sc, sq + 2);   // refill it with the tile after next
     ring.seq = sq + 1;
   }
-  return cnt;
 }
 
-// One closest-hit query for the renderer: unit direction, t in world units.
-template <bool EXACT, bool TILED, int STRIDE>
-__device__ __forceinline__ Hit closest_hit_unit(const DeviceScene& sc, const ulonglong2* s_pairs, TileRing& ring,
-                                                const CandList<STRIDE>& L, bool has_ray, float ox, float oy, float oz,
-                                                float dx, float dy, float dz, float tmin, int self_id) {
-  const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
-  Hit h;
-  h.id = -1;
+// What one closest-hit query needs: unit direction, t in world units.
+struct RayQuery {
+  float ox, oy, oz, dx, dy, dz, tmin;
+  int self_id;
+  bool live;
+};
+
+// R closest-hit queries of one thread (the renderer's form).
+template <bool EXACT, bool TILED, int R, int STRIDE>
+__device__ __forceinline__ void closest_hits(const DeviceScene& sc, const ulonglong2* s_pairs, TileRing& ring,
+                                             const CandList<STRIDE> (&L)[R], const RayQuery (&q)[R], Hit (&h)[R]) {
+  ScanRay sr[R];
+  int cnt[R];
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    sr[r] = make_scan_ray(q[r].ox, q[r].oy, q[r].oz, q[r].dx, q[r].dy, q[r].dz);
+    if (!q[r].live) sr[r].thr = 0x7f800000;     // +inf: a dead slot never produces a candidate
+    h[r].id = -1;
+    any = any || q[r].live;
+  }
   if (!EXACT) {
-    FastBest best{CUDART_INF_F, -1};
-    const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
-      fold_full_fast<STRIDE>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin, self_id, &best);
+    FastBest best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) best[r] = FastBest{CUDART_INF_F, -1};
+    collect_candidates<TILED, R>(sc, s_pairs, ring, L, any, sr, cnt, [&](int r, int c) {
+      // r is a compile-time constant after unrolling; the switch keeps best[] in registers
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (k == r)
+          fold_full_fast<STRIDE>(sc.geom, L[k].base, c, q[k].ox, q[k].oy, q[k].oz, q[k].dx, q[k].dy, q[k].dz, q[k].tmin,
+                                 q[k].self_id, &best[k]);
     });
-    if (has_ray) {
-      resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin, self_id, best);
-      if (best.id >= 0) {
-        h.id = best.id;
-        h.t = best.t;
-        finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!q[r].live) continue;
+      resolve_fast(sc.geom, L[r], cnt[r], q[r].ox, q[r].oy, q[r].oz, q[r].dx, q[r].dy, q[r].dz, q[r].tmin, q[r].self_id, best[r]);
+      if (best[r].id >= 0) {
+        h[r].id = best[r].id;
+        h[r].t = best[r].t;
+        finish_hit_fast(sc.geom, q[r].ox, q[r].oy, q[r].oz, q[r].dx, q[r].dy, q[r].dz, h[r]);
       }
     }
   } else {
-    const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
-    const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    ExactBest best{(double)CUDART_INF, -1};
-    const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
-      fold_full_exact<STRIDE>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, &best);
+    ExactBest best[R];
+    double a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      best[r] = ExactBest{(double)CUDART_INF, -1};
+      const double Dx = q[r].dx, Dy = q[r].dy, Dz = q[r].dz;
+      a[r] = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
+    }
+    collect_candidates<TILED, R>(sc, s_pairs, ring, L, any, sr, cnt, [&](int r, int c) {
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (k == r)
+          fold_full_exact<STRIDE>(sc.geom, L[k].base, c, (double)q[k].ox, (double)q[k].oy, (double)q[k].oz, (double)q[k].dx,
+                                  (double)q[k].dy, (double)q[k].dz, a[k], (double)q[k].tmin, &best[k]);
     });
-    if (has_ray) resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)tmin, best);
-    if (has_ray && best.id >= 0) {
-      const float4 g = __ldg(&sc.geom[best.id]);
-      const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
-      const double r = g.w;
-      double nx = (px - (double)g.x) / r, ny = (py - (double)g.y) / r, nz = (pz - (double)g.z) / r;   // sphere.hpp:44
-      const bool front = (Dx * nx + Dy * ny + Dz * nz) < 0;                                   // hittable.hpp:25
-      if (!front) { nx = -nx; ny = -ny; nz = -nz; }
-      h.id = best.id; h.t = (float)best.t; h.front = front;
-      h.px = (float)px; h.py = (float)py; h.pz = (float)pz;
-      h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!q[r].live) continue;
+      const double Ox = q[r].ox, Oy = q[r].oy, Oz = q[r].oz, Dx = q[r].dx, Dy = q[r].dy, Dz = q[r].dz;
+      resolve_exact(sc.geom, L[r], cnt[r], Ox, Oy, Oz, Dx, Dy, Dz, a[r], (double)q[r].tmin, best[r]);
+      if (best[r].id >= 0) {
+        const float4 g = __ldg(&sc.geom[best[r].id]);
+        const double px = Ox + Dx * best[r].t, py = Oy + Dy * best[r].t, pz = Oz + Dz * best[r].t;   // ray.hpp:16-19
+        const double rad = g.w;
+        double nx = (px - (double)g.x) / rad, ny = (py - (double)g.y) / rad, nz = (pz - (double)g.z) / rad;   // sphere.hpp:44
+        const bool front = (Dx * nx + Dy * ny + Dz * nz) < 0;                                     // hittable.hpp:25
+        if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+        h[r].id = best[r].id; h[r].t = (float)best[r].t; h[r].front = front;
+        h[r].px = (float)px; h[r].py = (float)py; h[r].pz = (float)pz;
+        h[r].nx = (float)nx; h[r].ny = (float)ny; h[r].nz = (float)nz;
+      }
     }
   }
-  return h;
 }
 
 // ---------------------------------------------------------------------------------------
 // K1
+// Per-slot path state: a thread owns RAYS independent paths ("slots").
+struct PathState {
+  bool active, done;
+  uint32_t pixel, s_next, s_end, sample, bounce, depth_left;
+  int self_id;
+  float acc_r, acc_g, acc_b, acc_n;
+  float ox, oy, oz, dx, dy, dz, dlen;
+  float thr_r, thr_g, thr_b;
+};
+
+// refill + start of the next sample for one slot; warp-convergent (uses __ballot_sync)
+__device__ __forceinline__ void slot_refill_and_start(PathState& p, const RenderArgs& a, unsigned lane,
+                                                      unsigned long long n_pixels, float inv_w, float inv_h,
+                                                      unsigned& n_paths) {
+  // lanes that finished an item publish it and pull the next one together: one atomicAdd per warp
+  const bool need_item = !p.active && !p.done && (p.s_next == p.s_end);
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need_item);
+  if (need_mask) {
+    if (need_item && p.acc_n > 0.f) {
+      red_add_v4(a.accum + p.pixel, p.acc_r, p.acc_g, p.acc_b, p.acc_n);
+      p.acc_r = p.acc_g = p.acc_b = p.acc_n = 0.f;
+    }
+    const int leader = __ffs(need_mask) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(need_mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (need_item) {
+      const unsigned long long w = base + __popc(need_mask & ((1u << lane) - 1u));
+      if (w < a.total_items) {
+        const unsigned long long q = w / n_pixels;
+        p.pixel = (uint32_t)(w - q * n_pixels);
+        p.s_next = a.sample_begin + (uint32_t)q * a.chunk;
+        const uint32_t lim = a.sample_begin + a.sample_count;
+        p.s_end = p.s_next + a.chunk < lim ? p.s_next + a.chunk : lim;
+      } else {
+        p.done = true;
+      }
+    }
+  }
+  // start the next sample of this slot's item: camera ray (source.cpp:154-165, camera.hpp:29-32)
+  if (!p.active && !p.done) {
+    p.sample = p.s_next++;
+    // pixel -> (row, column) without the ~20-instruction runtime integer divide: float reciprocal
+    // estimate (exact to +-1 for pixel < 2^24 * width) and one fix-up step each way
+    uint32_t py = (uint32_t)__fmul_rz((float)p.pixel, inv_w);
+    uint32_t px = p.pixel - py * a.width;
+    if ((int32_t)px < 0) { --py; px += a.width; }
+    if (px >= a.width) { ++py; px -= a.width; }
+    philox_out r = philox4x32_10(p.pixel, p.sample, 0u, 0u, a.key0, a.key1);
+    const float u = ((float)px + uecrt_u01(r.x)) * inv_w;
+    const float v = ((float)(a.height - py - 1u) + uecrt_u01(r.y)) * inv_h;
+    float tx = fmaf(v, a.cam.ver[0], fmaf(u, a.cam.hor[0], a.cam.ll[0]));
+    float ty = fmaf(v, a.cam.ver[1], fmaf(u, a.cam.hor[1], a.cam.ll[1]));
+    float tz = fmaf(v, a.cam.ver[2], fmaf(u, a.cam.hor[2], a.cam.ll[2]));
+    p.ox = a.cam.origin[0]; p.oy = a.cam.origin[1]; p.oz = a.cam.origin[2];
+    if (a.cam.lens > 0.f) {
+      // uniform point in the unit disk from the block's last two uniforms (polar map: r = sqrt(u),
+      // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop of the
+      // book (and of the CPU checker), but exactly two uniforms and no divergent retry loop.
+      const float rr = sqrt_fast(uecrt_u01(r.z)), phi = 6.28318530717958647692f * uecrt_u01(r.w);
+      const float rx = rr * __cosf(phi), ry = rr * __sinf(phi);
+      const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;
+      const float offx = fmaf(ly, a.cam.v[0], lx * a.cam.u[0]);
+      const float offy = fmaf(ly, a.cam.v[1], lx * a.cam.u[1]);
+      const float offz = fmaf(ly, a.cam.v[2], lx * a.cam.u[2]);
+      tx = tx - p.ox - offx; ty = ty - p.oy - offy; tz = tz - p.oz - offz;
+      p.ox += offx; p.oy += offy; p.oz += offz;
+    } else if (!a.cam.origin_is_zero) {
+      tx -= p.ox; ty -= p.oy; tz -= p.oz;
+    }
+    const float len2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+    const float inv = rsqrt_nr(len2);
+    p.dlen = len2 * inv;
+    p.dx = tx * inv; p.dy = ty * inv; p.dz = tz * inv;
+    p.thr_r = p.thr_g = p.thr_b = 1.f;
+    p.depth_left = a.max_depth;
+    p.self_id = -1;
+    p.bounce = 0;
+    p.active = p.depth_left > 0;
+    if (!p.active) { p.acc_n += 1.f; ++n_paths; }   // depth 0: black (raytracer.hpp:26)
+  }
+}
+
+// one path segment after its closest hit is known: scatter or terminate (raytracer.hpp:27-36)
+__device__ __forceinline__ void slot_shade(PathState& p, const Hit& h, const RenderArgs& a, unsigned& n_paths) {
+  float rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
+  bool ended = true;
+  if (h.id < 0) {
+    const float t = 0.5f * (p.dy + 1.0f);                       // raytracer.hpp:35
+    const float w0 = 1.0f - t;
+    rad_r = p.thr_r * fmaf(t, 0.5f, w0); rad_g = p.thr_g * fmaf(t, 0.7f, w0); rad_b = p.thr_b * (w0 + t);
+  } else {
+    ++p.bounce;
+    const uint32_t mt = __ldg(&a.sc.mat_type[h.id]);
+    const float4 mp = __ldg(&a.sc.mat_param[h.id]);
+    float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+    if (mt != UECRT_MAT_METAL || mp.w > 0.f) {
+      const philox_out r = philox4x32_10(p.pixel, p.sample, p.bounce, 0u, a.key0, a.key1);
+      u0 = uecrt_u01(r.x); u1 = uecrt_u01(r.y); u2 = uecrt_u01(r.z); u3 = uecrt_u01(r.w);
+    }
+    const ScatterOut s = scatter_material(mt, mp, p.dx, p.dy, p.dz, h.nx, h.ny, h.nz, h.front, u0, u1, u2, u3);
+    if (s.ok && p.depth_left > 1u) {                             // depth-1 == 0 returns black (raytracer.hpp:26)
+      p.thr_r *= s.ar; p.thr_g *= s.ag; p.thr_b *= s.ab;
+      p.ox = h.px; p.oy = h.py; p.oz = h.pz;
+      const float len2 = fmaf(s.dz, s.dz, fmaf(s.dy, s.dy, s.dx * s.dx));
+      const float inv = rsqrt_nr(len2);
+      p.dlen = len2 * inv;
+      p.dx = s.dx * inv; p.dy = s.dy * inv; p.dz = s.dz * inv;
+      p.self_id = h.id;
+      --p.depth_left;
+      ended = false;
+    }
+  }
+  if (ended) {
+    // a NaN radiance would hang the reference's math::sqrt (math.hpp:14); it contributes 0 here
+    p.acc_r += (rad_r == rad_r) ? rad_r : 0.f;
+    p.acc_g += (rad_g == rad_g) ? rad_g : 0.f;
+    p.acc_b += (rad_b == rad_b) ? rad_b : 0.f;
+    p.acc_n += 1.f;
+    ++n_paths;
+    p.active = false;
+  }
+}
+
 #ifndef UECRT_K1_MINB
-#define UECRT_K1_MINB 3          // CTAs per SM the register allocator must allow (tuning knob; 3 measured best)
+#define UECRT_K1_MINB 3          // CTAs per SM the register allocator must allow for the 1-ray fast kernel
 #endif
 // shared memory: RESIDENT [16 B mbarrier][(npairs+2)*32 B pairs][lists]; TILED [32 B: 2 mbarriers][2 tile buffers][lists]
-template <bool EXACT, bool TILED>
-__global__ void __launch_bounds__(kRenderThreads, EXACT ? 2 : UECRT_K1_MINB) k_render_paths(const RenderArgs a) {   // FP64 resolve needs the registers
+// lists: RAYS x kListCap x 256 uint16
+template <bool EXACT, bool TILED, int RAYS>
+__global__ void __launch_bounds__(kRenderThreads, (EXACT || RAYS > 1) ? 2 : UECRT_K1_MINB) k_render_paths(const RenderArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t pair_bytes = (uint32_t)(a.sc.npairs + 2) * 32u;   // one tile + its prefetch pad group
   ulonglong2* s_pairs = reinterpret_cast<ulonglong2*>(smem_raw + 16);
@@ -225,132 +388,47 @@ __global__ void __launch_bounds__(kRenderThreads, EXACT ? 2 : UECRT_K1_MINB) k_r
   if (TILED) ring_init(ring, a.sc, smem_raw);
   else stage_scene_tma(reinterpret_cast<uint64_t*>(smem_raw), s_pairs, a.sc.pairs, pair_bytes);
 
-  const CandList<kRenderThreads> L{s_lists + threadIdx.x};
+  CandList<kRenderThreads> L[RAYS];
+#pragma unroll
+  for (int s = 0; s < RAYS; ++s) L[s].base = s_lists + (size_t)s * kListCap * kRenderThreads + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long n_pixels = (unsigned long long)a.width * a.height;
   const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
 
-  bool active = false, done = false;
-  uint32_t pixel = 0, s_next = 0, s_end = 0, sample = 0, bounce = 0;
-  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_n = 0.f;
-  float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, dlen = 1.f;
-  float thr_r = 1.f, thr_g = 1.f, thr_b = 1.f;
-  uint32_t depth_left = 0;
-  int self_id = -1;
+  PathState st[RAYS];
+#pragma unroll
+  for (int s = 0; s < RAYS; ++s) {
+    st[s] = PathState{};
+    st[s].dz = 1.f; st[s].dlen = 1.f; st[s].self_id = -1;
+  }
   unsigned n_rays = 0, n_paths = 0;
 
   for (;;) {
-    // ---- refill: lanes that finished an item publish it and pull the next one together
-    const bool need_item = !active && !done && (s_next == s_end);
-    const unsigned need_mask = __ballot_sync(0xffffffffu, need_item);
-    if (need_mask) {
-      if (need_item && acc_n > 0.f) {
-        red_add_v4(a.accum + pixel, acc_r, acc_g, acc_b, acc_n);
-        acc_r = acc_g = acc_b = acc_n = 0.f;
-      }
-      const int leader = __ffs(need_mask) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(need_mask));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (need_item) {
-        const unsigned long long w = base + __popc(need_mask & ((1u << lane) - 1u));
-        if (w < a.total_items) {
-          const unsigned long long q = w / n_pixels;
-          pixel = (uint32_t)(w - q * n_pixels);
-          s_next = a.sample_begin + (uint32_t)q * a.chunk;
-          const uint32_t lim = a.sample_begin + a.sample_count;
-          s_end = s_next + a.chunk < lim ? s_next + a.chunk : lim;
-        } else {
-          done = true;
-        }
-      }
+    bool all_done = true;
+#pragma unroll
+    for (int s = 0; s < RAYS; ++s) {
+      slot_refill_and_start(st[s], a, lane, n_pixels, inv_w, inv_h, n_paths);
+      all_done = all_done && st[s].done;
     }
-    if (TILED ? __syncthreads_and(done) : __all_sync(0xffffffffu, done)) break;   // TILED: the whole CTA sweeps together
+    if (TILED ? __syncthreads_and(all_done) : __all_sync(0xffffffffu, all_done)) break;   // TILED: the whole CTA sweeps together
 
-    // ---- start the next sample of this lane's item: camera ray (source.cpp:154-165, camera.hpp:29-32)
-    if (!active && !done) {
-      sample = s_next++;
-      const uint32_t py = pixel / a.width, px = pixel - py * a.width;
-      philox_out r = philox4x32_10(pixel, sample, 0u, 0u, a.key0, a.key1);
-      const float u = ((float)px + uecrt_u01(r.x)) * inv_w;
-      const float v = ((float)(a.height - py - 1u) + uecrt_u01(r.y)) * inv_h;
-      float tx = fmaf(v, a.cam.ver[0], fmaf(u, a.cam.hor[0], a.cam.ll[0]));
-      float ty = fmaf(v, a.cam.ver[1], fmaf(u, a.cam.hor[1], a.cam.ll[1]));
-      float tz = fmaf(v, a.cam.ver[2], fmaf(u, a.cam.hor[2], a.cam.ll[2]));
-      ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
-      if (a.cam.lens > 0.f) {
-        // uniform point in the unit disk from the block's last two uniforms (polar map: r = sqrt(u),
-        // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop of the
-        // book (and of the CPU checker), but exactly two uniforms and no divergent retry loop.
-        const float rr = sqrt_fast(uecrt_u01(r.z)), phi = 6.28318530717958647692f * uecrt_u01(r.w);
-        const float rx = rr * __cosf(phi), ry = rr * __sinf(phi);
-        const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;
-        const float offx = fmaf(ly, a.cam.v[0], lx * a.cam.u[0]);
-        const float offy = fmaf(ly, a.cam.v[1], lx * a.cam.u[1]);
-        const float offz = fmaf(ly, a.cam.v[2], lx * a.cam.u[2]);
-        tx = tx - ox - offx; ty = ty - oy - offy; tz = tz - oz - offz;
-        ox += offx; oy += offy; oz += offz;
-      } else if (!a.cam.origin_is_zero) {
-        tx -= ox; ty -= oy; tz -= oz;
-      }
-      const float len2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-      const float inv = rsqrt_nr(len2);
-      dlen = len2 * inv;
-      dx = tx * inv; dy = ty * inv; dz = tz * inv;
-      thr_r = thr_g = thr_b = 1.f;
-      depth_left = a.max_depth;
-      self_id = -1;
-      bounce = 0;
-      active = depth_left > 0;
-      if (!active) { acc_n += 1.f; ++n_paths; }   // depth 0: black (raytracer.hpp:26)
+    // ---- closest hits of this thread's live slots: ONE scan over the scene for all of them
+    RayQuery q[RAYS];
+    Hit h[RAYS];
+    bool any_active = false;
+#pragma unroll
+    for (int s = 0; s < RAYS; ++s) {
+      q[s] = RayQuery{st[s].ox, st[s].oy, st[s].oz, st[s].dx, st[s].dy, st[s].dz, 0.001f * st[s].dlen, st[s].self_id, st[s].active};
+      h[s].id = -1;
+      any_active = any_active || st[s].active;
     }
-
-    // ---- one path segment: closest hit + scatter (raytracer.hpp:27-36)
-    Hit h;
-    h.id = -1;
-    if (TILED || active)
-      h = closest_hit_unit<EXACT, TILED, kRenderThreads>(a.sc, s_pairs, ring, L, active, ox, oy, oz, dx, dy, dz,
-                                                         0.001f * dlen, self_id);
-    if (active) {
-      ++n_rays;
-      float rad_r = 0.f, rad_g = 0.f, rad_b = 0.f;
-      bool ended = true;
-      if (h.id < 0) {
-        const float t = 0.5f * (dy + 1.0f);                       // raytracer.hpp:35
-        const float w0 = 1.0f - t;
-        rad_r = thr_r * fmaf(t, 0.5f, w0); rad_g = thr_g * fmaf(t, 0.7f, w0); rad_b = thr_b * (w0 + t);
-      } else {
-        ++bounce;
-        const uint32_t mt = __ldg(&a.sc.mat_type[h.id]);
-        const float4 mp = __ldg(&a.sc.mat_param[h.id]);
-        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-        if (mt != UECRT_MAT_METAL || mp.w > 0.f) {
-          const philox_out r = philox4x32_10(pixel, sample, bounce, 0u, a.key0, a.key1);
-          u0 = uecrt_u01(r.x); u1 = uecrt_u01(r.y); u2 = uecrt_u01(r.z); u3 = uecrt_u01(r.w);
-        }
-        const ScatterOut s = scatter_material(mt, mp, dx, dy, dz, h.nx, h.ny, h.nz, h.front, u0, u1, u2, u3);
-        if (s.ok && depth_left > 1u) {                             // depth-1 == 0 returns black (raytracer.hpp:26)
-          thr_r *= s.ar; thr_g *= s.ag; thr_b *= s.ab;
-          ox = h.px; oy = h.py; oz = h.pz;
-          const float len2 = fmaf(s.dz, s.dz, fmaf(s.dy, s.dy, s.dx * s.dx));
-          const float inv = rsqrt_nr(len2);
-          dlen = len2 * inv;
-          dx = s.dx * inv; dy = s.dy * inv; dz = s.dz * inv;
-          self_id = h.id;
-          --depth_left;
-          ended = false;
-        }
+    if (TILED || any_active) closest_hits<EXACT, TILED, RAYS>(a.sc, s_pairs, ring, L, q, h);
+#pragma unroll
+    for (int s = 0; s < RAYS; ++s)
+      if (st[s].active) {
+        ++n_rays;
+        slot_shade(st[s], h[s], a, n_paths);
       }
-      if (ended) {
-        // a NaN radiance would hang the reference's math::sqrt (math.hpp:14); it contributes 0 here
-        acc_r += (rad_r == rad_r) ? rad_r : 0.f;
-        acc_g += (rad_g == rad_g) ? rad_g : 0.f;
-        acc_b += (rad_b == rad_b) ? rad_b : 0.f;
-        acc_n += 1.f;
-        ++n_paths;
-        active = false;
-      }
-    }
   }
 
   if (TILED) ring_drain(ring);
@@ -382,7 +460,8 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
   TileRing ring{};
   if (TILED) ring_init(ring, sc, smem_raw);
   else stage_scene_tma(reinterpret_cast<uint64_t*>(smem_raw), s_pairs, sc.pairs, pair_bytes);
-  const CandList<kHitsThreads> L{s_lists + threadIdx.x};
+  CandList<kHitsThreads> L[1];
+  L[0].base = s_lists + threadIdx.x;
 
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   const unsigned long long batches = (n_rays + stride - 1) / stride;
@@ -396,17 +475,19 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
     const float dlen = sqrtf(fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
     const float inv = 1.0f / dlen;
     const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
-    const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
+    ScanRay sr[1] = {make_scan_ray(ox, oy, oz, dx, dy, dz)};
+    if (!has_ray) sr[0].thr = 0x7f800000;
+    int cnt[1];
     double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
     int id = -1;
     bool front = false;
     if (!EXACT) {
       const float tmin_w = (float)tmin * dlen;
       FastBest best{(float)tmax * dlen, -1};
-      const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
-        fold_full_fast<kHitsThreads>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
+      collect_candidates<TILED, 1>(sc, s_pairs, ring, L, has_ray, sr, cnt, [&](int, int c) {
+        fold_full_fast<kHitsThreads>(sc.geom, L[0].base, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
       });
-      if (has_ray) resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
+      if (has_ray) resolve_fast(sc.geom, L[0], cnt[0], ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
       if (has_ray && best.id >= 0) {
         Hit h; h.id = best.id; h.t = best.t;
         finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
@@ -416,10 +497,10 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
       const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
       const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
       ExactBest best{tmax, -1};
-      const int cnt = collect_candidates<TILED>(sc, s_pairs, ring, L, has_ray, sr, [&](int c) {
-        fold_full_exact<kHitsThreads>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
+      collect_candidates<TILED, 1>(sc, s_pairs, ring, L, has_ray, sr, cnt, [&](int, int c) {
+        fold_full_exact<kHitsThreads>(sc.geom, L[0].base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
       });
-      if (has_ray) resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
+      if (has_ray) resolve_exact(sc.geom, L[0], cnt[0], Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
       if (has_ray && best.id >= 0) {
         const float4 g = __ldg(&sc.geom[best.id]);
         const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
@@ -486,57 +567,56 @@ __global__ void k_philox(unsigned long long n, uint32_t k0, uint32_t k1, const u
 
 // ---------------------------------------------------------------------------------------
 // host launchers
-size_t render_smem_bytes(int npairs, int ntiles, int threads) {
-  const size_t tile = (size_t)(npairs + 2) * 32, lists = (size_t)kListCap * threads * sizeof(uint16_t);
+size_t render_smem_bytes(int npairs, int ntiles, int threads, int rays) {
+  const size_t tile = (size_t)(npairs + 2) * 32, lists = (size_t)rays * kListCap * threads * sizeof(uint16_t);
   return ntiles > 1 ? 32 + 2 * tile + lists : 16 + tile + lists;
 }
 
-// max_blocks_per_sm[0] = fast variant, [1] = exact variant
-cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled) {
+// Kernel table: [exact][tiled][rays-1]
+typedef void (*RenderKernel)(const RenderArgs);
+static RenderKernel render_kernel(bool exact, bool tiled, int rays) {
+  static const RenderKernel table[2][2][2] = {
+      {{k_render_paths<false, false, 1>, k_render_paths<false, false, 2>}, {k_render_paths<false, true, 1>, k_render_paths<false, true, 2>}},
+      {{k_render_paths<true, false, 1>, k_render_paths<true, false, 2>}, {k_render_paths<true, true, 1>, k_render_paths<true, true, 2>}}};
+  return table[exact ? 1 : 0][tiled ? 1 : 0][rays == 2 ? 1 : 0];
+}
+
+// max_blocks_per_sm[0] = fast variant, [1] = exact variant (for `rays` rays per thread)
+cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled, int rays) {
   cudaError_t e;
   const int optin = 232448;
   static bool attrs_set[16] = {};
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if (dev < 16 && !attrs_set[dev]) {
+    for (int ex = 0; ex < 2; ++ex)
+      for (int ti = 0; ti < 2; ++ti)
+        for (int ry = 1; ry <= 2; ++ry)
+          if ((e = cudaFuncSetAttribute(render_kernel(ex, ti, ry), cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
 #define UECRT_SET(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
-    UECRT_SET((k_render_paths<false, false>)) UECRT_SET((k_render_paths<true, false>))
-    UECRT_SET((k_render_paths<false, true>)) UECRT_SET((k_render_paths<true, true>))
     UECRT_SET((k_primary_hits<false, false>)) UECRT_SET((k_primary_hits<true, false>))
     UECRT_SET((k_primary_hits<false, true>)) UECRT_SET((k_primary_hits<true, true>))
 #undef UECRT_SET
     attrs_set[dev] = true;
   }
   cudaFuncAttributes fa;
-  if ((e = cudaFuncGetAttributes(&fa, tiled ? k_render_paths<false, true> : k_render_paths<false, false>)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, render_kernel(false, tiled, rays))) != cudaSuccess) return e;
   if (regs_render) *regs_render = fa.numRegs;
-  // CTAs per SM: the minimum over the fast and the exact variant, so one grid size serves both
-  int nb = 1 << 30;
   for (int exact = 0; exact < 2; ++exact) {
     int n1 = 0;
-    if (tiled && exact) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<true, true>, kRenderThreads, smem_render);
-    else if (tiled) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<false, true>, kRenderThreads, smem_render);
-    else if (exact) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<true, false>, kRenderThreads, smem_render);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths<false, false>, kRenderThreads, smem_render);
-    if (e != cudaSuccess) return e;
-    if (exact == 0 && max_blocks_per_sm) max_blocks_per_sm[0] = n1;
-    if (exact == 1 && max_blocks_per_sm) max_blocks_per_sm[1] = n1;
-    nb = n1 < nb ? n1 : nb;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, render_kernel(exact, tiled, rays), kRenderThreads, smem_render)) != cudaSuccess) return e;
+    if (max_blocks_per_sm) max_blocks_per_sm[exact] = n1;
   }
   return cudaSuccess;
 }
 
-void launch_render_paths(const RenderArgs& a, bool exact, int blocks, int threads, size_t smem, cudaStream_t st) {
-  const bool tiled = a.sc.ntiles > 1;
-  if (exact && tiled) k_render_paths<true, true><<<blocks, threads, smem, st>>>(a);
-  else if (exact) k_render_paths<true, false><<<blocks, threads, smem, st>>>(a);
-  else if (tiled) k_render_paths<false, true><<<blocks, threads, smem, st>>>(a);
-  else k_render_paths<false, false><<<blocks, threads, smem, st>>>(a);
+void launch_render_paths(const RenderArgs& a, bool exact, int rays, int blocks, int threads, size_t smem, cudaStream_t st) {
+  render_kernel(exact, a.sc.ntiles > 1, rays)<<<blocks, threads, smem, st>>>(a);
 }
 
 void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
                          double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, cudaStream_t st) {
-  const size_t smem = render_smem_bytes(sc.npairs, sc.ntiles, kHitsThreads);
+  const size_t smem = render_smem_bytes(sc.npairs, sc.ntiles, kHitsThreads, 1);
   unsigned long long want = (n_rays + kHitsThreads - 1) / kHitsThreads;
   const int blocks = (int)(want < 1 ? 1 : (want > 148ull * 16 ? 148ull * 16 : want));
   const bool tiled = sc.ntiles > 1;

@@ -38,9 +38,9 @@ struct RenderArgs {
 constexpr int kRenderThreads = 256;
 constexpr int kHitsThreads = 128;
 
-size_t render_smem_bytes(int npairs, int ntiles, int threads);
+size_t render_smem_bytes(int npairs, int ntiles, int threads, int rays);
 
-void launch_render_paths(const RenderArgs& a, bool exact, int blocks, int threads, size_t smem, cudaStream_t st);
+void launch_render_paths(const RenderArgs& a, bool exact, int rays, int blocks, int threads, size_t smem, cudaStream_t st);
 void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,
                          double tmin, double tmax, bool exact, double* t, double* nrm, int32_t* id,
                          uint8_t* ff, cudaStream_t st);
@@ -49,6 +49,6 @@ void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4
                     const float* p, const float* nrm, const uint8_t* ff, const float* uniforms4,
                     uint8_t* scattered, float* att, float* o_out, float* d_out, cudaStream_t st);
 void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st);
-cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled);
+cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled, int rays);
 
 }  // namespace uecrt

@@ -23,6 +23,10 @@
 #include "kernels.cuh"
 #include "scene_pack.hpp"
 
+#ifndef UECRT_DEFAULT_RAYS
+#define UECRT_DEFAULT_RAYS 1
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -112,11 +116,13 @@ struct uecrt_ctx {
   size_t cap_pairs = 0;    // bytes allocated for d_pairs
   uint32_t cap_n = 0;      // spheres allocated for geom / materials
   bool configured = false;
+  int rays = 1;            // paths per K1 thread
 };
 
 namespace {
 
 std::atomic<uint32_t> g_tile_spheres{0};   // 0 = automatic (uecrt_set_tile_spheres)
+std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
 constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists = 73 KB -> 3 CTAs per SM
 constexpr size_t kSmemOptin = 232448;
 
@@ -127,11 +133,12 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
   uint32_t tile = g_tile_spheres.load();
   if (tile == 0) {
     const uecrt::PackedScene whole = uecrt::pack_scene(*scene, 0);
-    if (uecrt::render_smem_bytes((int)whole.tile_pairs, 1, uecrt::kRenderThreads) > kSmemOptin / 3 - 1024) tile = kAutoTileSpheres;
+    if (uecrt::render_smem_bytes((int)whole.tile_pairs, 1, uecrt::kRenderThreads, g_rays_per_thread.load()) > kSmemOptin / 3 - 1024) tile = kAutoTileSpheres;
   }
   const uecrt::PackedScene ps = uecrt::pack_scene(*scene, tile);
   const size_t pair_bytes = ps.bytes();
-  const size_t smem_need = uecrt::render_smem_bytes((int)ps.tile_pairs, (int)ps.ntiles, uecrt::kRenderThreads);
+  c->rays = g_rays_per_thread.load();
+  const size_t smem_need = uecrt::render_smem_bytes((int)ps.tile_pairs, (int)ps.ntiles, uecrt::kRenderThreads, c->rays);
   if (smem_need > kSmemOptin)
     return fail(UECRT_ERR_INVALID, "tile of %u sphere pairs needs %zu B of shared memory per CTA (max %zu)", ps.tile_pairs, smem_need, kSmemOptin);
   const uint32_t n_alloc = std::max<uint32_t>(scene->n, 1);
@@ -201,7 +208,7 @@ int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* ca
     cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, c->device);
     c->configured = true;
   }
-  if ((e = uecrt::configure_kernels(&c->regs, c->blocks_per_sm, c->smem, c->sc.ntiles > 1)) != cudaSuccess)
+  if ((e = uecrt::configure_kernels(&c->regs, c->blocks_per_sm, c->smem, c->sc.ntiles > 1, c->rays)) != cudaSuccess)
     return fail(UECRT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e));
   if (c->blocks_per_sm[0] < 1 || c->blocks_per_sm[1] < 1) return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem);
   c->timed = false;
@@ -297,7 +304,7 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   const int blocks = ctx->sm_count * ctx->blocks_per_sm[exact ? 1 : 0];
   ctx->last_blocks = blocks;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  uecrt::launch_render_paths(a, exact, blocks, uecrt::kRenderThreads, ctx->smem, st);
+  uecrt::launch_render_paths(a, exact, ctx->rays, blocks, uecrt::kRenderThreads, ctx->smem, st);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->timed = true;
@@ -543,6 +550,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 
 void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
+void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store(rays == 2 ? 2 : 1); }
 
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
                        double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
