@@ -112,7 +112,8 @@ void uecrt_release(void);
  * ~4000 spheres), otherwise it is swept in tiles of 2048 spheres through a two-buffer TMA ring.  A non-zero value forces tiles of that many
  * spheres for every scene loaded afterwards (tests use tiny tiles to exercise the ring). */
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile);
-/* Paths per K1 thread that share one sweep of the scene (1 or 2); applies to scenes loaded afterwards. */
+/* Paths per K1 thread that share one sweep of the scene; applies to scenes loaded afterwards.
+ * 2 is honoured only by builds with -DUECRT_ENABLE_RAYS2 (measured slower on B200; see kernels.cu). */
 void uecrt_set_rays_per_thread(int rays);
 
 /* uecrt_primary_hits replaces hittable_list::hit_impl (hittable_list.hpp:32-58) on caller

@@ -15,13 +15,13 @@
 //    the CTA sweeps the scene through a two-buffer ring, every live ray of the block testing tile
 //    k while the TMA fills the other buffer with tile k+1; the scan reads shared memory with
 //    warp-broadcast LDS.128, so there is no bank conflict and no global traffic in the loop;
-//  * work items are (pixel, chunk of samples); a lane whose path ended starts its next sample
-//    at once, and lanes that finished an item refill together with ONE atomicAdd per warp
-//    (__ballot_sync/__popc/__shfl_sync), so all 32 lanes run the scan on every iteration until
-//    the queue is empty -- no lane idles while its neighbours finish long paths;
-//  * a lane accumulates its item's samples in registers and publishes one float4
-//    red.global.add.v4.f32 per item (16 B vector atomic into the W*H float4 accumulation
-//    buffer; consecutive lanes own consecutive pixels);
+//  * a work item is ONE path (pixel, sample), numbered sample-major so that consecutive items are
+//    consecutive pixels of the same sample; lanes whose path ended refill together with ONE
+//    atomicAdd per warp (__ballot_sync/__popc/__shfl_sync) and so pick up neighbouring pixels, which
+//    keeps the warp's rays coherent (measured: 69% of FP32 peak vs 66% with 16-sample items) and
+//    all 32 lanes scanning on every iteration until the queue is empty;
+//  * a finished path publishes its radiance with one red.global.add.v4.f32 (16 B vector atomic
+//    {r,g,b,1} into the W*H float4 accumulation buffer, which lives in L2);
 //  * RNG: Philox4x32-10 keyed by seed, counter (pixel, sample, bounce, sub) -- see philox.cuh.
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -252,52 +252,48 @@ __device__ __forceinline__ void closest_hits(const DeviceScene& sc, const ulongl
 // Per-slot path state: a thread owns RAYS independent paths ("slots").
 struct PathState {
   bool active, done;
-  uint32_t pixel, s_next, s_end, sample, bounce, depth_left;
+  uint32_t pixel, sample, bounce, depth_left;
   int self_id;
-  float acc_r, acc_g, acc_b, acc_n;
   float ox, oy, oz, dx, dy, dz, dlen;
   float thr_r, thr_g, thr_b;
 };
 
-// refill + start of the next sample for one slot; warp-convergent (uses __ballot_sync)
+// refill + start of the next path for one slot; warp-convergent (uses __ballot_sync)
 __device__ __forceinline__ void slot_refill_and_start(PathState& p, const RenderArgs& a, unsigned lane,
-                                                      unsigned long long n_pixels, float inv_w, float inv_h,
-                                                      unsigned& n_paths) {
-  // lanes that finished an item publish it and pull the next one together: one atomicAdd per warp
-  const bool need_item = !p.active && !p.done && (p.s_next == p.s_end);
-  const unsigned need_mask = __ballot_sync(0xffffffffu, need_item);
+                                                      unsigned long long n_pixels, double inv_np, float inv_w,
+                                                      float inv_h, unsigned& n_paths) {
+  // lanes whose path ended pull the next paths together: one atomicAdd per warp
+  const bool need = !p.active && !p.done;
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need);
   if (need_mask) {
-    if (need_item && p.acc_n > 0.f) {
-      red_add_v4(a.accum + p.pixel, p.acc_r, p.acc_g, p.acc_b, p.acc_n);
-      p.acc_r = p.acc_g = p.acc_b = p.acc_n = 0.f;
-    }
     const int leader = __ffs(need_mask) - 1;
     unsigned long long base = 0;
     if ((int)lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(need_mask));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (need_item) {
+    if (need) {
       const unsigned long long w = base + __popc(need_mask & ((1u << lane) - 1u));
       if (w < a.total_items) {
-        const unsigned long long q = w / n_pixels;
-        p.pixel = (uint32_t)(w - q * n_pixels);
-        p.s_next = a.sample_begin + (uint32_t)q * a.chunk;
-        const uint32_t lim = a.sample_begin + a.sample_count;
-        p.s_end = p.s_next + a.chunk < lim ? p.s_next + a.chunk : lim;
+        // w = sample * n_pixels + pixel; FP64 reciprocal estimate + fix-up instead of a 64-bit divide
+        unsigned long long q = __double2ull_rz(__ull2double_rz(w) * inv_np);
+        long long rem = (long long)(w - q * n_pixels);
+        if (rem < 0) { --q; rem += (long long)n_pixels; }
+        if (rem >= (long long)n_pixels) { ++q; rem -= (long long)n_pixels; }
+        p.pixel = (uint32_t)rem;
+        p.sample = a.sample_begin + (uint32_t)q;
       } else {
         p.done = true;
       }
     }
   }
-  // start the next sample of this slot's item: camera ray (source.cpp:154-165, camera.hpp:29-32)
-  if (!p.active && !p.done) {
-    p.sample = p.s_next++;
+  // start the path: camera ray (source.cpp:154-165, camera.hpp:29-32)
+  if (need && !p.done) {
     // pixel -> (row, column) without the ~20-instruction runtime integer divide: float reciprocal
     // estimate (exact to +-1 for pixel < 2^24 * width) and one fix-up step each way
     uint32_t py = (uint32_t)__fmul_rz((float)p.pixel, inv_w);
     uint32_t px = p.pixel - py * a.width;
     if ((int32_t)px < 0) { --py; px += a.width; }
     if (px >= a.width) { ++py; px -= a.width; }
-    philox_out r = philox4x32_10(p.pixel, p.sample, 0u, 0u, a.key0, a.key1);
+    const philox_out r = philox4x32_10(p.pixel, p.sample, 0u, 0u, a.key0, a.key1);
     const float u = ((float)px + uecrt_u01(r.x)) * inv_w;
     const float v = ((float)(a.height - py - 1u) + uecrt_u01(r.y)) * inv_h;
     float tx = fmaf(v, a.cam.ver[0], fmaf(u, a.cam.hor[0], a.cam.ll[0]));
@@ -328,7 +324,10 @@ __device__ __forceinline__ void slot_refill_and_start(PathState& p, const Render
     p.self_id = -1;
     p.bounce = 0;
     p.active = p.depth_left > 0;
-    if (!p.active) { p.acc_n += 1.f; ++n_paths; }   // depth 0: black (raytracer.hpp:26)
+    if (!p.active) {                               // depth 0: black (raytracer.hpp:26)
+      red_add_v4(a.accum + p.pixel, 0.f, 0.f, 0.f, 1.f);
+      ++n_paths;
+    }
   }
 }
 
@@ -364,10 +363,8 @@ __device__ __forceinline__ void slot_shade(PathState& p, const Hit& h, const Ren
   }
   if (ended) {
     // a NaN radiance would hang the reference's math::sqrt (math.hpp:14); it contributes 0 here
-    p.acc_r += (rad_r == rad_r) ? rad_r : 0.f;
-    p.acc_g += (rad_g == rad_g) ? rad_g : 0.f;
-    p.acc_b += (rad_b == rad_b) ? rad_b : 0.f;
-    p.acc_n += 1.f;
+    red_add_v4(a.accum + p.pixel, (rad_r == rad_r) ? rad_r : 0.f, (rad_g == rad_g) ? rad_g : 0.f,
+               (rad_b == rad_b) ? rad_b : 0.f, 1.f);
     ++n_paths;
     p.active = false;
   }
@@ -393,6 +390,7 @@ __global__ void __launch_bounds__(kRenderThreads, (EXACT || RAYS > 1) ? 2 : UECR
   for (int s = 0; s < RAYS; ++s) L[s].base = s_lists + (size_t)s * kListCap * kRenderThreads + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long n_pixels = (unsigned long long)a.width * a.height;
+  const double inv_np = 1.0 / (double)n_pixels;
   const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
 
   PathState st[RAYS];
@@ -407,7 +405,7 @@ __global__ void __launch_bounds__(kRenderThreads, (EXACT || RAYS > 1) ? 2 : UECR
     bool all_done = true;
 #pragma unroll
     for (int s = 0; s < RAYS; ++s) {
-      slot_refill_and_start(st[s], a, lane, n_pixels, inv_w, inv_h, n_paths);
+      slot_refill_and_start(st[s], a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
       all_done = all_done && st[s].done;
     }
     if (TILED ? __syncthreads_and(all_done) : __all_sync(0xffffffffu, all_done)) break;   // TILED: the whole CTA sweeps together
@@ -572,13 +570,28 @@ size_t render_smem_bytes(int npairs, int ntiles, int threads, int rays) {
   return ntiles > 1 ? 32 + 2 * tile + lists : 16 + tile + lists;
 }
 
-// Kernel table: [exact][tiled][rays-1]
+// Kernel table: [exact][tiled][rays-1].  Two paths per thread (one shared scene sweep for both) is
+// correct and tested but MEASURED SLOWER on B200 (54% vs 65% of FP32 peak on the final scene: the
+// duplicated per-slot code grows the kernel to ~60 KB of SASS, past the instruction cache, and the
+// 128 registers leave 2 CTAs/SM).  It is compiled only with -DUECRT_ENABLE_RAYS2.
 typedef void (*RenderKernel)(const RenderArgs);
+#ifdef UECRT_ENABLE_RAYS2
+#define UECRT_R2(e, t) k_render_paths<e, t, 2>
+#else
+#define UECRT_R2(e, t) k_render_paths<e, t, 1>
+#endif
 static RenderKernel render_kernel(bool exact, bool tiled, int rays) {
   static const RenderKernel table[2][2][2] = {
-      {{k_render_paths<false, false, 1>, k_render_paths<false, false, 2>}, {k_render_paths<false, true, 1>, k_render_paths<false, true, 2>}},
-      {{k_render_paths<true, false, 1>, k_render_paths<true, false, 2>}, {k_render_paths<true, true, 1>, k_render_paths<true, true, 2>}}};
+      {{k_render_paths<false, false, 1>, UECRT_R2(false, false)}, {k_render_paths<false, true, 1>, UECRT_R2(false, true)}},
+      {{k_render_paths<true, false, 1>, UECRT_R2(true, false)}, {k_render_paths<true, true, 1>, UECRT_R2(true, true)}}};
   return table[exact ? 1 : 0][tiled ? 1 : 0][rays == 2 ? 1 : 0];
+}
+int max_rays_per_thread() {
+#ifdef UECRT_ENABLE_RAYS2
+  return 2;
+#else
+  return 1;
+#endif
 }
 
 // max_blocks_per_sm[0] = fast variant, [1] = exact variant (for `rays` rays per thread)

@@ -26,10 +26,10 @@ struct RenderArgs {
   DeviceScene sc;
   DeviceCamera cam;
   uint32_t width, height;
-  uint32_t sample_begin, sample_count, chunk;   // chunk = samples per work item
+  uint32_t sample_begin, sample_count;          // global sample ids [begin, begin+count) of every pixel
   uint32_t max_depth;
   uint32_t key0, key1;                          // Philox key (seed)
-  unsigned long long total_items;               // pixels * ceil(sample_count / chunk)
+  unsigned long long total_items;               // pixels * sample_count: one work item per path
   float4* accum;
   unsigned long long* counters;
   int count_stats;
@@ -38,6 +38,7 @@ struct RenderArgs {
 constexpr int kRenderThreads = 256;
 constexpr int kHitsThreads = 128;
 
+int max_rays_per_thread();   // 2 only when built with -DUECRT_ENABLE_RAYS2
 size_t render_smem_bytes(int npairs, int ntiles, int threads, int rays);
 
 void launch_render_paths(const RenderArgs& a, bool exact, int rays, int blocks, int threads, size_t smem, cudaStream_t st);

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -291,11 +292,9 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.sc = ctx->sc; a.cam = ctx->cam;
   a.width = p->width; a.height = p->height;
   a.sample_begin = begin; a.sample_count = count;
-  a.chunk = std::max<uint32_t>(1, std::min<uint32_t>(count, 16));
   a.max_depth = p->max_depth;
   a.key0 = (uint32_t)(p->seed & 0xffffffffull); a.key1 = (uint32_t)(p->seed >> 32);
-  const unsigned long long chunks = count ? (count + a.chunk - 1) / a.chunk : 0;
-  a.total_items = (unsigned long long)p->width * p->height * chunks;
+  a.total_items = (unsigned long long)p->width * p->height * count;   // one work item per (pixel, sample) path
   a.accum = reinterpret_cast<float4*>(d_accum);
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
@@ -550,7 +549,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 
 void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
-void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store(rays == 2 ? 2 : 1); }
+void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store((rays == 2 && uecrt::max_rays_per_thread() == 2) ? 2 : 1); }
 
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
                        double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
