@@ -100,6 +100,19 @@ def test_sample_shards_add_up(u):
     assert np.abs(other[..., :3] - full[..., :3]).mean() > 1e-3     # a different seed is a different image
 
 
+@pytest.mark.parametrize("W", [17, 36, 100])
+def test_ragged_tile_edges(u, oracle, W):
+    """Work items are laid out on a grid of 8x4-pixel tiles; widths / heights that are not multiples of
+    8 / 4 must still give every pixel exactly spp samples and nothing outside the frame."""
+    sc, c = u.Scene.named("ref4"), u.Camera.named("ref")
+    H, S = u.image_height(W), 64
+    rgb, acc, st = u.render(sc, c, W, S, 50, seed=3, return_accum=True)
+    assert acc.shape == (H, W, 4) and np.all(acc[..., 3] == S) and st["paths"] == W * H * S
+    ref, _ = oracle.render(sc, c, W, H, S, 50, 1)
+    assert abs(acc[..., :3].mean() / ref.mean() - 1) < 0.02
+    assert psnr8(rgb, oracle.to_color3b(ref, S)) > 30
+
+
 def test_depth_semantics(u):
     """raytracer.hpp:26: depth 0 -> black.  With max_depth 1 a hit's scattered ray gets depth 0, so
     the image is sky where primary rays miss and black elsewhere."""

@@ -224,7 +224,10 @@ __device__ __forceinline__ void scan_pairs(const ulonglong2* __restrict__ pairs,
   const ulonglong2* p = pairs;
   ulonglong2 A0 = p[0], B0 = p[1], A1 = p[2], B1 = p[3];
   const int niter = npairs >> 2;          // 8 spheres per iteration; npairs is a multiple of 8
-#pragma unroll 2
+#ifndef UECRT_SCAN_UNROLL
+#define UECRT_SCAN_UNROLL 2               // tuning knob (1, 2: npairs is padded to 8 pairs)
+#endif
+#pragma unroll UECRT_SCAN_UNROLL
   for (int it = 0; it < niter; ++it) {
     int f[R][8], mlo[R], mhi[R];
     const ulonglong2 A2 = p[4], B2 = p[5], A3 = p[6], B3 = p[7];          // second group of this iteration

@@ -251,7 +251,7 @@ __device__ __forceinline__ void closest_hits(const DeviceScene& sc, const ulongl
 // K1
 // Per-slot path state: a thread owns RAYS independent paths ("slots").
 struct PathState {
-  bool active, done;
+  bool active, done, valid;
   uint32_t pixel, sample, bounce, depth_left;
   int self_id;
   float ox, oy, oz, dx, dy, dz, dlen;
@@ -273,20 +273,29 @@ __device__ __forceinline__ void slot_refill_and_start(PathState& p, const Render
     if (need) {
       const unsigned long long w = base + __popc(need_mask & ((1u << lane) - 1u));
       if (w < a.total_items) {
-        // w = sample * n_pixels + pixel; FP64 reciprocal estimate + fix-up instead of a 64-bit divide
+        // w = sample * n_slots + slot, slot = (tile << 5) | within: tiles of 8x4 pixels in row-major
+        // tile order, so the 32 lanes of a warp start on a compact 8x4 pixel block (coherent rays).
+        // FP64 / FP32 reciprocal estimates + fix-up instead of integer divides.
         unsigned long long q = __double2ull_rz(__ull2double_rz(w) * inv_np);
         long long rem = (long long)(w - q * n_pixels);
         if (rem < 0) { --q; rem += (long long)n_pixels; }
         if (rem >= (long long)n_pixels) { ++q; rem -= (long long)n_pixels; }
-        p.pixel = (uint32_t)rem;
+        const uint32_t slot = (uint32_t)rem, tile = slot >> 5, within = slot & 31u;
+        uint32_t ty = (uint32_t)__fmul_rz((float)tile, a.inv_tiles_x);
+        uint32_t tx = tile - ty * a.tiles_x;
+        if ((int32_t)tx < 0) { --ty; tx += a.tiles_x; }
+        if (tx >= a.tiles_x) { ++ty; tx -= a.tiles_x; }
+        const uint32_t x = tx * 8u + (within & 7u), y = ty * 4u + (within >> 3);
+        p.pixel = y * a.width + x;
         p.sample = a.sample_begin + (uint32_t)q;
+        p.valid = (x < a.width) && (y < a.height);      // ragged right / bottom edge of the tile grid
       } else {
         p.done = true;
       }
     }
   }
   // start the path: camera ray (source.cpp:154-165, camera.hpp:29-32)
-  if (need && !p.done) {
+  if (need && !p.done && p.valid) {
     // pixel -> (row, column) without the ~20-instruction runtime integer divide: float reciprocal
     // estimate (exact to +-1 for pixel < 2^24 * width) and one fix-up step each way
     uint32_t py = (uint32_t)__fmul_rz((float)p.pixel, inv_w);
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(kRenderThreads, (EXACT || RAYS > 1) ? 2 : UECR
 #pragma unroll
   for (int s = 0; s < RAYS; ++s) L[s].base = s_lists + (size_t)s * kListCap * kRenderThreads + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned long long n_pixels = (unsigned long long)a.width * a.height;
+  const unsigned long long n_pixels = a.n_slots;     // pixel slots of the 8x4 tile grid (>= width*height)
   const double inv_np = 1.0 / (double)n_pixels;
   const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
 

@@ -29,7 +29,10 @@ struct RenderArgs {
   uint32_t sample_begin, sample_count;          // global sample ids [begin, begin+count) of every pixel
   uint32_t max_depth;
   uint32_t key0, key1;                          // Philox key (seed)
-  unsigned long long total_items;               // pixels * sample_count: one work item per path
+  uint32_t tiles_x;                             // 8x4-pixel tiles per row (ceil(width / 8))
+  float inv_tiles_x;
+  unsigned long long n_slots;                   // tiles * 32 (pixel slots incl. the ragged edge)
+  unsigned long long total_items;               // n_slots * sample_count: one work item per path slot
   float4* accum;
   unsigned long long* counters;
   int count_stats;

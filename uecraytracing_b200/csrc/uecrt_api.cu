@@ -294,7 +294,10 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.sample_begin = begin; a.sample_count = count;
   a.max_depth = p->max_depth;
   a.key0 = (uint32_t)(p->seed & 0xffffffffull); a.key1 = (uint32_t)(p->seed >> 32);
-  a.total_items = (unsigned long long)p->width * p->height * count;   // one work item per (pixel, sample) path
+  a.tiles_x = (p->width + 7) / 8;
+  a.inv_tiles_x = 1.0f / (float)a.tiles_x;
+  a.n_slots = (unsigned long long)a.tiles_x * ((p->height + 3) / 4) * 32ull;
+  a.total_items = a.n_slots * count;   // one work item per (pixel slot, sample) path
   a.accum = reinterpret_cast<float4*>(d_accum);
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
