@@ -227,7 +227,9 @@ __device__ __forceinline__ void scan_pairs(const ulonglong2* __restrict__ pairs,
 #ifndef UECRT_SCAN_UNROLL
 #define UECRT_SCAN_UNROLL 2               // tuning knob (1, 2: npairs is padded to 8 pairs)
 #endif
-#pragma unroll UECRT_SCAN_UNROLL
+#define UECRT_PRAGMA_(x) _Pragma(#x)
+#define UECRT_UNROLL_(n) UECRT_PRAGMA_(unroll n)
+  UECRT_UNROLL_(UECRT_SCAN_UNROLL)
   for (int it = 0; it < niter; ++it) {
     int f[R][8], mlo[R], mhi[R];
     const ulonglong2 A2 = p[4], B2 = p[5], A3 = p[6], B3 = p[7];          // second group of this iteration
