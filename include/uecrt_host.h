@@ -18,6 +18,17 @@ uint32_t uecrt_host_scene_count(const char* name, uint32_t n_hint, uint32_t seed
 int uecrt_host_scene_fill(const char* name, uint32_t n_hint, uint32_t seed, uint32_t cap,
                           uecrt_float4* geom, uint32_t* mat_type, uecrt_float4* mat_param);
 
+/* Scene description files (host/yk/scene_io.hpp: `sphere cx cy cz r lambertian|metal|dielectric ...`,
+ * optional `camera ...`).  uecrt_host_scene_file_count returns the sphere count or -1 on a parse error
+ * (message through uecrt_host_last_error); _fill copies the arrays and, when the file has a camera
+ * line, the camera (has_camera_out = 1).  uecrt_host_scene_file_write writes arrays back as text. */
+int32_t uecrt_host_scene_file_count(const char* path);
+int uecrt_host_scene_file_fill(const char* path, uint32_t cap, uecrt_float4* geom, uint32_t* mat_type,
+                               uecrt_float4* mat_param, uecrt_camera* cam_out, int* has_camera_out);
+int uecrt_host_scene_file_write(const char* path, uint32_t n, const uecrt_float4* geom,
+                                const uint32_t* mat_type, const uecrt_float4* mat_param);
+const char* uecrt_host_last_error(void);
+
 /* Cameras: "ref" = yk::camera<T>{} (camera.hpp:16-27); "final" / "dense" = RTIOW look-at. */
 int uecrt_host_camera(const char* name, uecrt_camera* out);
 int uecrt_host_camera_lookat(const double from[3], const double at[3], const double vup[3],
@@ -26,6 +37,10 @@ int uecrt_host_camera_lookat(const double from[3], const double at[3], const dou
 
 /* image_height = uint32(width / (16/9)) (source.cpp:59-62) */
 uint32_t uecrt_host_image_height(uint32_t width);
+
+/* Portable float map (PFM, "PF", little-endian, bottom row first) of the linear image sum/spp taken
+ * from a W*H*4 accumulation buffer.  Returns 0 on success. */
+int uecrt_host_write_pfm(const char* path, uint32_t width, uint32_t height, const float* accum4, uint32_t spp);
 
 /* 8-bit RGB PNG, stride 3*width, top row first (what source.cpp:224-226 asks of
  * stbi_write_png).  Returns 0 on success. */

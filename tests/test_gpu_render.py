@@ -172,6 +172,23 @@ def test_cli_renders_reference_default(u, oracle, tmp_path):
     assert psnr8(img, oracle.to_color3b(a, 25)) > 30
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")), reason="binary not built")
+def test_cli_scene_file_and_pfm(u, tmp_path):
+    scene = tmp_path / "s.scene"
+    u.save_scene_file(scene, u.Scene.named("ref4"))
+    out, pfm = tmp_path / "o.png", tmp_path / "o.pfm"
+    r = subprocess.run([os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace"), "-o", str(out), "--scene-file", str(scene), "--width", "96",
+                        "--spp", "32", "--seed", "9", "--dump-accum", str(pfm)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.split("\n")[3] == "success", r.stdout + r.stderr
+    img = read_png_rgb(out)
+    rgb, acc, _ = u.render(u.Scene.named("ref4"), u.Camera.named("ref"), 96, 32, 50, seed=9, return_accum=True)
+    assert img.shape == (54, 96, 3) and psnr8(img, rgb) > 45
+    raw = pfm.read_bytes()
+    body = raw[raw.index(b"-1.0\n") + 5:]
+    lin = np.frombuffer(body, "<f4").reshape(54, 96, 3)[::-1]
+    np.testing.assert_allclose(lin, acc[..., :3] / 32, rtol=1e-4, atol=1e-5)
+
+
 def test_multi_gpu_single_process(u):
     if u.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -125,6 +125,49 @@ def test_png_writer_roundtrip(u, tmp_path):
         u.write_png("/nonexistent_dir/x.png", img)
 
 
+def test_scene_file_roundtrip_and_errors(u, tmp_path):
+    """Runtime scene description (the step before the path; the reference hard-codes source.cpp:103-112)."""
+    s = u.Scene.named("final", seed=1)
+    path = tmp_path / "final.scene"
+    u.save_scene_file(path, s)
+    s2, cam = u.load_scene_file(path)
+    assert cam is None and s2.n == s.n
+    assert np.array_equal(s.geom, s2.geom) and np.array_equal(s.mat_type, s2.mat_type) and np.array_equal(s.mat_param, s2.mat_param)
+    txt = tmp_path / "mini.scene"
+    txt.write_text("# the reference scene, by hand\n"
+                   "sphere 0 0 -1 0.5 lambertian 0.7 0.3 0.3\n"
+                   "sphere 0 -100.5 -1 100 lambertian 0.8 0.8 0.0   # ground\n"
+                   "\n"
+                   "sphere -1 0 -1 0.5 metal 0.8 0.8 0.8\n"
+                   "sphere 1 0 -1 0.5 metal 0.8 0.6 0.2 0.0\n"
+                   "camera 13 2 3  0 0 0  20 0.1 10\n")
+    s3, cam3 = u.load_scene_file(txt)
+    ref = u.Scene.named("ref4")
+    assert np.array_equal(s3.geom, ref.geom) and np.array_equal(s3.mat_type, ref.mat_type) and np.array_equal(s3.mat_param, ref.mat_param)
+    fin = u.Camera.named("final").s
+    for k in ("origin", "lower_left", "horizontal", "vertical", "u", "v"):
+        assert list(getattr(cam3.s, k)) == list(getattr(fin, k))
+    assert cam3.s.lens_radius == fin.lens_radius
+    for bad, msg in (("sphere 0 0 0 1 plastic 1 1 1\n", "unknown material"), ("sphere 0 0\n", "expected"), ("cube 1\n", "unknown keyword"),
+                     ("sphere 0 0 0 1 dielectric\n", "index of refraction")):
+        b = tmp_path / "bad.scene"; b.write_text("# ok\n" + bad)
+        with pytest.raises(ValueError, match=msg + "|bad.scene:2"):
+            u.load_scene_file(b)
+    with pytest.raises(ValueError, match="cannot open"):
+        u.load_scene_file(tmp_path / "missing.scene")
+
+
+def test_pfm_writer(u, tmp_path):
+    acc = np.zeros((3, 5, 4), np.float32)
+    acc[..., 0] = np.arange(15).reshape(3, 5) * 4; acc[..., 1] = 2; acc[..., 2] = 8; acc[..., 3] = 4
+    u.write_pfm(tmp_path / "a.pfm", acc, 4)
+    raw = (tmp_path / "a.pfm").read_bytes()
+    head, body = raw[:raw.index(b"-1.0\n") + 5], raw[raw.index(b"-1.0\n") + 5:]
+    assert head == b"PF\n5 3\n-1.0\n"
+    img = np.frombuffer(body, "<f4").reshape(3, 5, 3)[::-1]          # PFM stores the bottom row first
+    assert np.array_equal(img[..., 0], np.arange(15).reshape(3, 5)) and np.all(img[..., 1] == 0.5) and np.all(img[..., 2] == 2)
+
+
 def _run(*args):
     return subprocess.run([BIN, *args], capture_output=True, text=True, timeout=60)
 

@@ -45,7 +45,8 @@ EXPORTS = [
     "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_primary_hits", "uecrt_scatter",
     "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_ctx_set_scene", "uecrt_accumulate_device", "uecrt_resolve_device",
     "uecrt_ctx_stats", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
-    "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox",
+    "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox", "uecrt_host_scene_file_count", "uecrt_host_scene_file_fill",
+    "uecrt_host_scene_file_write", "uecrt_host_last_error", "uecrt_host_write_pfm",
 ]
 
 
@@ -84,6 +85,15 @@ def _load():
     L.uecrt_host_image_height.restype = u32
     L.uecrt_host_write_png.argtypes = [C.c_char_p, u32, u32, vp]
     L.uecrt_host_philox.argtypes = [u64, vp, vp]
+    L.uecrt_host_scene_file_count.argtypes = [C.c_char_p]
+    L.uecrt_host_scene_file_count.restype = i32
+    L.uecrt_host_scene_file_fill.argtypes = [C.c_char_p, u32, vp, vp, vp, vp, vp]
+    L.uecrt_host_scene_file_fill.restype = C.c_int
+    L.uecrt_host_scene_file_write.argtypes = [C.c_char_p, u32, vp, vp, vp]
+    L.uecrt_host_scene_file_write.restype = C.c_int
+    L.uecrt_host_last_error.restype = C.c_char_p
+    L.uecrt_host_write_pfm.argtypes = [C.c_char_p, u32, u32, vp, u32]
+    L.uecrt_host_write_pfm.restype = C.c_int
     L.uecrt_host_philox.restype = None
     for name in ("uecrt_render", "uecrt_primary_hits", "uecrt_scatter", "uecrt_philox", "uecrt_ctx_create",
                  "uecrt_accumulate_device", "uecrt_resolve_device", "uecrt_ctx_stats", "uecrt_host_scene_fill",

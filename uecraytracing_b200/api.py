@@ -52,6 +52,29 @@ class Scene:
         return cls(geom, mt, mp)
 
 
+def load_scene_file(path):
+    """(Scene, Camera or None) from a text scene description (host/yk/scene_io.hpp)."""
+    n = lib.uecrt_host_scene_file_count(str(path).encode())
+    if n < 0:
+        raise ValueError(lib.uecrt_host_last_error().decode(errors="replace"))
+    geom = np.zeros((n, 4), np.float32); mt = np.zeros(n, np.uint32); mp = np.zeros((n, 4), np.float32)
+    cam = CameraStruct(); has = C.c_int(0)
+    check(lib.uecrt_host_scene_file_fill(str(path).encode(), n, _ptr(geom), _ptr(mt), _ptr(mp), C.byref(cam), C.byref(has)),
+          "scene_file_fill")
+    return Scene(geom, mt, mp), (Camera(cam) if has.value else None)
+
+
+def save_scene_file(path, scene):
+    check(lib.uecrt_host_scene_file_write(str(path).encode(), scene.n, _ptr(scene.geom), _ptr(scene.mat_type),
+                                          _ptr(scene.mat_param)), "scene_file_write")
+
+
+def write_pfm(path, accum, spp):
+    a = np.ascontiguousarray(accum, np.float32)
+    h, w, _ = a.shape
+    check(lib.uecrt_host_write_pfm(str(path).encode(), w, h, _ptr(a), int(spp)), "uecrt_host_write_pfm")
+
+
 class Camera:
     def __init__(self, struct):
         self.s = struct

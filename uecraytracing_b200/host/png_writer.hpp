@@ -46,4 +46,21 @@ inline int write_png(const char* filename, int w, int h, int comp, const void* d
   return (std::fclose(f) == 0 && ok) ? 1 : 0;
 }
 
+// PFM ("PF": 3 x float32 per pixel, little-endian, BOTTOM row first) of sum/spp from a W*H*4 buffer
+inline int write_pfm(const char* filename, int w, int h, const float* accum4, unsigned spp) {
+  if (w <= 0 || h <= 0 || !accum4 || spp == 0) return 0;
+  std::FILE* f = std::fopen(filename, "wb");
+  if (!f) return 0;
+  std::fprintf(f, "PF\n%d %d\n-1.0\n", w, h);
+  std::vector<float> row((std::size_t)w * 3);
+  const float inv = 1.0f / (float)spp;
+  bool ok = true;
+  for (int y = h - 1; y >= 0 && ok; --y) {
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < 3; ++c) row[(std::size_t)x * 3 + c] = accum4[((std::size_t)y * w + x) * 4 + c] * inv;
+    ok = std::fwrite(row.data(), sizeof(float), row.size(), f) == row.size();
+  }
+  return (std::fclose(f) == 0 && ok) ? 1 : 0;
+}
+
 }  // namespace uecrt_host

@@ -14,6 +14,7 @@
 #include "cli_options.hpp"
 #include "png_writer.hpp"
 #include "yk/render.hpp"
+#include "yk/scene_io.hpp"
 #include "yk/scenes.hpp"
 
 int main(int argc, char* argv[]) {
@@ -31,10 +32,11 @@ int main(int argc, char* argv[]) {
       .add(0, "seed", "Philox seed (default: random)", true)
       .add(0, "gpus", "number of B200s to shard samples over (default 1)", true)
       .add(0, "scene", "ref4 | ref4d | final | dense (default ref4)", true)
+      .add(0, "scene-file", "render the spheres (and camera) described in a text file (see host/yk/scene_io.hpp)", true)
       .add(0, "scene-seed", "seed of the random scene generator (default 1)", true)
       .add(0, "dense-n", "sphere count of --scene dense (default 10000)", true)
       .add(0, "exact-hits", "resolve every closest hit in FP64", false)
-      .add(0, "dump-accum", "also write the linear float accumulation buffer (raw W*H*4 f32)", true);
+      .add(0, "dump-accum", "also write the linear float image (.pfm) or the raw W*H*4 f32 accumulation buffer", true);
   options.positional("output");
   options.parse(argc, argv);
   if (options.count("help") || !options.count("output")) {
@@ -60,7 +62,17 @@ int main(int argc, char* argv[]) {
 
   yk::hittable_list<double> world;
   yk::camera<double> cam;
-  if (scene == "ref4") { world = yk::scenes::reference_scene(); cam = yk::scenes::reference_camera(); }
+  if (options.count("scene-file")) {
+    try {
+      yk::scene_io::scene_file f = yk::scene_io::load(options.last("scene-file"));
+      world = f.world;
+      cam = f.cam;
+    } catch (const std::exception& e) {
+      std::cout << "error" << std::endl;
+      std::cerr << e.what() << std::endl;
+      std::exit(EXIT_FAILURE);
+    }
+  } else if (scene == "ref4") { world = yk::scenes::reference_scene(); cam = yk::scenes::reference_camera(); }
   else if (scene == "ref4d") { world = yk::scenes::reference_scene_dielectric(); cam = yk::scenes::reference_camera(); }
   else if (scene == "final") { world = yk::scenes::final_scene(scene_seed); cam = yk::scenes::final_camera(); }
   else if (scene == "dense") { world = yk::scenes::dense_scene(dense_n, scene_seed); cam = yk::scenes::dense_camera(); }
@@ -83,12 +95,19 @@ int main(int argc, char* argv[]) {
     std::exit(EXIT_FAILURE);
   }
   if (dump) {
-    std::FILE* f = std::fopen(options.last("dump-accum").c_str(), "wb");
-    if (!f || std::fwrite(image.accum.data(), sizeof(float), image.accum.size(), f) != image.accum.size()) {
+    const std::string path = options.last("dump-accum");
+    bool ok;
+    if (path.size() > 4 && path.substr(path.size() - 4) == ".pfm") {
+      ok = uecrt_host::write_pfm(path.c_str(), (int)image.width, (int)image.height, image.accum.data(), cfg.spp) != 0;
+    } else {
+      std::FILE* f = std::fopen(path.c_str(), "wb");
+      ok = f && std::fwrite(image.accum.data(), sizeof(float), image.accum.size(), f) == image.accum.size();
+      if (f) ok = (std::fclose(f) == 0) && ok;
+    }
+    if (!ok) {
       std::cout << "error" << std::endl;
       std::exit(EXIT_FAILURE);
     }
-    std::fclose(f);
   }
   std::cout << "success" << std::endl;
 }
