@@ -12,7 +12,7 @@ CSRC = $(PKG)/csrc
 HOST = $(PKG)/host
 BUILD = build
 
-all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace
+all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface
 
 $(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
@@ -30,6 +30,10 @@ $(PKG)/libuecrt.so: $(BUILD)/kernels.o $(BUILD)/uecrt_api.o $(BUILD)/host_api.o
 $(PKG)/bin/raytrace: $(HOST)/raytrace.cpp $(HOST)/cli_options.hpp $(HOST)/png_writer.hpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so
 	@mkdir -p $(PKG)/bin
 	$(HOSTCXX) -std=c++20 -O2 $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/..'
+
+# C++ test of the yk:: host surface (run by tests/test_cpp_surface.py)
+$(BUILD)/test_yk_surface: tests/cpp/test_yk_surface.cpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so
+	$(HOSTCXX) -std=c++20 -O1 -I$(HOST) $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/../$(PKG)'
 
 oracle:
 	$(MAKE) -C oracle all

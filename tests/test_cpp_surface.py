@@ -1,0 +1,21 @@
+"""The C++ yk:: host surface used as the reference's source.cpp uses its own (tests/cpp/test_yk_surface.cpp)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "build", "test_yk_surface")
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="build/test_yk_surface not built (make)")
+def test_yk_surface_cpu():
+    r = subprocess.run([EXE, "--cpu-only"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "cpu checks ok", r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(EXE), reason="build/test_yk_surface not built (make)")
+def test_yk_surface_gpu():
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.split("\n")[:2] == ["cpu checks ok", "gpu checks ok"], r.stdout + r.stderr
