@@ -76,6 +76,23 @@ def test_secondary_rays_from_surfaces_exact(u, oracle):
     assert (want[2] >= 0).mean() > 0.2
 
 
+@pytest.mark.parametrize("shift", [(300.0, 0.0, 300.0), (3000.0, 50.0, -2000.0)])
+def test_far_from_origin_stays_exact(u, oracle, shift):
+    """The FP32 scan's error bound grows with |o|^2 and |c|^2: far from the world origin it admits many
+    false candidates (the per-thread lists overflow and are folded), but the FP64 resolve must still
+    return the reference's sphere.  Correctness may never depend on where the scene sits."""
+    base, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    g = base.geom.copy(); g[:, :3] += np.array(shift, np.float32)
+    sc = u.Scene(g, base.mat_type, base.mat_param)
+    o, d = primary_rays(c, 240, 135)
+    o = o + np.array(shift, np.float32)
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    assert (want[2] >= 0).mean() > 0.5
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, f"shift {shift}")
+    t, n, i, f = u.primary_hits(sc, o, d, exact=False)
+    assert (i != want[2]).mean() < 0.02                      # FP32 resolve: silhouettes may differ at this distance
+
+
 def test_edge_cases_golden(u):
     for c in golden("hit_edge_cases.json")["cases"]:
         g = np.array(c["spheres"], np.float32)
