@@ -22,14 +22,14 @@ $(BUILD)/uecrt_api.o: $(CSRC)/uecrt_api.cu $(CSRC)/kernels.cuh $(CSRC)/scene_pac
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(BUILD)/host_api.o: $(HOST)/host_api.cpp $(wildcard $(HOST)/yk/*.hpp) $(HOST)/png_writer.hpp include/uecrt_host.h include/uecrt.h
 	@mkdir -p $(BUILD)
-	$(HOSTCXX) -std=c++20 -O2 -fPIC -c $< -o $@
+	$(HOSTCXX) -std=c++20 -O2 -fPIC -pthread -c $< -o $@
 
 $(PKG)/libuecrt.so: $(BUILD)/kernels.o $(BUILD)/uecrt_api.o $(BUILD)/host_api.o
 	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $^ -lz -ldl
 
 $(PKG)/bin/raytrace: $(HOST)/raytrace.cpp $(HOST)/cli_options.hpp $(HOST)/png_writer.hpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so
 	@mkdir -p $(PKG)/bin
-	$(HOSTCXX) -std=c++20 -O2 $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/..'
+	$(HOSTCXX) -std=c++20 -O2 -pthread $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/..'
 
 # C++ test of the yk:: host surface (run by tests/test_cpp_surface.py)
 $(BUILD)/test_yk_surface: tests/cpp/test_yk_surface.cpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so

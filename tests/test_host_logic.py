@@ -123,6 +123,18 @@ def test_png_writer_roundtrip(u, tmp_path):
     assert np.all(rows[:, 0] == 0) and np.array_equal(rows[:, 1:].reshape(9, 16, 3), img)
     with pytest.raises(u.UecrtError):
         u.write_png("/nonexistent_dir/x.png", img)
+    # tall images are deflated in independent bands on several host threads and stitched into ONE zlib
+    # stream (sync-flushed raw deflate pieces + combined Adler-32): any zlib must decode it
+    from conftest import read_png_rgb
+    big = rng.integers(0, 256, (301, 67, 3), dtype=np.uint8)
+    big[100:200] = 7                                    # a compressible band too
+    u.write_png(tmp_path / "big.png", big)
+    assert np.array_equal(read_png_rgb(tmp_path / "big.png"), big)
+    try:
+        from PIL import Image
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "big.png").convert("RGB")), big)
+    except ImportError:
+        pass
 
 
 def test_scene_file_roundtrip_and_errors(u, tmp_path):
