@@ -189,6 +189,20 @@ def test_cli_scene_file_and_pfm(u, tmp_path):
     np.testing.assert_allclose(lin, acc[..., :3] / 32, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "raytrace_dropin")), reason="oracle/_ref/raytrace_dropin not built")
+def test_reference_translation_unit_rehosted_on_the_abi(u, tmp_path):
+    """oracle/dropin_demo.cpp: the reference's OWN source.cpp types (tuple hittable_list, camera, image_t,
+    vendored stbi_write_png) with render()'s loop replaced by one uecrt_render call, as INTEGRATION.md shows."""
+    from PIL import Image
+    out = tmp_path / "dropin.png"
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "raytrace_dropin"), str(out), "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split("\n")[:4] == ["rendering...", "rendering finished", f"write to file : {out}", "success"]
+    img = np.asarray(Image.open(out).convert("RGB"))
+    rgb, _, _ = u.render(u.Scene.named("ref4"), u.Camera.named("ref"), 400, 100, 50, seed=5)
+    assert img.shape == (225, 400, 3) and psnr8(img, rgb) > 45      # same seed, same scene: equal up to FP32 sum order
+
+
 def test_multi_gpu_single_process(u):
     if u.device_count() < 2:
         pytest.skip("needs 2 GPUs")
