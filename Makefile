@@ -14,10 +14,10 @@ BUILD = build
 
 all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface
 
-$(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh include/uecrt.h
+$(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh $(CSRC)/tc_scan.cuh $(CSRC)/tc_collect.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/kernels.ptxas.log || (cat $(BUILD)/kernels.ptxas.log; false)
-$(BUILD)/uecrt_api.o: $(CSRC)/uecrt_api.cu $(CSRC)/kernels.cuh $(CSRC)/scene_pack.hpp include/uecrt.h
+$(BUILD)/uecrt_api.o: $(CSRC)/uecrt_api.cu $(CSRC)/kernels.cuh $(CSRC)/scene_pack.hpp $(CSRC)/tc_scan.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(BUILD)/host_api.o: $(HOST)/host_api.cpp $(wildcard $(HOST)/yk/*.hpp) $(HOST)/png_writer.hpp include/uecrt_host.h include/uecrt.h

@@ -71,8 +71,16 @@ typedef struct {
 
 enum {
   UECRT_FLAG_EXACT_HITS = 1u, /* resolve every closest hit in FP64 (reference-exact index) inside K1 */
-  UECRT_FLAG_NO_COUNTERS = 2u /* do not count rays/sphere tests (saves two atomics per CTA)          */
+  UECRT_FLAG_NO_COUNTERS = 2u, /* do not count rays/sphere tests (saves two atomics per CTA)         */
+  UECRT_FLAG_SCAN_FP32 = 4u,   /* force the FP32-pipe candidate scan (packed FFMA2 from shared memory) */
+  UECRT_FLAG_SCAN_TENSOR = 8u  /* force the tensor-core candidate scan (tcgen05 TF32 x3, TMEM); fails
+                                  with UECRT_ERR_INVALID when the scene is too large for it           */
 };
+/* scan used by a render / hit call: the all-pairs discriminant test of hittable_list::hit_impl
+ * (hittable_list.hpp:32-58) runs either on the FP32 pipe or on the tensor cores; both produce a
+ * superset of the reference's "discriminant >= 0" spheres and share the resolve phase, so the
+ * closest hit is the same. */
+enum { UECRT_SCAN_AUTO = 0, UECRT_SCAN_FP32 = 1, UECRT_SCAN_TENSOR = 2 };
 
 typedef struct {
   uint64_t rays_traced;  /* closest-hit scans executed (one per path segment)          */
@@ -85,6 +93,8 @@ typedef struct {
   int32_t sm_count, sm_clock_khz;
   int32_t k1_blocks, k1_threads, k1_smem_bytes, k1_regs;
   int32_t tiles, tile_spheres; /* 1 tile = scene resident in shared memory */
+  int32_t scan_mode;           /* UECRT_SCAN_FP32 or UECRT_SCAN_TENSOR: what K1 ran with */
+  int32_t reserved_;
 } uecrt_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
@@ -115,6 +125,11 @@ void uecrt_set_tile_spheres(uint32_t spheres_per_tile);
 /* Paths per K1 thread that share one sweep of the scene; applies to scenes loaded afterwards.
  * 2 is honoured only by builds with -DUECRT_ENABLE_RAYS2 (measured slower on B200; see kernels.cu). */
 void uecrt_set_rays_per_thread(int rays);
+
+/* Process default for calls that force neither scan (UECRT_SCAN_AUTO picks the tensor-core scan when
+ * the scene fits its shared-memory residency limit, uecrt_tensor_scan_max_spheres(), else FP32). */
+void uecrt_set_scan_mode(int uecrt_scan_mode);
+int uecrt_tensor_scan_max_spheres(void);
 
 /* uecrt_primary_hits replaces hittable_list::hit_impl (hittable_list.hpp:32-58) on caller
  * rays: closest hit in the CLOSED interval [t_min, t_max], later index wins ties.

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
-FLAG_EXACT_HITS, FLAG_NO_COUNTERS = 1, 2
+FLAG_EXACT_HITS, FLAG_NO_COUNTERS, FLAG_SCAN_FP32, FLAG_SCAN_TENSOR = 1, 2, 4, 8
+SCAN_AUTO, SCAN_FP32, SCAN_TENSOR = 0, 1, 2
 
 
 class UecrtError(RuntimeError):
@@ -34,7 +35,7 @@ class StatsStruct(C.Structure):
                 ("kernel_ms", C.c_double), ("reduce_ms", C.c_double), ("resolve_ms", C.c_double),
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("sm_count", C.c_int32), ("sm_clock_khz", C.c_int32),
                 ("k1_blocks", C.c_int32), ("k1_threads", C.c_int32), ("k1_smem_bytes", C.c_int32), ("k1_regs", C.c_int32),
-                ("tiles", C.c_int32), ("tile_spheres", C.c_int32)]
+                ("tiles", C.c_int32), ("tile_spheres", C.c_int32), ("scan_mode", C.c_int32), ("reserved_", C.c_int32)]
 
 
 # UECRT_LIB selects an alternative build of the same ABI (kernel tuning experiments only)
@@ -42,7 +43,7 @@ lib_path = os.environ.get("UECRT_LIB") or os.path.join(os.path.dirname(os.path.a
 
 # every symbol include/uecrt.h and include/uecrt_host.h declare
 EXPORTS = [
-    "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_primary_hits", "uecrt_scatter",
+    "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_set_scan_mode", "uecrt_tensor_scan_max_spheres", "uecrt_primary_hits", "uecrt_scatter",
     "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_ctx_set_scene", "uecrt_accumulate_device", "uecrt_resolve_device",
     "uecrt_ctx_stats", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
     "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox", "uecrt_host_scene_file_count", "uecrt_host_scene_file_fill",
@@ -65,6 +66,9 @@ def _load():
     L.uecrt_set_tile_spheres.restype = None
     L.uecrt_set_rays_per_thread.argtypes = [C.c_int]
     L.uecrt_set_rays_per_thread.restype = None
+    L.uecrt_set_scan_mode.argtypes = [C.c_int]
+    L.uecrt_set_scan_mode.restype = None
+    L.uecrt_tensor_scan_max_spheres.restype = C.c_int
     L.uecrt_primary_hits.argtypes = [vp, u64, vp, vp, dbl, dbl, C.c_int, vp, vp, vp, vp]
     L.uecrt_scatter.argtypes = [u64] + [vp] * 11
     L.uecrt_philox.argtypes = [u64, u64, vp, vp]

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import (CameraStruct, ParamsStruct, SceneStruct, StatsStruct, UecrtError, check, lib,
-                   FLAG_EXACT_HITS)
+                   FLAG_EXACT_HITS, FLAG_SCAN_FP32, FLAG_SCAN_TENSOR, SCAN_AUTO, SCAN_FP32, SCAN_TENSOR)
 
 
 def _ptr(a):
@@ -104,15 +104,19 @@ def _params(width, height, spp, max_depth, seed, sample_begin=0, sample_count=0,
     return ParamsStruct(width, height, spp, max_depth, seed, sample_begin, sample_count, num_gpus, flags)
 
 
+_SCAN_FLAGS = {None: 0, "auto": 0, "fp32": FLAG_SCAN_FP32, "tensor": FLAG_SCAN_TENSOR}
+
+
 def render(scene, camera, width=400, spp=100, max_depth=50, seed=0, gpus=1, exact=False, return_accum=False,
-           sample_begin=0, sample_count=0):
+           sample_begin=0, sample_count=0, scan=None):
     """uecrt_render with HOST buffers: the call the re-hosted yk::render() makes."""
     height = image_height(width)
     rgb = np.zeros((height, width, 3), np.uint8)
     accum = np.zeros((height, width, 4), np.float32) if return_accum else None
     st = StatsStruct()
     sc, cam = scene.struct(), camera.struct()
-    p = _params(width, height, spp, max_depth, seed, sample_begin, sample_count, gpus, FLAG_EXACT_HITS if exact else 0)
+    p = _params(width, height, spp, max_depth, seed, sample_begin, sample_count, gpus,
+                (FLAG_EXACT_HITS if exact else 0) | _SCAN_FLAGS[scan])
     check(lib.uecrt_render(C.byref(sc), C.byref(cam), C.byref(p), _ptr(rgb), _ptr(accum) if return_accum else None,
                            C.byref(st)), "uecrt_render")
     return rgb, accum, stats_to_dict(st)
@@ -212,3 +216,12 @@ def set_tile_spheres(n):
 def set_rays_per_thread(n):
     """Paths per K1 thread sharing one scene scan (1 or 2); applies to scenes loaded afterwards."""
     lib.uecrt_set_rays_per_thread(int(n))
+
+
+def set_scan_mode(mode):
+    """'auto' | 'fp32' | 'tensor': process default of the candidate scan (include/uecrt.h UECRT_SCAN_*)."""
+    lib.uecrt_set_scan_mode({"auto": SCAN_AUTO, "fp32": SCAN_FP32, "tensor": SCAN_TENSOR}[mode])
+
+
+def tensor_scan_max_spheres():
+    return int(lib.uecrt_tensor_scan_max_spheres())

@@ -31,6 +31,7 @@
 #include "kernels.cuh"
 #include "materials.cuh"
 #include "philox.cuh"
+#include "tc_collect.cuh"
 
 namespace uecrt {
 
@@ -530,6 +531,175 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
 }
 
 // ---------------------------------------------------------------------------------------
+// K1 / K2 on the TENSOR-CORE scan (tc_scan.cuh, tc_collect.cuh).  Same path loop, same candidate
+// lists, same resolve and shading as above; only the all-pairs discriminant evaluation moves from
+// the FP32 pipe to tcgen05.mma.kind::tf32 (three-way TF32 split, FP32 accumulation in TMEM).
+// CTA = 4 groups of 128 consumer threads (one path each) + 4 issuer warps; 1 CTA per SM; the
+// lifted sphere operand (128 B per sphere) stays resident in shared memory.
+template <bool EXACT>
+__device__ __forceinline__ void tc_closest_hit(tc::Consumer& pc, int nchunks, const DeviceScene& sc,
+                                               const CandList<tc::kConsumers>& L, const RayQuery& q, Hit& h) {
+  ScanRay sr = make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz);
+  if (!q.live) sr.thr = 0x7f800000;              // +inf: a dead slot never produces a candidate
+  h.id = -1;
+  int cnt = 0;
+  if (!EXACT) {
+    FastBest best{CUDART_INF_F, -1};
+    tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
+      fold_full_fast<tc::kConsumers>(sc.geom, L.base, c, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, &best);
+    });
+    if (!q.live) return;
+    resolve_fast(sc.geom, L, cnt, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best);
+    if (best.id >= 0) {
+      h.id = best.id;
+      h.t = best.t;
+      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+    }
+  } else {
+    ExactBest best{(double)CUDART_INF, -1};
+    const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
+    const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
+    tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
+      fold_full_exact<tc::kConsumers>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, &best);
+    });
+    if (!q.live) return;
+    resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best);
+    if (best.id >= 0) {
+      const float4 g = __ldg(&sc.geom[best.id]);
+      const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
+      const double rad = g.w;
+      double nx = (px - (double)g.x) / rad, ny = (py - (double)g.y) / rad, nz = (pz - (double)g.z) / rad;   // sphere.hpp:44
+      const bool front = (Dx * nx + Dy * ny + Dz * nz) < 0;                                     // hittable.hpp:25
+      if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+      h.id = best.id; h.t = (float)best.t; h.front = front;
+      h.px = (float)px; h.py = (float)py; h.pz = (float)pz;
+      h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
+    }
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const RenderArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int nchunks = a.sc.tc_nrows / tc::kNC;
+  const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, (uint32_t)a.sc.tc_nrows * 128u);
+  const unsigned lane = threadIdx.x & 31u;
+  if (threadIdx.x >= tc::kConsumers) {
+    if (lane == 0) tc::issuer_loop(smem_raw, (int)(threadIdx.x - tc::kConsumers) >> 5, tmem_base, nchunks);
+  } else {
+    tc::Consumer pc = tc::make_consumer(smem_raw, tmem_base, nchunks);
+    CandList<tc::kConsumers> L;
+    L.base = reinterpret_cast<uint16_t*>(smem_raw + tc::kHeaderBytes + (size_t)a.sc.tc_nrows * 128 + (size_t)tc::kGroups * tc::kATileBytes) + threadIdx.x;
+    const uint32_t bar_id = 1u + threadIdx.x / tc::kGroupThreads;
+    const unsigned long long n_pixels = a.n_slots;
+    const double inv_np = 1.0 / (double)n_pixels;
+    const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
+    PathState st{};
+    st.dz = 1.f; st.dlen = 1.f; st.self_id = -1;
+    unsigned n_rays = 0, n_paths = 0;
+    for (;;) {
+      slot_refill_and_start(st, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+      // the 128 threads of a group sweep the scene together: leave only when all of them are done
+      if (tc::group_all(bar_id, tc::kGroupThreads, st.done)) { tc::consumer_stop(pc); break; }
+      const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
+      Hit h;
+      tc_closest_hit<EXACT>(pc, nchunks, a.sc, L, q, h);
+      if (st.active) {
+        ++n_rays;
+        slot_shade(st, h, a, n_paths);
+      }
+    }
+    if (a.count_stats) {
+      unsigned r = n_rays, p = n_paths;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+      if (lane == 0) {
+        atomicAdd(a.counters + 1, (unsigned long long)r);
+        atomicAdd(a.counters + 2, (unsigned long long)p);
+      }
+    }
+  }
+  tc::cta_teardown(tmem_base);
+}
+
+// K2 on the tensor-core scan: every consumer thread takes one caller ray per round; all CTAs run
+// the same number of rounds (threads past the end of the ray array carry has_ray = false).
+template <bool EXACT>
+__global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const DeviceScene sc, unsigned long long n_rays,
+                                                                     const float* __restrict__ o, const float* __restrict__ d,
+                                                                     double tmin, double tmax, double* __restrict__ t_out,
+                                                                     double* __restrict__ n_out, int32_t* __restrict__ id_out,
+                                                                     uint8_t* __restrict__ ff_out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int nchunks = sc.tc_nrows / tc::kNC;
+  const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, (uint32_t)sc.tc_nrows * 128u);
+  if (threadIdx.x >= tc::kConsumers) {
+    if ((threadIdx.x & 31u) == 0) tc::issuer_loop(smem_raw, (int)(threadIdx.x - tc::kConsumers) >> 5, tmem_base, nchunks);
+  } else {
+    tc::Consumer pc = tc::make_consumer(smem_raw, tmem_base, nchunks);
+    CandList<tc::kConsumers> L;
+    L.base = reinterpret_cast<uint16_t*>(smem_raw + tc::kHeaderBytes + (size_t)sc.tc_nrows * 128 + (size_t)tc::kGroups * tc::kATileBytes) + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * tc::kConsumers;
+    const unsigned long long batches = (n_rays + stride - 1) / stride;
+    for (unsigned long long b = 0; b < batches; ++b) {
+      const unsigned long long i = b * stride + (unsigned long long)blockIdx.x * tc::kConsumers + threadIdx.x;
+      const bool has_ray = i < n_rays;
+      const unsigned long long j = has_ray ? i : 0;
+      const float ox = o[3 * j], oy = o[3 * j + 1], oz = o[3 * j + 2];
+      const float rx = d[3 * j], ry = d[3 * j + 1], rz = d[3 * j + 2];
+      const float dlen = sqrtf(fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
+      const float inv = 1.0f / dlen;
+      const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
+      ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
+      if (!has_ray) sr.thr = 0x7f800000;
+      int cnt = 0;
+      double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
+      int id = -1;
+      bool front = false;
+      if (!EXACT) {
+        const float tmin_w = (float)tmin * dlen;
+        FastBest best{(float)tmax * dlen, -1};
+        tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
+          fold_full_fast<tc::kConsumers>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
+        });
+        if (has_ray) resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
+        if (has_ray && best.id >= 0) {
+          Hit h; h.id = best.id; h.t = best.t;
+          finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+          id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
+        }
+      } else {
+        const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
+        const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
+        ExactBest best{tmax, -1};
+        tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
+          fold_full_exact<tc::kConsumers>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
+        });
+        if (has_ray) resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
+        if (has_ray && best.id >= 0) {
+          const float4 g = __ldg(&sc.geom[best.id]);
+          const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
+                       pz = __dadd_rn(Oz, __dmul_rn(Dz, best.t));                                   // ray.hpp:16-19
+          const double r = g.w;
+          nx = __ddiv_rn(__dsub_rn(px, (double)g.x), r);                                             // sphere.hpp:44
+          ny = __ddiv_rn(__dsub_rn(py, (double)g.y), r);
+          nz = __ddiv_rn(__dsub_rn(pz, (double)g.z), r);
+          front = __dadd_rn(__dadd_rn(__dmul_rn(Dx, nx), __dmul_rn(Dy, ny)), __dmul_rn(Dz, nz)) < 0;  // hittable.hpp:25
+          if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+          id = best.id; t = best.t;
+        }
+      }
+      if (has_ray) {
+        t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
+        id_out[i] = id; ff_out[i] = front ? 1 : 0;
+      }
+    }
+    tc::consumer_stop(pc);
+  }
+  tc::cta_teardown(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------
 // K3: to_color3b (source.cpp:73-83): sum / spp -> sqrt -> clamp [0, 0.999] -> * 256 -> truncate.
 // Done in double like the reference (the input is an FP32 sum); NaN / negative -> 0.
 __global__ void k_resolve(const float4* __restrict__ accum, uint32_t n_pixels, uint32_t spp, uint8_t* __restrict__ rgb) {
@@ -646,6 +816,51 @@ void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const
   else if (exact) k_primary_hits<true, false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
   else if (tiled) k_primary_hits<false, true><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
   else k_primary_hits<false, false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+}
+
+// ---- tensor-core scan variants
+int tc_max_spheres() {
+  const size_t fixed = tc::smem_bytes(0, (uint32_t)(tc::kConsumers * kListCap * sizeof(uint16_t)));
+  return (int)((232448 - fixed) / 128 / tc::kNC * tc::kNC);
+}
+int tc_threads() { return tc::kThreads; }
+int tc_chunk() { return tc::kNC; }
+size_t tc_smem_bytes(int tc_nrows) { return tc::smem_bytes((uint32_t)tc_nrows, (uint32_t)(tc::kConsumers * kListCap * sizeof(uint16_t))); }
+
+cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
+  cudaError_t e;
+  static bool attrs_set[16] = {};
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if (dev < 16 && !attrs_set[dev]) {
+    const int optin = 232448;
+#define UECRT_SET(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+    UECRT_SET(k_render_paths_tc<false>) UECRT_SET(k_render_paths_tc<true>)
+    UECRT_SET(k_primary_hits_tc<false>) UECRT_SET(k_primary_hits_tc<true>)
+#undef UECRT_SET
+    attrs_set[dev] = true;
+  }
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, k_render_paths_tc<false>)) != cudaSuccess) return e;
+  if (regs_render) *regs_render = fa.numRegs;
+  int n1 = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths_tc<false>, tc::kThreads, smem)) != cudaSuccess) return e;
+  return n1 >= 1 ? cudaSuccess : cudaErrorInvalidConfiguration;
+}
+
+void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t smem, cudaStream_t st) {
+  if (exact) k_render_paths_tc<true><<<blocks, tc::kThreads, smem, st>>>(a);
+  else k_render_paths_tc<false><<<blocks, tc::kThreads, smem, st>>>(a);
+}
+
+void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
+                            double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, int sm_count,
+                            cudaStream_t st) {
+  const size_t smem = tc_smem_bytes(sc.tc_nrows);
+  unsigned long long want = (n_rays + tc::kConsumers - 1) / tc::kConsumers;
+  const int blocks = (int)(want < 1 ? 1 : (want > (unsigned long long)sm_count ? (unsigned long long)sm_count : want));
+  if (exact) k_primary_hits_tc<true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  else k_primary_hits_tc<false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
 }
 
 void launch_resolve(const float4* accum, uint32_t n_pixels, uint32_t spp, uint8_t* rgb, cudaStream_t st) {

@@ -13,6 +13,8 @@ struct DeviceScene {
   const float4* geom;        // {cx,cy,cz,r}
   const uint32_t* mat_type;
   const float4* mat_param;
+  const unsigned char* tc_rows;   // tensor-core scan operand (scene_pack.hpp pack_scene_tc), or null when the scene is too large
+  int tc_nrows;                   // rows (spheres padded to a multiple of tc::kNC)
 };
 
 struct DeviceCamera {
@@ -54,5 +56,16 @@ void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4
                     uint8_t* scattered, float* att, float* o_out, float* d_out, cudaStream_t st);
 void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st);
 cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled, int rays);
+
+// ---- tensor-core scan variants (tc_scan.cuh): resident scenes of up to tc_max_spheres() spheres
+int tc_max_spheres();
+int tc_threads();
+int tc_chunk();
+size_t tc_smem_bytes(int tc_nrows);
+cudaError_t configure_kernels_tc(int* regs_render, size_t smem);
+void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t smem, cudaStream_t st);
+void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,
+                            double tmin, double tmax, bool exact, double* t, double* nrm, int32_t* id,
+                            uint8_t* ff, int sm_count, cudaStream_t st);
 
 }  // namespace uecrt

@@ -18,9 +18,11 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "../../include/uecrt.h"
+#include "tc_scan.cuh"
 
 namespace uecrt {
 
@@ -74,6 +76,52 @@ inline PackedScene pack_scene(const uecrt_scene& sc, uint32_t tile_spheres = 0) 
     float* q = &p.pairs[((size_t)tile * stride + within) * 8];
     q[0 + half] = -sc.geom[i].x; q[2 + half] = -sc.geom[i].y; q[4 + half] = -sc.geom[i].z;
     q[6 + half] = round_up_to_float(-k + bound);
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core scan operand (tc_scan.cuh): one 32-slot row per sphere, rows padded to a multiple
+// of `chunk` with never-hit rows, stored in the UMMA K-major no-swizzle canonical layout.
+//   b = [cx^2, cy^2, cz^2, cx cy, cx cz, cy cz, -cx, -cy, -cz, nk],  nk = -(|c|^2 - r^2) + bound
+// (the ray side carries -q in slots 6..8, so the product is +q.c).
+//
+// Error bound of the tensor-core evaluation of G = f - P against the exact value on the same
+// float inputs (u = 2^-24, S = sum |a_i b_i| <= 3|c|^2 + |o|^2 + r^2):
+//   TF32 3-way split + TMEM accumulation   <= 12 u S measured (tools/microbench/tc_probe.cu,
+//                                             1.7e7 pairs of a final-scene-like world), taken as 24 u S
+//   rounding of the lifted ray vector      <= u|c|^2 + 4u(|o|^2 + |c|^2)
+//   rounding of the lifted sphere vector   <= 1.5 u|c|^2
+//   rounding of P                          <= 4 u|o|^2
+//   direction not exactly unit (|d|^2 = 1 +- 6u) <= 12u(|o|^2 + |c|^2) + 6u r^2
+//   => |G_tc - G_exact| <= 44u|o|^2 + 91u|c|^2 + 31u r^2
+// applied as 80u|o|^2 on the ray (kRayBound, closest_hit.cuh) and 128u|c|^2 + 40u r^2 here.
+struct PackedSceneTc {
+  uint32_t n = 0, rows = 0;              // spheres, padded rows (multiple of chunk)
+  std::vector<unsigned char> bytes;      // rows * 128
+};
+
+inline PackedSceneTc pack_scene_tc(const uecrt_scene& sc, uint32_t chunk) {
+  PackedSceneTc p;
+  p.n = sc.n;
+  p.rows = (sc.n + chunk - 1) / chunk * chunk;
+  if (p.rows == 0) p.rows = chunk;
+  p.bytes.assign((size_t)p.rows * 128, 0);
+  const double u = 5.9604644775390625e-8;
+  for (uint32_t i = 0; i < p.rows; ++i) {
+    float b[tc::kTerms] = {0, 0, 0, 0, 0, 0, 0, 0, 0, -1e30f};   // never-hit pad row
+    if (i < sc.n) {
+      const double cx = sc.geom[i].x, cy = sc.geom[i].y, cz = sc.geom[i].z, r = sc.geom[i].w;
+      const double c2 = cx * cx + cy * cy + cz * cz;
+      const double bound = 128.0 * u * c2 + 40.0 * u * r * r;
+      b[0] = (float)(cx * cx); b[1] = (float)(cy * cy); b[2] = (float)(cz * cz);
+      b[3] = (float)(cx * cy); b[4] = (float)(cx * cz); b[5] = (float)(cy * cz);
+      b[6] = -sc.geom[i].x; b[7] = -sc.geom[i].y; b[8] = -sc.geom[i].z;
+      b[9] = round_up_to_float(-(c2 - r * r) + bound);
+    }
+    float row[tc::kSlots];
+    tc::fill_row_b(b, row);
+    for (uint32_t ch = 0; ch < 8; ++ch) std::memcpy(&p.bytes[tc::row_chunk_offset(i, ch)], &row[4 * ch], 16);
   }
   return p;
 }

@@ -118,11 +118,22 @@ struct uecrt_ctx {
   uint32_t cap_n = 0;      // spheres allocated for geom / materials
   bool configured = false;
   int rays = 1;            // paths per K1 thread
+  // tensor-core scan (tc_scan.cuh): available when the scene fits its residency limit
+  void* d_tc = nullptr;
+  size_t cap_tc = 0;
+  size_t smem_tc = 0;
+  int regs_tc = 0;
+  int last_scan_mode = UECRT_SCAN_FP32, last_threads = uecrt::kRenderThreads, last_regs = 0;
+  size_t last_smem = 0;
 };
 
 namespace {
 
 std::atomic<uint32_t> g_tile_spheres{0};   // 0 = automatic (uecrt_set_tile_spheres)
+std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
+#ifndef UECRT_AUTO_SCAN
+#define UECRT_AUTO_SCAN UECRT_SCAN_FP32   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
+#endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
 constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists = 73 KB -> 3 CTAs per SM
 constexpr size_t kSmemOptin = 232448;
@@ -162,6 +173,20 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     CUDA_TRY(cudaMemcpy(c->d_mat_type, scene->mat_type, (size_t)scene->n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_mat_param, scene->mat_param, (size_t)scene->n * sizeof(uecrt_float4), cudaMemcpyHostToDevice));
   }
+  // tensor-core scan operand (128 B per sphere, resident): only when the scene fits
+  c->sc.tc_rows = nullptr; c->sc.tc_nrows = 0; c->smem_tc = 0;
+  if ((int)scene->n <= uecrt::tc_max_spheres()) {
+    const uecrt::PackedSceneTc pt = uecrt::pack_scene_tc(*scene, (uint32_t)uecrt::tc_chunk());
+    if (pt.bytes.size() > c->cap_tc) {
+      cudaFree(c->d_tc); c->d_tc = nullptr; c->cap_tc = 0;
+      CUDA_TRY(cudaMalloc(&c->d_tc, pt.bytes.size()));
+      c->cap_tc = pt.bytes.size();
+    }
+    CUDA_TRY(cudaMemcpy(c->d_tc, pt.bytes.data(), pt.bytes.size(), cudaMemcpyHostToDevice));
+    c->sc.tc_rows = static_cast<const unsigned char*>(c->d_tc);
+    c->sc.tc_nrows = (int)pt.rows;
+    c->smem_tc = uecrt::tc_smem_bytes((int)pt.rows);
+  }
   c->n = scene->n;
   c->sc.pairs = static_cast<const ulonglong2*>(c->d_pairs);
   c->sc.npairs = (int)ps.tile_pairs;
@@ -179,7 +204,7 @@ void ctx_free(uecrt_ctx* c) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
-  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters);
+  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   cudaSetDevice(prev);
@@ -212,6 +237,8 @@ int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* ca
   if ((e = uecrt::configure_kernels(&c->regs, c->blocks_per_sm, c->smem, c->sc.ntiles > 1, c->rays)) != cudaSuccess)
     return fail(UECRT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e));
   if (c->blocks_per_sm[0] < 1 || c->blocks_per_sm[1] < 1) return fail(UECRT_ERR_CUDA, "K1 does not fit on an SM (smem %zu B)", c->smem);
+  if (c->sc.tc_rows && (e = uecrt::configure_kernels_tc(&c->regs_tc, c->smem_tc)) != cudaSuccess)
+    return fail(UECRT_ERR_CUDA, "tensor-scan kernel configuration failed: %s", cudaGetErrorString(e));
   c->timed = false;
   return UECRT_OK;
 }
@@ -283,6 +310,19 @@ void release_workspaces() {
   cudaSetDevice(prev);
 }
 
+// which scan a call runs with: forced by flag, else the process default, else UECRT_AUTO_SCAN when the scene fits
+int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
+  int want = (flags & UECRT_FLAG_SCAN_TENSOR) ? UECRT_SCAN_TENSOR : (flags & UECRT_FLAG_SCAN_FP32) ? UECRT_SCAN_FP32 : g_scan_mode.load();
+  const bool forced = want != UECRT_SCAN_AUTO;
+  if (want == UECRT_SCAN_AUTO) want = UECRT_AUTO_SCAN;
+  if (want == UECRT_SCAN_TENSOR && !ctx->sc.tc_rows) {
+    if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but the scene has %u spheres (resident limit %d)", ctx->n, uecrt::tc_max_spheres());
+    want = UECRT_SCAN_FP32;
+  }
+  *out = want;
+  return UECRT_OK;
+}
+
 int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream_t st) {
   if (!ctx || !p || !d_accum) return fail(UECRT_ERR_INVALID, "null argument");
   if (p->width == 0 || p->height == 0) return fail(UECRT_ERR_INVALID, "empty image");
@@ -303,10 +343,18 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
   CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
   const bool exact = (p->flags & UECRT_FLAG_EXACT_HITS) != 0;
-  const int blocks = ctx->sm_count * ctx->blocks_per_sm[exact ? 1 : 0];
+  int mode = 0;
+  if ((rc_mode(p->flags, ctx, &mode))) return UECRT_ERR_INVALID;
+  const bool tensor = mode == UECRT_SCAN_TENSOR;
+  const int blocks = tensor ? ctx->sm_count : ctx->sm_count * ctx->blocks_per_sm[exact ? 1 : 0];
   ctx->last_blocks = blocks;
+  ctx->last_scan_mode = mode;
+  ctx->last_threads = tensor ? uecrt::tc_threads() : uecrt::kRenderThreads;
+  ctx->last_smem = tensor ? ctx->smem_tc : ctx->smem;
+  ctx->last_regs = tensor ? ctx->regs_tc : ctx->regs;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  uecrt::launch_render_paths(a, exact, ctx->rays, blocks, uecrt::kRenderThreads, ctx->smem, st);
+  if (tensor) uecrt::launch_render_paths_tc(a, exact, blocks, ctx->smem_tc, st);
+  else uecrt::launch_render_paths(a, exact, ctx->rays, blocks, uecrt::kRenderThreads, ctx->smem, st);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->timed = true;
@@ -317,8 +365,9 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   if (!ctx || !out) return fail(UECRT_ERR_INVALID, "null argument");
   std::memset(out, 0, sizeof *out);
   out->sm_count = ctx->sm_count; out->sm_clock_khz = ctx->sm_clock_khz;
-  out->k1_blocks = ctx->last_blocks; out->k1_threads = uecrt::kRenderThreads;
-  out->k1_smem_bytes = (int32_t)ctx->smem; out->k1_regs = ctx->regs;
+  out->k1_blocks = ctx->last_blocks; out->k1_threads = ctx->last_threads;
+  out->k1_smem_bytes = (int32_t)(ctx->last_smem ? ctx->last_smem : ctx->smem); out->k1_regs = ctx->last_regs ? ctx->last_regs : ctx->regs;
+  out->scan_mode = ctx->last_scan_mode;
   out->tiles = ctx->sc.ntiles; out->tile_spheres = ctx->sc.npairs * 2;
   if (!ctx->timed) return UECRT_OK;
   CUDA_TRY(cudaEventSynchronize(ctx->ev1));
@@ -552,6 +601,8 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 
 void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
+void uecrt_set_scan_mode(int m) { g_scan_mode.store((m == UECRT_SCAN_FP32 || m == UECRT_SCAN_TENSOR) ? m : UECRT_SCAN_AUTO); }
+int uecrt_tensor_scan_max_spheres(void) { return uecrt::tc_max_spheres(); }
 void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store((rays == 2 && uecrt::max_rays_per_thread() == 2) ? 2 : 1); }
 
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
@@ -572,7 +623,10 @@ int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o
     CUDA_TRY(cudaMalloc(&d_id, n_rays * sizeof(int32_t))); CUDA_TRY(cudaMalloc(&d_ff, n_rays));
     CUDA_TRY(cudaMemcpy(d_o, o_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_d, d_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    uecrt::launch_primary_hits(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
+    int mode = 0;
+    if (rc_mode(0, c, &mode)) return UECRT_ERR_INVALID;
+    if (mode == UECRT_SCAN_TENSOR) uecrt::launch_primary_hits_tc(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, c->sm_count, 0);
+    else uecrt::launch_primary_hits(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(t, d_t, n_rays * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(n_xyz, d_n, n_rays * 3 * sizeof(double), cudaMemcpyDeviceToHost));
