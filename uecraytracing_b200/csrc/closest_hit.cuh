@@ -73,6 +73,7 @@ struct ScanRay {
   float dx, dy, dz;        // unit direction
   float nqx, nqy, nqz;     // -q = 2((o.d)d - o)
   int thr;                 // bit pattern of P lowered by the ray part of the error bound, clamped to >= +0
+  float p_low;             // the same lowered P before the clamp (tensor-core scan: subtracted inside the MMA)
 };
 
 // Fraction of |o|^2 by which the ray part of the discriminant bound lowers P (scene_pack.hpp).
@@ -88,6 +89,7 @@ __device__ __forceinline__ ScanRay make_scan_ray(float ox, float oy, float oz, f
   // f >= P as a signed-integer compare needs P >= +0: a lowered P below zero becomes +0, which only
   // adds candidates (every f with a clear sign bit), never drops one
   s.thr = __float_as_int(fmaxf(P, 0.0f));
+  s.p_low = P;
   return s;
 }
 
@@ -104,67 +106,70 @@ struct CandList {
 // t is the distance along the UNIT direction; tmin is 0.001*|d| in those units.
 struct FastBest { float t; int id; };
 
+// one candidate sphere j against the running best (sphere.hpp:32-39 + hittable_list.hpp:37-44)
+__device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j, float ox, float oy, float oz, float dx,
+                                          float dy, float dz, float tmin, int self_id, FastBest& best) {
+  const float4 g = __ldg(&geom[j]);
+  const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
+  const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
+  float t;
+  if (j == self_id) {
+    // the ray starts ON this sphere: the roots are exactly 0 and -2*hb (reference: the
+    // ~1e-16 self-hit is below t_min = 0.001 and only the far root can be accepted)
+    t = -2.0f * hb;
+    if (!(t >= tmin)) return;
+  } else {
+    const float lx = fmaf(-hb, dx, ocx), ly = fmaf(-hb, dy, ocy), lz = fmaf(-hb, dz, ocz);
+    const float disc = fmaf(g.w, g.w, -fmaf(lz, lz, fmaf(ly, ly, lx * lx)));
+    if (disc < 0.0f) return;                         // sphere.hpp:32
+    const float s = sqrt_fast(disc);
+    t = -hb - s;                                      // sphere.hpp:35
+    if (t < tmin) {                                   // sphere.hpp:36-39 (t_max test below)
+      t = -hb + s;
+      if (t < tmin) return;
+    }
+  }
+  if (t <= best.t) { best.t = t; best.id = j; }       // closed interval: later index wins ties
+}
+
 template <int STRIDE>
 __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, const CandList<STRIDE>& L, int cnt,
                                              float ox, float oy, float oz, float dx, float dy, float dz,
                                              float tmin, int self_id, FastBest& best) {
-  for (int e = 0; e < cnt; ++e) {
-    const int j = L.base[e * STRIDE];
-    const float4 g = __ldg(&geom[j]);
-    const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
-    const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
-    float t;
-    if (j == self_id) {
-      // the ray starts ON this sphere: the roots are exactly 0 and -2*hb (reference: the
-      // ~1e-16 self-hit is below t_min = 0.001 and only the far root can be accepted)
-      t = -2.0f * hb;
-      if (!(t >= tmin)) continue;
-    } else {
-      const float lx = fmaf(-hb, dx, ocx), ly = fmaf(-hb, dy, ocy), lz = fmaf(-hb, dz, ocz);
-      const float disc = fmaf(g.w, g.w, -fmaf(lz, lz, fmaf(ly, ly, lx * lx)));
-      if (disc < 0.0f) continue;                       // sphere.hpp:32
-      const float s = sqrt_fast(disc);
-      t = -hb - s;                                      // sphere.hpp:35
-      if (t < tmin) {                                   // sphere.hpp:36-39 (t_max test below)
-        t = -hb + s;
-        if (t < tmin) continue;
-      }
-    }
-    if (t <= best.t) { best.t = t; best.id = j; }       // closed interval: later index wins ties
-  }
+  for (int e = 0; e < cnt; ++e) test_fast(geom, L.base[e * STRIDE], ox, oy, oz, dx, dy, dz, tmin, self_id, best);
 }
-
 // ---------------------------------------------------------------------------------------
 // Phase 2, EXACT: FP64 with the reference's operation order.  (dx,dy,dz) is the direction the
 // caller wants t measured in (the ORIGINAL unnormalised direction for K2, so t == the
 // reference's root; the unit direction inside K1).
 struct ExactBest { double t; int id; };
 
+__device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int j, double ox, double oy, double oz, double dx,
+                                           double dy, double dz, double a, double tmin, ExactBest& best) {
+  const float4 g = __ldg(&geom[j]);
+  const double cx = g.x, cy = g.y, cz = g.z, r = g.w;
+  const double ocx = __dsub_rn(ox, cx), ocy = __dsub_rn(oy, cy), ocz = __dsub_rn(oz, cz);     // sphere.hpp:27
+  const double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));  // :29
+  const double oc2 = __dadd_rn(__dadd_rn(__dmul_rn(ocx, ocx), __dmul_rn(ocy, ocy)), __dmul_rn(ocz, ocz));
+  const double c = __dsub_rn(oc2, __dmul_rn(r, r));                                            // :30
+  const double disc = __dsub_rn(__dmul_rn(half_b, half_b), __dmul_rn(a, c));                   // :31
+  if (disc < 0.0) return;                                                                       // :32
+  const double sqrtd = __dsqrt_rn(disc);                                                        // :33
+  double root = __ddiv_rn(__dsub_rn(-half_b, sqrtd), a);                                       // :35
+  if (root < tmin || best.t < root) {                                                           // :36
+    root = __ddiv_rn(__dadd_rn(-half_b, sqrtd), a);                                            // :37
+    if (root < tmin || best.t < root) return;                                                   // :38
+  }
+  best.t = root;                                                                                // hittable_list.hpp:40-41
+  best.id = j;
+}
+
 template <int STRIDE>
 __device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, const CandList<STRIDE>& L, int cnt,
                                               double ox, double oy, double oz, double dx, double dy, double dz,
                                               double a, double tmin, ExactBest& best) {
-  for (int e = 0; e < cnt; ++e) {
-    const int j = L.base[e * STRIDE];
-    const float4 g = __ldg(&geom[j]);
-    const double cx = g.x, cy = g.y, cz = g.z, r = g.w;
-    const double ocx = __dsub_rn(ox, cx), ocy = __dsub_rn(oy, cy), ocz = __dsub_rn(oz, cz);     // sphere.hpp:27
-    const double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));  // :29
-    const double oc2 = __dadd_rn(__dadd_rn(__dmul_rn(ocx, ocx), __dmul_rn(ocy, ocy)), __dmul_rn(ocz, ocz));
-    const double c = __dsub_rn(oc2, __dmul_rn(r, r));                                            // :30
-    const double disc = __dsub_rn(__dmul_rn(half_b, half_b), __dmul_rn(a, c));                   // :31
-    if (disc < 0.0) continue;                                                                     // :32
-    const double sqrtd = __dsqrt_rn(disc);                                                        // :33
-    double root = __ddiv_rn(__dsub_rn(-half_b, sqrtd), a);                                       // :35
-    if (root < tmin || best.t < root) {                                                           // :36
-      root = __ddiv_rn(__dadd_rn(-half_b, sqrtd), a);                                            // :37
-      if (root < tmin || best.t < root) continue;                                                 // :38
-    }
-    best.t = root;                                                                                // hittable_list.hpp:40-41
-    best.id = j;
-  }
+  for (int e = 0; e < cnt; ++e) test_exact(geom, L.base[e * STRIDE], ox, oy, oz, dx, dy, dz, a, tmin, best);
 }
-
 // ---------------------------------------------------------------------------------------
 // Phase 1: the scan.  pairs: shared memory, 2 x 16 B per sphere pair
 //   A = {-cx0, -cx1, -cy0, -cy1},  B = {-cz0, -cz1, nk0, nk1},  nk = -(|c|^2 - r^2) + bound

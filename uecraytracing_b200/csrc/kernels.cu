@@ -531,25 +531,33 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
 }
 
 // ---------------------------------------------------------------------------------------
-// K1 / K2 on the TENSOR-CORE scan (tc_scan.cuh, tc_collect.cuh).  Same path loop, same candidate
-// lists, same resolve and shading as above; only the all-pairs discriminant evaluation moves from
-// the FP32 pipe to tcgen05.mma.kind::tf32 (three-way TF32 split, FP32 accumulation in TMEM).
-// CTA = 4 groups of 128 consumer threads (one path each) + 4 issuer warps; 1 CTA per SM; the
-// lifted sphere operand (128 B per sphere) stays resident in shared memory.
+// K1 / K2 on the TENSOR-CORE scan (tc_scan.cuh, tc_collect.cuh).  Same path loop, same resolve and
+// shading as above; only the all-pairs discriminant evaluation moves from the FP32 pipe to
+// tcgen05.mma.kind::tf32 (three-way TF32 split, FP32 accumulation in TMEM), and the CTA is
+// warp-specialised: 4 shade groups of 128 threads, one scan warpgroup, one issuer warp (1 CTA/SM).
+#ifdef UECRT_TC_PROFILE
+struct TcProf { long long t[8]; long long last; };
+#define UECRT_TCP(p, i) { __syncwarp(); const long long now_ = clock64(); (p).t[i] += now_ - (p).last; (p).last = now_; }
+#else
+struct TcProf {};
+#define UECRT_TCP(p, i)
+#endif
+
+// closest hit of one shade thread's ray through the pipeline; every shade thread calls it once per round
 template <bool EXACT>
-__device__ __forceinline__ void tc_closest_hit(tc::Consumer& pc, int nchunks, const DeviceScene& sc,
-                                               const CandList<tc::kConsumers>& L, const RayQuery& q, Hit& h) {
-  ScanRay sr = make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz);
-  if (!q.live) sr.thr = 0x7f800000;              // +inf: a dead slot never produces a candidate
+__device__ __forceinline__ void tc_closest_hit(const tc::Shade& sh, uint32_t round, const DeviceScene& sc, const RayQuery& q, Hit& h,
+                                               TcProf& prof) {
+  const ScanRay sr = make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz);
   h.id = -1;
-  int cnt = 0;
+  tc::shade_submit(sh, sr, q.live);
+  UECRT_TCP(prof, 2)
+  tc::shade_wait(sh, round);
+  UECRT_TCP(prof, 3)
+  if (!q.live) return;
+  const int nwords = sc.tc_nrows >> 5;
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
-      fold_full_fast<tc::kConsumers>(sc.geom, L.base, c, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, &best);
-    });
-    if (!q.live) return;
-    resolve_fast(sc.geom, L, cnt, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best);
+    tc::for_each_candidate(sh, nwords, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
@@ -559,11 +567,7 @@ __device__ __forceinline__ void tc_closest_hit(tc::Consumer& pc, int nchunks, co
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
-      fold_full_exact<tc::kConsumers>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, &best);
-    });
-    if (!q.live) return;
-    resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best);
+    tc::for_each_candidate(sh, nwords, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
     if (best.id >= 0) {
       const float4 g = __ldg(&sc.geom[best.id]);
       const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
@@ -584,31 +588,55 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   const int nchunks = a.sc.tc_nrows / tc::kNC;
   const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, (uint32_t)a.sc.tc_nrows * 128u);
   const unsigned lane = threadIdx.x & 31u;
-  if (threadIdx.x >= tc::kConsumers) {
-    if (lane == 0) tc::issuer_loop(smem_raw, (int)(threadIdx.x - tc::kConsumers) >> 5, tmem_base, nchunks);
+  if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
+    tc::reg_dealloc<tc::kIssuerRegs>();
+    if (threadIdx.x == tc::kShadeThreads + tc::kScanThreads) tc::issuer_role(smem_raw, tmem_base, nchunks, -1);
+  } else if (threadIdx.x >= tc::kShadeThreads) {
+    tc::reg_alloc<tc::kScanRegs>();
+    tc::scanner_role(smem_raw, tmem_base, nchunks, -1, a.counters);
   } else {
-    tc::Consumer pc = tc::make_consumer(smem_raw, tmem_base, nchunks);
-    CandList<tc::kConsumers> L;
-    L.base = reinterpret_cast<uint16_t*>(smem_raw + tc::kHeaderBytes + (size_t)a.sc.tc_nrows * 128 + (size_t)tc::kGroups * tc::kATileBytes) + threadIdx.x;
-    const uint32_t bar_id = 1u + threadIdx.x / tc::kGroupThreads;
+    tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
+    const tc::Shade sh = tc::make_shade(smem_raw, nchunks);
     const unsigned long long n_pixels = a.n_slots;
     const double inv_np = 1.0 / (double)n_pixels;
     const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
     PathState st{};
     st.dz = 1.f; st.dlen = 1.f; st.self_id = -1;
     unsigned n_rays = 0, n_paths = 0;
-    for (;;) {
+    TcProf prof{};
+#ifdef UECRT_TC_PROFILE
+    unsigned long long pc_rounds = 0;
+#endif
+    for (uint32_t round = 0; tc::round_continues(hdr, round, -1); ++round) {
+#ifdef UECRT_TC_PROFILE
+      prof.last = clock64();
+      const long long pc_start = prof.last;
+#endif
       slot_refill_and_start(st, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
-      // the 128 threads of a group sweep the scene together: leave only when all of them are done
-      if (tc::group_all(bar_id, tc::kGroupThreads, st.done)) { tc::consumer_stop(pc); break; }
+      // termination vote (tc_scan.cuh): this warp's flag of this round, stored before its a_ready arrive
+      const bool warp_done = __all_sync(0xffffffffu, st.done);
+      if (lane == 0) hdr->done_flags[round & 7u][threadIdx.x >> 5] = warp_done ? 1 : 0;
+      UECRT_TCP(prof, 0)
       const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
       Hit h;
-      tc_closest_hit<EXACT>(pc, nchunks, a.sc, L, q, h);
+      tc_closest_hit<EXACT>(sh, round, a.sc, q, h, prof);
+      UECRT_TCP(prof, 4)
       if (st.active) {
         ++n_rays;
         slot_shade(st, h, a, n_paths);
       }
+#ifdef UECRT_TC_PROFILE
+      UECRT_TCP(prof, 5)
+      prof.t[6] += prof.last - pc_start;
+      ++pc_rounds;
+#endif
     }
+#ifdef UECRT_TC_PROFILE
+    if (lane == 0) {
+      atomicAdd(a.counters + 4, pc_rounds);
+      for (int i = 0; i < 7; ++i) atomicAdd(a.counters + 5 + i, (unsigned long long)prof.t[i]);
+    }
+#endif
     if (a.count_stats) {
       unsigned r = n_rays, p = n_paths;
 #pragma unroll
@@ -622,8 +650,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   tc::cta_teardown(tmem_base);
 }
 
-// K2 on the tensor-core scan: every consumer thread takes one caller ray per round; all CTAs run
-// the same number of rounds (threads past the end of the ray array carry has_ray = false).
+// K2 on the tensor-core scan: every shade thread takes one caller ray per round; all CTAs run the
+// same number of rounds (threads past the end of the ray array carry has_ray = false).
 template <bool EXACT>
 __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const DeviceScene sc, unsigned long long n_rays,
                                                                      const float* __restrict__ o, const float* __restrict__ d,
@@ -633,16 +661,19 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int nchunks = sc.tc_nrows / tc::kNC;
   const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, (uint32_t)sc.tc_nrows * 128u);
-  if (threadIdx.x >= tc::kConsumers) {
-    if ((threadIdx.x & 31u) == 0) tc::issuer_loop(smem_raw, (int)(threadIdx.x - tc::kConsumers) >> 5, tmem_base, nchunks);
+  const unsigned long long stride = (unsigned long long)gridDim.x * tc::kShadeThreads;
+  const int batches = (int)((n_rays + stride - 1) / stride);
+  if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
+    tc::reg_dealloc<tc::kIssuerRegs>();
+    if (threadIdx.x == tc::kShadeThreads + tc::kScanThreads) tc::issuer_role(smem_raw, tmem_base, nchunks, batches);
+  } else if (threadIdx.x >= tc::kShadeThreads) {
+    tc::reg_alloc<tc::kScanRegs>();
+    tc::scanner_role(smem_raw, tmem_base, nchunks, batches);
   } else {
-    tc::Consumer pc = tc::make_consumer(smem_raw, tmem_base, nchunks);
-    CandList<tc::kConsumers> L;
-    L.base = reinterpret_cast<uint16_t*>(smem_raw + tc::kHeaderBytes + (size_t)sc.tc_nrows * 128 + (size_t)tc::kGroups * tc::kATileBytes) + threadIdx.x;
-    const unsigned long long stride = (unsigned long long)gridDim.x * tc::kConsumers;
-    const unsigned long long batches = (n_rays + stride - 1) / stride;
-    for (unsigned long long b = 0; b < batches; ++b) {
-      const unsigned long long i = b * stride + (unsigned long long)blockIdx.x * tc::kConsumers + threadIdx.x;
+    const tc::Shade sh = tc::make_shade(smem_raw, nchunks);
+    const int nwords = sc.tc_nrows >> 5;
+    for (int b = 0; b < batches; ++b) {
+      const unsigned long long i = (unsigned long long)b * stride + (unsigned long long)blockIdx.x * tc::kShadeThreads + threadIdx.x;
       const bool has_ray = i < n_rays;
       const unsigned long long j = has_ray ? i : 0;
       const float ox = o[3 * j], oy = o[3 * j + 1], oz = o[3 * j + 2];
@@ -650,20 +681,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
       const float dlen = sqrtf(fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
       const float inv = 1.0f / dlen;
       const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
-      ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
-      if (!has_ray) sr.thr = 0x7f800000;
-      int cnt = 0;
+      const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
+      tc::shade_submit(sh, sr, has_ray);
+      tc::shade_wait(sh, (uint32_t)b);
+      if (!has_ray) continue;
       double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
       int id = -1;
       bool front = false;
       if (!EXACT) {
         const float tmin_w = (float)tmin * dlen;
         FastBest best{(float)tmax * dlen, -1};
-        tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
-          fold_full_fast<tc::kConsumers>(sc.geom, L.base, c, ox, oy, oz, dx, dy, dz, tmin_w, -1, &best);
-        });
-        if (has_ray) resolve_fast(sc.geom, L, cnt, ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
-        if (has_ray && best.id >= 0) {
+        tc::for_each_candidate(sh, nwords, [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+        if (best.id >= 0) {
           Hit h; h.id = best.id; h.t = best.t;
           finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
           id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
@@ -672,11 +701,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
         const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
         ExactBest best{tmax, -1};
-        tc::collect(pc, nchunks, sr, L, cnt, [&](int c) {
-          fold_full_exact<tc::kConsumers>(sc.geom, L.base, c, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, &best);
-        });
-        if (has_ray) resolve_exact(sc.geom, L, cnt, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best);
-        if (has_ray && best.id >= 0) {
+        tc::for_each_candidate(sh, nwords, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+        if (best.id >= 0) {
           const float4 g = __ldg(&sc.geom[best.id]);
           const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
                        pz = __dadd_rn(Oz, __dmul_rn(Dz, best.t));                                   // ray.hpp:16-19
@@ -689,12 +715,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
           id = best.id; t = best.t;
         }
       }
-      if (has_ray) {
-        t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
-        id_out[i] = id; ff_out[i] = front ? 1 : 0;
-      }
+      t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
+      id_out[i] = id; ff_out[i] = front ? 1 : 0;
     }
-    tc::consumer_stop(pc);
   }
   tc::cta_teardown(tmem_base);
 }
@@ -820,12 +843,12 @@ void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const
 
 // ---- tensor-core scan variants
 int tc_max_spheres() {
-  const size_t fixed = tc::smem_bytes(0, (uint32_t)(tc::kConsumers * kListCap * sizeof(uint16_t)));
+  const size_t fixed = tc::make_layout(0).total;
   return (int)((232448 - fixed) / 128 / tc::kNC * tc::kNC);
 }
 int tc_threads() { return tc::kThreads; }
 int tc_chunk() { return tc::kNC; }
-size_t tc_smem_bytes(int tc_nrows) { return tc::smem_bytes((uint32_t)tc_nrows, (uint32_t)(tc::kConsumers * kListCap * sizeof(uint16_t))); }
+size_t tc_smem_bytes(int tc_nrows) { return tc::make_layout((uint32_t)tc_nrows).total; }
 
 cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
   cudaError_t e;
@@ -857,7 +880,7 @@ void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, co
                             double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, int sm_count,
                             cudaStream_t st) {
   const size_t smem = tc_smem_bytes(sc.tc_nrows);
-  unsigned long long want = (n_rays + tc::kConsumers - 1) / tc::kConsumers;
+  unsigned long long want = (n_rays + tc::kShadeThreads - 1) / tc::kShadeThreads;
   const int blocks = (int)(want < 1 ? 1 : (want > (unsigned long long)sm_count ? (unsigned long long)sm_count : want));
   if (exact) k_primary_hits_tc<true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
   else k_primary_hits_tc<false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);

@@ -1,7 +1,8 @@
-// tc_collect.cuh -- consumer side of the tensor-core scan: one ray per thread, candidates into the
-// same per-thread shared-memory list the FP32 scan fills (closest_hit.cuh), so the resolve phase
-// (reference root selection, closed interval, later index wins: hittable_list.hpp:32-58,
-// sphere.hpp:32-39) is shared by both scans.
+// tc_collect.cuh -- the SCAN role and the shade-side hand-off of the tensor-core scan.  The scan
+// leaves one candidate BITMAP per ray (bit set = the sphere's discriminant may be >= 0); the shade
+// thread walks the set bits in ascending sphere index and applies the same per-candidate test as
+// the FP32 scan's resolve phase (closest_hit.cuh test_fast / test_exact: reference root selection,
+// closed interval, later index wins -- hittable_list.hpp:32-58, sphere.hpp:32-39).
 #pragma once
 #include "closest_hit.cuh"
 #include "tc_scan.cuh"
@@ -9,63 +10,108 @@
 namespace uecrt {
 namespace tc {
 
-// One round: publish this thread's lifted ray as row `c.row` of the group's A tile, then read the
-// f values of this ray against every sphere chunk from TMEM as the issuer's MMAs complete.
-// EVERY consumer thread of the group must call this once per round (a thread without a live ray
-// passes ray.thr = +inf).  cnt returns the number of candidates left in the list.
-template <int STRIDE, class OnFull>
-__device__ __forceinline__ void collect(Consumer& c, int nchunks, const ScanRay& ray, const CandList<STRIDE>& L, int& cnt,
-                                        OnFull&& on_full) {
-  {
-    const float a[kTerms] = {ray.dx * ray.dx, ray.dy * ray.dy, ray.dz * ray.dz, 2.0f * ray.dx * ray.dy, 2.0f * ray.dx * ray.dz,
-                             2.0f * ray.dy * ray.dz, ray.nqx, ray.nqy, ray.nqz, 1.0f};
-    float row[kSlots];
-    fill_row_a(a, row);
-    store_row(c.a_tile, c.row, row);
-    fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
-    mbar_arrive(c.a_ready);
-  }
-  constexpr uint32_t kEntryBytes = (uint32_t)STRIDE * (uint32_t)sizeof(uint16_t);
-  constexpr uint32_t kFullAt = (uint32_t)(kListCap - 8) * kEntryBytes;   // < 8 free entries left
-  unsigned char* lbase = reinterpret_cast<unsigned char*>(L.base);
-  uint32_t ofs = 0;
-  const int thr = ray.thr;
-  const unsigned lane = threadIdx.x & 31u;
-  for (int j = 0; j < nchunks; ++j) {
-    const uint32_t s = c.seq++, b = s & 1u;
-    mbar_wait(c.full0 + 8u * b, (s >> 1) & 1u);
-    fence_after_sync();
-#pragma unroll
-    for (int blk = 0; blk < kNC / 32; ++blk) {
-      int v[32];
-      __syncwarp();
-      tmem_ld32(c.taddr + b * kNC + blk * 32, v);
-      tmem_ld_wait();
-      if (blk == kNC / 32 - 1) {       // this warp holds the whole buffer in registers: hand it back
-        fence_before_sync();
-        if (lane == 0) mbar_arrive(c.empty0 + 8u * b);
-      }
-      // f >= P as an integer compare of the bit patterns (P >= +0): 8-wide integer maxima, one branch per 32
-      int m8[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        m8[k] = max(max(max(v[8 * k], v[8 * k + 1]), max(v[8 * k + 2], v[8 * k + 3])),
-                    max(max(v[8 * k + 4], v[8 * k + 5]), max(v[8 * k + 6], v[8 * k + 7])));
-      if (max(max(m8[0], m8[1]), max(m8[2], m8[3])) >= thr) {
-        const int i0 = j * kNC + blk * 32;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (m8[k] >= thr) {
-            if (ofs > kFullAt) { on_full((int)(ofs / kEntryBytes)); ofs = 0; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (v[8 * k + i] >= thr) { *reinterpret_cast<uint16_t*>(lbase + ofs) = (uint16_t)(i0 + 8 * k + i); ofs += kEntryBytes; }
-          }
-        }
-      }
+// SHADE: publish this thread's ray for the current round.  A thread without a live ray passes
+// live = false: its row is still written (every row of the tile takes part in the MMA) with
+// P = +1e30, so all its accumulators come out negative and its bitmap is empty.
+__device__ __forceinline__ void shade_submit(const Shade& s, const ScanRay& ray, bool live) {
+  const float a[kTerms] = {ray.dx * ray.dx, ray.dy * ray.dy, ray.dz * ray.dz, 2.0f * ray.dx * ray.dy, 2.0f * ray.dx * ray.dz,
+                           2.0f * ray.dy * ray.dz, ray.nqx, ray.nqy, ray.nqz, 1.0f};
+  float row[kSlots];
+  fill_row_a(a, live ? ray.p_low : 1e30f, row);
+  store_row(s.a_tile, s.row, row);
+  fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+  mbar_arrive(s.a_ready);
+}
+// SHADE: wait for the bitmaps of round r
+__device__ __forceinline__ void shade_wait(const Shade& s, uint32_t round) { mbar_wait(s.scan_done, round & 1u); }
+
+// SHADE: f(sphere index) for every candidate of this thread's ray, ascending index
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const Shade& s, int nwords, F&& f) {
+  for (int w = 0; w < nwords; ++w) {
+    uint32_t m = s.bitmap[w * kShadeThreads];
+    while (m) {
+      const int b = __clz((int)m);
+      f(w * 32 + b);
+      m &= ~(0x80000000u >> b);
     }
   }
-  cnt = (int)(ofs / kEntryBytes);
+}
+
+// 32 accumulators -> one bitmap word: bit (31 - i) = (v[i] >= 0).  Four independent funnel-shift
+// chains (mask = (mask << 1) | sign(v)), merged with byte permutes.
+__device__ __forceinline__ uint32_t sign_word(const int (&v)[32]) {
+  uint32_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = __funnelshift_l((uint32_t)v[8 * k + i], m, 1);
+    c[k] = m;
+  }
+  const uint32_t hi = __byte_perm(c[1], c[0], 0x0040);   // low 16 bits = (c0 << 8) | c1
+  const uint32_t lo = __byte_perm(c[3], c[2], 0x0040);   // low 16 bits = (c2 << 8) | c3
+  return ~__byte_perm(lo, hi, 0x5410);                   // a set sign bit = NOT a candidate
+}
+
+// SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
+__device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds,
+                                             unsigned long long* prof_counters = nullptr) {
+#ifdef UECRT_TC_PROFILE
+  long long pw = 0, pl = 0, ps = 0, plast = clock64();
+  unsigned long long ptiles = 0;
+#define UECRT_TCS(acc) { const long long now_ = clock64(); acc += now_ - plast; plast = now_; }
+#else
+#define UECRT_TCS(acc)
+#endif
+  Header* h = reinterpret_cast<Header*>(smem_raw);
+  const Layout lay = make_layout((uint32_t)nchunks * kNC);
+  const uint32_t row = threadIdx.x - kShadeThreads, lane = row & 31u;
+  const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
+  const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]);
+  const uint32_t ready0 = smem_addr(&h->a_ready[0]), done0 = smem_addr(&h->scan_done[0]);
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw + lay.bitmap);
+  uint32_t seq = 0;
+  for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
+    for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
+      uint32_t* out = bitmap + g * kGroupThreads + row;       // word w of this ray at out[w * kShadeThreads]
+      for (int j = 0; j < nchunks; ++j, ++seq) {
+        const uint32_t slot = seq % kRing, use = seq / kRing;
+        mbar_wait(full0 + 8u * slot, use & 1u);
+        fence_after_sync();
+        UECRT_TCS(pw)
+        const uint32_t t0 = lane_taddr + slot * kNC;
+        uint32_t* o = out + (size_t)j * (kNC / 32) * kShadeThreads;
+        int va[32], vb[32];
+        tmem_ld32(t0, va);
+        tmem_ld32(t0 + 32, vb);
+        tmem_ld_wait();
+        o[0] = sign_word(va);
+        tmem_ld32(t0 + 64, va);
+        o[kShadeThreads] = sign_word(vb);
+        tmem_ld32(t0 + 96, vb);
+        tmem_ld_wait();
+        fence_before_sync();                              // the whole slot is in registers: hand it back
+        if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+        o[2 * kShadeThreads] = sign_word(va);
+        o[3 * kShadeThreads] = sign_word(vb);
+        UECRT_TCS(pl)
+      }
+      mbar_arrive(done0 + 8u * g);
+#ifdef UECRT_TC_PROFILE
+      ++ptiles;
+      UECRT_TCS(ps)
+#endif
+    }
+  }
+#ifdef UECRT_TC_PROFILE
+  if (prof_counters && lane == 0) {
+    atomicAdd(prof_counters + 12, ptiles);
+    atomicAdd(prof_counters + 13, (unsigned long long)pw);
+    atomicAdd(prof_counters + 14, (unsigned long long)pl);
+    atomicAdd(prof_counters + 15, (unsigned long long)ps);
+  }
+#endif
 }
 
 }  // namespace tc

@@ -10,7 +10,9 @@
 // the 5th-generation tensor cores as tcgen05.mma.kind::tf32 with FP32 accumulation in TMEM.  TF32
 // keeps 11 significand bits, so every operand is split a = a_hi + a_lo (each exactly representable
 // in TF32) and the product is taken as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi: 3 x 10 = 30 of the 32
-// K slots of four K=8 MMA steps.  All products of TF32 values are exact in FP32; what is lost is
+// K slots of four K=8 MMA steps; the last two slots carry -P (hi, lo) against a sphere-side 1, so
+// the accumulator holds G = f - P and a sphere is a candidate iff G >= 0, i.e. iff the SIGN BIT of
+// the TMEM word is clear.  All products of TF32 values are exact in FP32; what is lost is
 // a_lo*b_lo (<= 2^-22 |a||b|), the truncation of the lo parts (<= 2^-21 each) and the accumulator's
 // own rounding.  The bound on the sum of those is applied exactly like the FP32 scan's bound
 // (scene_pack.hpp): the sphere part raises -k, the ray part lowers P, so {f >= P} stays a SUPERSET
@@ -54,15 +56,17 @@ __host__ __device__ inline void split_tf32(float v, float& hi, float& lo) {
 #endif
 }
 
-// K-slot order of one row.  A (ray) side: [hi(10) | hi(10) | lo(10) | 0 0];  B (sphere) side:
-// [hi(10) | lo(10) | hi(10) | 0 0]  ->  sum over slots = hi.hi + hi.lo + lo.hi.
-__host__ __device__ inline void fill_row_a(const float (&a)[kTerms], float (&row)[kSlots]) {
+// K-slot order of one row.  A (ray) side: [hi(10) | hi(10) | lo(10) | -P_hi -P_lo];  B (sphere) side:
+// [hi(10) | lo(10) | hi(10) | 1 1]  ->  sum over slots = hi.hi + hi.lo + lo.hi - P.
+__host__ __device__ inline void fill_row_a(const float (&a)[kTerms], float p, float (&row)[kSlots]) {
   for (int i = 0; i < kTerms; ++i) {
     float h, l;
     split_tf32(a[i], h, l);
     row[i] = h; row[kTerms + i] = h; row[2 * kTerms + i] = l;
   }
-  row[30] = 0.f; row[31] = 0.f;
+  float ph, pl;
+  split_tf32(p, ph, pl);
+  row[30] = -ph; row[31] = -pl;
 }
 __host__ __device__ inline void fill_row_b(const float (&b)[kTerms], float (&row)[kSlots]) {
   for (int i = 0; i < kTerms; ++i) {
@@ -70,7 +74,7 @@ __host__ __device__ inline void fill_row_b(const float (&b)[kTerms], float (&row
     split_tf32(b[i], h, l);
     row[i] = h; row[kTerms + i] = l; row[2 * kTerms + i] = h;
   }
-  row[30] = 0.f; row[31] = 0.f;
+  row[30] = 1.f; row[31] = 1.f;
 }
 
 #ifdef __CUDACC__
@@ -160,52 +164,74 @@ __device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_smem, uin
     mma_tf32(d_tmem, make_smem_desc(a_smem + s * 256u), make_smem_desc(b_smem + s * 256u), idesc, s);
 }
 // ---------------------------------------------------------------------------------------
-// Producer / consumer pipeline of one CTA.
-//   kGroups groups of 128 CONSUMER threads (one ray each; thread t of a group = TMEM lane t = row t
-//   of the group's A tile) + one ISSUER warp per group (lane 0 issues the group's MMAs).
-//   TMEM: group g owns 2 buffers of kNC columns at column (2g + b) * kNC (4 x 2 x 64 = 512).
-//   Barriers per group: a_ready (128 arrivals: every consumer stored its A row), full[b] (tcgen05.commit:
-//   the MMAs of one chunk into buffer b are complete), empty[b] (4 arrivals: every consumer warp has
-//   read buffer b).  Chunks are numbered by a sequence number that runs across rounds; chunk s uses
-//   buffer s & 1 and is the (s >> 1)-th use of it, which gives every barrier its phase parity.
+// Warp-specialised pipeline of one CTA (kThreads = 768 threads = 6 warpgroups, 1 CTA per SM; launched
+// at 80 registers per thread, then setmaxnreg moves registers from the issuer warpgroup (-> 32) to
+// the scan warpgroup (-> 128), whose two 32-register TMEM loads in flight do not fit in 80):
+//   SHADE   4 groups x 128 threads (warps 0-15): each thread owns one path; per round it publishes
+//           its lifted ray as row t of the group's A tile (+ its threshold P), waits for the group's
+//           candidate lists, resolves the closest hit and shades.
+//   ISSUER  lane 0 of warp 20 (warps 21-23 only donate their registers): for round r = 0, 1, ... and group g = 0..3 IN THAT FIXED ORDER it waits
+//           for the group's A tile and issues the MMAs of every sphere chunk into a ring of kRing
+//           TMEM slots of kNC columns (4 x 128 = all 512 columns).
+//   SCAN    warps 16-19 (warp 16+q owns TMEM lanes 32q..32q+31): consume the ring in the same fixed
+//           order; thread t reads the f values of ray row t of the current group with
+//           tcgen05.ld.32x32b (two loads in flight) and packs the 32 sign bits of every load into
+//           one word of that ray's candidate BITMAP in shared memory (funnel shifts: no compare,
+//           no branch, no divergence; bit 31 of word w = sphere 32w).
+// Barriers (all mbarriers with deterministic phase parity):
+//   a_ready[g]   128 arrivals (shade threads of group g): the A tile of round r is stored
+//   tmem_full[s] 1 arrival (tcgen05.commit): the MMAs of the chunk in ring slot s are complete
+//   tmem_empty[s] 4 arrivals (scan warps): slot s has been read into registers
+//   scan_done[g] 128 arrivals (scan threads): the bitmaps of group g, round r are complete
+// Ring slots are numbered by a sequence number running across groups and rounds (slot = seq % kRing,
+// use = seq / kRing, parity = use & 1).
+// Termination: every shade warp stores "all my paths are done" for round r into done_flags[r & 7]
+// before its a_ready arrive; EVERY role leaves at the first round r >= 2 for which all 16 flags of
+// round r-2 are set.  All roles are within two rounds of each other and the flags of round r-2
+// are ordered before anything a role does in round r by the barrier chain, so all roles read the
+// same values and leave at the same round.  (fixed_rounds >= 0: exactly that many rounds, K2.)
 constexpr int kGroups = 4;
 constexpr int kGroupThreads = 128;
-constexpr int kConsumers = kGroups * kGroupThreads;          // 512
-constexpr int kThreads = kConsumers + 32 * kGroups;          // 640: + one issuer warp per group
-constexpr int kNC = 64;                                      // spheres (TMEM columns) per chunk
+constexpr int kShadeThreads = kGroups * kGroupThreads;       // 512
+constexpr int kScanThreads = 128;
+constexpr int kThreads = kShadeThreads + kScanThreads + 128; // 768: + the issuer warpgroup (one working warp)
+constexpr int kScanRegs = 128, kIssuerRegs = 32;             // setmaxnreg targets (launch allocation: 80)
+constexpr int kNC = 128;                                     // spheres (TMEM columns) per ring slot
+constexpr int kRing = 4;                                     // ring slots
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kATileBytes = 128u * kSlots * 4u;         // 16 KB per group
 constexpr uint32_t kHeaderBytes = 1024;
 
-struct GroupBars {            // 64 B
-  uint64_t a_ready, full[2], empty[2];
-  uint32_t stop;
-  uint32_t pad[5];
-};
 struct Header {               // first kHeaderBytes of dynamic shared memory
-  GroupBars g[kGroups];
+  uint64_t a_ready[kGroups];
+  uint64_t scan_done[kGroups];
+  uint64_t tmem_full[kRing];
+  uint64_t tmem_empty[kRing];
   uint64_t b_loaded;          // the sphere operand has landed (cp.async.bulk)
   uint32_t tmem_base;
+  uint32_t pad_;
+  uint8_t done_flags[8][16];  // [round & 7][shade warp]
 };
+
+// smem layout: [Header][B: rows * 128 B][A: kGroups tiles][bitmap: rows/32 words x 512 rays]
+// bitmap word w of ray i lives at bitmap[w * 512 + i] (the 32 lanes of a warp touch consecutive words)
+struct Layout {
+  uint32_t b, a, bitmap, total;
+};
+__host__ __device__ inline Layout make_layout(uint32_t b_rows) {
+  Layout l;
+  l.b = kHeaderBytes;
+  l.a = l.b + b_rows * 128u;
+  l.bitmap = l.a + (uint32_t)kGroups * kATileBytes;
+  l.total = l.bitmap + (b_rows / 32u) * (uint32_t)kShadeThreads * 4u;
+  return l;
+}
+
+template <int R> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// named-barrier AND-reduction over the `count` threads that use barrier `id`
-__device__ __forceinline__ bool group_all(uint32_t id, uint32_t count, bool pred) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred pi, po;\n\tsetp.ne.u32 pi, %3, 0;\n\t"
-      "bar.red.and.pred po, %1, %2, pi;\n\tselp.u32 %0, 1, 0, po;\n\t}"
-      : "=r"(out)
-      : "r"(id), "r"(count), "r"((uint32_t)pred)
-      : "memory");
-  return out != 0;
-}
-
-// smem layout of the tensor-scan kernels: [Header][B rows * 128][kGroups A tiles][lists]
-__host__ __device__ inline size_t smem_bytes(uint32_t b_rows, uint32_t list_bytes) {
-  return kHeaderBytes + (size_t)b_rows * 128 + (size_t)kGroups * kATileBytes + list_bytes;
 }
 
 // CTA-wide setup: barriers, TMEM, the bulk copy of the sphere operand.  Every thread calls it.
@@ -213,12 +239,15 @@ __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const voi
   Header* h = reinterpret_cast<Header*>(smem_raw);
   if (threadIdx.x == 0) {
     for (int g = 0; g < kGroups; ++g) {
-      mbar_init(smem_addr(&h->g[g].a_ready), kGroupThreads);
-      mbar_init(smem_addr(&h->g[g].full[0]), 1); mbar_init(smem_addr(&h->g[g].full[1]), 1);
-      mbar_init(smem_addr(&h->g[g].empty[0]), 4); mbar_init(smem_addr(&h->g[g].empty[1]), 4);
-      h->g[g].stop = 0;
+      mbar_init(smem_addr(&h->a_ready[g]), kGroupThreads);
+      mbar_init(smem_addr(&h->scan_done[g]), kScanThreads);
+    }
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(smem_addr(&h->tmem_full[s]), 1);
+      mbar_init(smem_addr(&h->tmem_empty[s]), kScanThreads / 32);
     }
     mbar_init(smem_addr(&h->b_loaded), 1);
+    for (int i = 0; i < 8 * 16; ++i) (&h->done_flags[0][0])[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if ((threadIdx.x >> 5) == 0) tmem_alloc(smem_addr(&h->tmem_base), kTmemCols);
@@ -245,55 +274,54 @@ __device__ __forceinline__ void cta_teardown(uint32_t tmem_base) {
   if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// ISSUER: lane 0 of issuer warp `g`.  Runs until the group's consumers raise `stop`.
-__device__ __forceinline__ void issuer_loop(unsigned char* smem_raw, int g, uint32_t tmem_base, int nchunks) {
+__device__ __forceinline__ bool all_done_at(const Header* h, uint32_t r) {
+  const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(&h->done_flags[r & 7u][0]);
+  return (f[0] & f[1] & f[2] & f[3]) == 0x01010101u;
+}
+__device__ __forceinline__ bool round_continues(const Header* h, uint32_t r, int fixed_rounds) {
+  if (fixed_rounds >= 0) return r < (uint32_t)fixed_rounds;
+  return !(r >= 2u && all_done_at(h, r - 2u));
+}
+
+// ISSUER: one thread.
+__device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
-  GroupBars* gb = &h->g[g];
-  const uint32_t a_ready = smem_addr(&gb->a_ready), full0 = smem_addr(&gb->full[0]), empty0 = smem_addr(&gb->empty[0]);
-  const uint32_t b_smem = smem_addr(smem_raw + kHeaderBytes);
-  const uint32_t a_smem = b_smem + (uint32_t)nchunks * (kNC * 128u) + (uint32_t)g * kATileBytes;
-  const uint32_t d_tmem = tmem_base + (uint32_t)g * 2u * kNC;
-  const volatile uint32_t* stop = &gb->stop;
+  const Layout lay = make_layout((uint32_t)nchunks * kNC);
+  const uint32_t b_smem = smem_addr(smem_raw + lay.b), a_smem0 = smem_addr(smem_raw + lay.a);
+  const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), ready0 = smem_addr(&h->a_ready[0]);
   mbar_wait(smem_addr(&h->b_loaded), 0);
   uint32_t seq = 0;
-  for (uint32_t round = 0;; ++round) {
-    mbar_wait(a_ready, round & 1u);
-    if (*stop) break;
-    for (int j = 0; j < nchunks; ++j, ++seq) {
-      const uint32_t b = seq & 1u, use = seq >> 1;
-      if (use >= 1u) mbar_wait(empty0 + 8u * b, (use - 1u) & 1u);      // the consumers have read the previous contents
-      fence_after_sync();
-      issue_tile(d_tmem + b * kNC, a_smem, b_smem + (uint32_t)j * (kNC * 128u), kNC);
-      mma_commit(full0 + 8u * b);
+  for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
+    for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
+      mbar_wait(ready0 + 8u * g, r & 1u);
+      for (int j = 0; j < nchunks; ++j, ++seq) {
+        const uint32_t slot = seq % kRing, use = seq / kRing;
+        if (use >= 1u) mbar_wait(empty0 + 8u * slot, (use - 1u) & 1u);      // the scanners have read the previous contents
+        fence_after_sync();
+        issue_tile(tmem_base + slot * kNC, a_smem0 + g * kATileBytes, b_smem + (uint32_t)j * (kNC * 128u), kNC);
+        mma_commit(full0 + 8u * slot);
+      }
     }
   }
 }
 
-// CONSUMER state of one thread
-struct Consumer {
-  uint32_t a_ready, full0, empty0;   // shared addresses of the group's barriers
+// SHADE side of one thread
+struct Shade {
+  uint32_t a_ready, scan_done;       // shared addresses of the group's barriers
   unsigned char* a_tile;             // the group's A tile
-  uint32_t taddr;                    // TMEM address: this warp's lane quarter | the group's first column
-  uint32_t row;                      // row in the A tile == TMEM lane
-  uint32_t seq;                      // chunks consumed so far
-  volatile uint32_t* stop;
+  const uint32_t* bitmap;            // this ray's candidate bitmap: word w at bitmap[w * kShadeThreads]
+  uint32_t row;
 };
-__device__ __forceinline__ Consumer make_consumer(unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
+__device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, int nchunks) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
-  const int g = threadIdx.x / kGroupThreads;
-  Consumer c;
-  c.a_ready = smem_addr(&h->g[g].a_ready); c.full0 = smem_addr(&h->g[g].full[0]); c.empty0 = smem_addr(&h->g[g].empty[0]);
-  c.a_tile = smem_raw + kHeaderBytes + (size_t)nchunks * (kNC * 128u) + (size_t)g * kATileBytes;
-  c.row = threadIdx.x % kGroupThreads;
-  c.taddr = tmem_base + (uint32_t)g * 2u * kNC + ((((uint32_t)threadIdx.x >> 5) & 3u) * 32u << 16);
-  c.seq = 0;
-  c.stop = &h->g[g].stop;
-  return c;
-}
-// the group has no more rays: tell its issuer to leave (every consumer of the group calls this once)
-__device__ __forceinline__ void consumer_stop(Consumer& c) {
-  if (c.row == 0) *c.stop = 1u;
-  mbar_arrive(c.a_ready);
+  const Layout lay = make_layout((uint32_t)nchunks * kNC);
+  const uint32_t g = threadIdx.x / kGroupThreads;
+  Shade s;
+  s.a_ready = smem_addr(&h->a_ready[g]); s.scan_done = smem_addr(&h->scan_done[g]);
+  s.a_tile = smem_raw + lay.a + g * kATileBytes;
+  s.bitmap = reinterpret_cast<const uint32_t*>(smem_raw + lay.bitmap) + threadIdx.x;
+  s.row = threadIdx.x % kGroupThreads;
+  return s;
 }
 #endif  // __CUDACC__
 
