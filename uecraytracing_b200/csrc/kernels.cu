@@ -259,6 +259,34 @@ struct PathState {
   float thr_r, thr_g, thr_b;
 };
 
+// work item w -> (pixel, sample) of the path this slot runs next, or done when the queue is exhausted.
+// w = sample * n_slots + slot, slot = (tile << 5) | within: tiles of 8x4 pixels in row-major tile
+// order, so the 32 lanes of a warp start on a compact 8x4 pixel block (coherent rays).
+// FP64 / FP32 reciprocal estimates + fix-up instead of integer divides.
+__device__ __forceinline__ void slot_assign(PathState& p, const RenderArgs& a, unsigned long long w,
+                                            unsigned long long n_pixels, double inv_np) {
+  if (w < a.total_items) {
+    unsigned long long q = __double2ull_rz(__ull2double_rz(w) * inv_np);
+    long long rem = (long long)(w - q * n_pixels);
+    if (rem < 0) { --q; rem += (long long)n_pixels; }
+    if (rem >= (long long)n_pixels) { ++q; rem -= (long long)n_pixels; }
+    const uint32_t slot = (uint32_t)rem, tile = slot >> 5, within = slot & 31u;
+    uint32_t ty = (uint32_t)__fmul_rz((float)tile, a.inv_tiles_x);
+    uint32_t tx = tile - ty * a.tiles_x;
+    if ((int32_t)tx < 0) { --ty; tx += a.tiles_x; }
+    if (tx >= a.tiles_x) { ++ty; tx -= a.tiles_x; }
+    const uint32_t x = tx * 8u + (within & 7u), y = ty * 4u + (within >> 3);
+    p.pixel = y * a.width + x;
+    p.sample = a.sample_begin + (uint32_t)q;
+    p.valid = (x < a.width) && (y < a.height);      // ragged right / bottom edge of the tile grid
+  } else {
+    p.done = true;
+  }
+}
+
+__device__ __forceinline__ void slot_start_path(PathState& p, const RenderArgs& a, bool need, float inv_w, float inv_h,
+                                                unsigned& n_paths);
+
 // refill + start of the next path for one slot; warp-convergent (uses __ballot_sync)
 __device__ __forceinline__ void slot_refill_and_start(PathState& p, const RenderArgs& a, unsigned lane,
                                                       unsigned long long n_pixels, double inv_np, float inv_w,
@@ -271,30 +299,51 @@ __device__ __forceinline__ void slot_refill_and_start(PathState& p, const Render
     unsigned long long base = 0;
     if ((int)lane == leader) base = atomicAdd(a.counters, (unsigned long long)__popc(need_mask));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (need) {
-      const unsigned long long w = base + __popc(need_mask & ((1u << lane) - 1u));
-      if (w < a.total_items) {
-        // w = sample * n_slots + slot, slot = (tile << 5) | within: tiles of 8x4 pixels in row-major
-        // tile order, so the 32 lanes of a warp start on a compact 8x4 pixel block (coherent rays).
-        // FP64 / FP32 reciprocal estimates + fix-up instead of integer divides.
-        unsigned long long q = __double2ull_rz(__ull2double_rz(w) * inv_np);
-        long long rem = (long long)(w - q * n_pixels);
-        if (rem < 0) { --q; rem += (long long)n_pixels; }
-        if (rem >= (long long)n_pixels) { ++q; rem -= (long long)n_pixels; }
-        const uint32_t slot = (uint32_t)rem, tile = slot >> 5, within = slot & 31u;
-        uint32_t ty = (uint32_t)__fmul_rz((float)tile, a.inv_tiles_x);
-        uint32_t tx = tile - ty * a.tiles_x;
-        if ((int32_t)tx < 0) { --ty; tx += a.tiles_x; }
-        if (tx >= a.tiles_x) { ++ty; tx -= a.tiles_x; }
-        const uint32_t x = tx * 8u + (within & 7u), y = ty * 4u + (within >> 3);
-        p.pixel = y * a.width + x;
-        p.sample = a.sample_begin + (uint32_t)q;
-        p.valid = (x < a.width) && (y < a.height);      // ragged right / bottom edge of the tile grid
-      } else {
-        p.done = true;
-      }
-    }
+    if (need) slot_assign(p, a, base + __popc(need_mask & ((1u << lane) - 1u)), n_pixels, inv_np);
   }
+  slot_start_path(p, a, need, inv_w, inv_h, n_paths);
+}
+
+// Work items of a warp drawn from a range claimed one round AHEAD (tensor-scan K1): the global
+// atomicAdd that claims the next 32 items is issued when the previous claim is opened, and its
+// ~700-cycle round trip to L2 overlaps a whole scan instead of stalling the warp every round.
+// cur: [next, end) being handed out; nxt: start of the claimed-but-unopened range of kBatch items.
+struct WorkPool {
+  static constexpr unsigned kBatch = 32;
+  unsigned long long next, end, nxt;
+};
+__device__ __forceinline__ void pool_init(WorkPool& wp, const RenderArgs& a, unsigned lane) {
+  unsigned long long b0 = 0, b1 = 0;
+  if (lane == 0) { b0 = atomicAdd(a.counters, (unsigned long long)WorkPool::kBatch); b1 = atomicAdd(a.counters, (unsigned long long)WorkPool::kBatch); }
+  wp.next = __shfl_sync(0xffffffffu, b0, 0);
+  wp.end = wp.next + WorkPool::kBatch;
+  wp.nxt = __shfl_sync(0xffffffffu, b1, 0);
+}
+__device__ __forceinline__ void slot_refill_pooled(PathState& p, WorkPool& wp, const RenderArgs& a, unsigned lane,
+                                                   unsigned long long n_pixels, double inv_np, float inv_w, float inv_h,
+                                                   unsigned& n_paths) {
+  const bool need = !p.active && !p.done;
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+  if (need_mask) {
+    const unsigned n = __popc(need_mask), k = __popc(need_mask & ((1u << lane) - 1u));
+    const unsigned long long avail = wp.end - wp.next;
+    const unsigned long long w = k < avail ? wp.next + k : wp.nxt + (k - avail);
+    if (n <= avail) {
+      wp.next += n;
+    } else {                                   // open the range claimed earlier, claim the one after it
+      wp.next = wp.nxt + (n - avail);
+      wp.end = wp.nxt + WorkPool::kBatch;
+      unsigned long long b = 0;
+      if (lane == 0) b = atomicAdd(a.counters, (unsigned long long)WorkPool::kBatch);
+      wp.nxt = __shfl_sync(0xffffffffu, b, 0);   // consumed at the earliest one round from now
+    }
+    if (need) slot_assign(p, a, w, n_pixels, inv_np);
+  }
+  slot_start_path(p, a, need, inv_w, inv_h, n_paths);
+}
+
+__device__ __forceinline__ void slot_start_path(PathState& p, const RenderArgs& a, bool need, float inv_w, float inv_h,
+                                                unsigned& n_paths) {
   // start the path: camera ray (source.cpp:154-165, camera.hpp:29-32)
   if (need && !p.done && p.valid) {
     // pixel -> (row, column) without the ~20-instruction runtime integer divide: float reciprocal
@@ -545,7 +594,7 @@ struct TcProf {};
 
 // closest hit of one shade thread's ray through the pipeline; every shade thread calls it once per round
 template <bool EXACT>
-__device__ __forceinline__ void tc_closest_hit(const tc::Shade& sh, uint32_t round, const DeviceScene& sc, const RayQuery& q, Hit& h,
+__device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t round, const DeviceScene& sc, const RayQuery& q, Hit& h,
                                                TcProf& prof) {
   const ScanRay sr = make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz);
   h.id = -1;
@@ -553,11 +602,9 @@ __device__ __forceinline__ void tc_closest_hit(const tc::Shade& sh, uint32_t rou
   UECRT_TCP(prof, 2)
   tc::shade_wait(sh, round);
   UECRT_TCP(prof, 3)
-  if (!q.live) return;
-  const int nwords = sc.tc_nrows >> 5;
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    tc::for_each_candidate(sh, nwords, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+    tc::for_each_candidate(sh, q.live, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
@@ -567,7 +614,7 @@ __device__ __forceinline__ void tc_closest_hit(const tc::Shade& sh, uint32_t rou
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    tc::for_each_candidate(sh, nwords, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+    tc::for_each_candidate(sh, q.live, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
     if (best.id >= 0) {
       const float4 g = __ldg(&sc.geom[best.id]);
       const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
@@ -596,7 +643,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
     tc::scanner_role(smem_raw, tmem_base, nchunks, -1, a.counters);
   } else {
     tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
-    const tc::Shade sh = tc::make_shade(smem_raw, nchunks);
+    tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
     const unsigned long long n_pixels = a.n_slots;
     const double inv_np = 1.0 / (double)n_pixels;
     const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
@@ -607,12 +654,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
 #ifdef UECRT_TC_PROFILE
     unsigned long long pc_rounds = 0;
 #endif
+    WorkPool pool;
+    pool_init(pool, a, lane);
     for (uint32_t round = 0; tc::round_continues(hdr, round, -1); ++round) {
 #ifdef UECRT_TC_PROFILE
       prof.last = clock64();
       const long long pc_start = prof.last;
 #endif
-      slot_refill_and_start(st, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+      slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
       // termination vote (tc_scan.cuh): this warp's flag of this round, stored before its a_ready arrive
       const bool warp_done = __all_sync(0xffffffffu, st.done);
       if (lane == 0) hdr->done_flags[round & 7u][threadIdx.x >> 5] = warp_done ? 1 : 0;
@@ -635,7 +684,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
     if (lane == 0) {
       atomicAdd(a.counters + 4, pc_rounds);
       for (int i = 0; i < 7; ++i) atomicAdd(a.counters + 5 + i, (unsigned long long)prof.t[i]);
+      atomicAdd(a.counters + 16, sh.prof_trips);
     }
+#endif
+#ifdef UECRT_TC_PROFILE
+    atomicAdd(a.counters + 18, sh.prof_cands);
 #endif
     if (a.count_stats) {
       unsigned r = n_rays, p = n_paths;
@@ -670,8 +723,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role(smem_raw, tmem_base, nchunks, batches);
   } else {
-    const tc::Shade sh = tc::make_shade(smem_raw, nchunks);
-    const int nwords = sc.tc_nrows >> 5;
+    tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
     for (int b = 0; b < batches; ++b) {
       const unsigned long long i = (unsigned long long)b * stride + (unsigned long long)blockIdx.x * tc::kShadeThreads + threadIdx.x;
       const bool has_ray = i < n_rays;
@@ -684,14 +736,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
       const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
       tc::shade_submit(sh, sr, has_ray);
       tc::shade_wait(sh, (uint32_t)b);
-      if (!has_ray) continue;
       double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
       int id = -1;
       bool front = false;
       if (!EXACT) {
         const float tmin_w = (float)tmin * dlen;
         FastBest best{(float)tmax * dlen, -1};
-        tc::for_each_candidate(sh, nwords, [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+        tc::for_each_candidate(sh, has_ray, [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
         if (best.id >= 0) {
           Hit h; h.id = best.id; h.t = best.t;
           finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
@@ -701,7 +752,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
         const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
         ExactBest best{tmax, -1};
-        tc::for_each_candidate(sh, nwords, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+        tc::for_each_candidate(sh, has_ray, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
         if (best.id >= 0) {
           const float4 g = __ldg(&sc.geom[best.id]);
           const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
@@ -715,8 +766,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
           id = best.id; t = best.t;
         }
       }
-      t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
-      id_out[i] = id; ff_out[i] = front ? 1 : 0;
+      if (has_ray) {
+        t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
+        id_out[i] = id; ff_out[i] = front ? 1 : 0;
+      }
     }
   }
   tc::cta_teardown(tmem_base);
@@ -844,7 +897,8 @@ void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const
 // ---- tensor-core scan variants
 int tc_max_spheres() {
   const size_t fixed = tc::make_layout(0).total;
-  return (int)((232448 - fixed) / 128 / tc::kNC * tc::kNC);
+  const int fit = (int)((232448 - fixed) / (128 + 64) / tc::kNC * tc::kNC);   // 128 B operand + 64 B bitmap per sphere row
+  return fit < tc::kMaxRows ? fit : tc::kMaxRows;
 }
 int tc_threads() { return tc::kThreads; }
 int tc_chunk() { return tc::kNC; }

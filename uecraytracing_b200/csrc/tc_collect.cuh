@@ -10,30 +10,48 @@
 namespace uecrt {
 namespace tc {
 
-// SHADE: publish this thread's ray for the current round.  A thread without a live ray passes
-// live = false: its row is still written (every row of the tile takes part in the MMA) with
-// P = +1e30, so all its accumulators come out negative and its bitmap is empty.
+// SHADE: publish this thread's ray for the current round: its 32 K slots go to TMEM lane t of the group's
+// A tile (warp-collective store).  A thread without a live ray passes live = false: its row is still
+// written (every row of the tile takes part in the MMA) with P = +1e30, so all its accumulators
+// come out negative and its bitmap is empty.
 __device__ __forceinline__ void shade_submit(const Shade& s, const ScanRay& ray, bool live) {
   const float a[kTerms] = {ray.dx * ray.dx, ray.dy * ray.dy, ray.dz * ray.dz, 2.0f * ray.dx * ray.dy, 2.0f * ray.dx * ray.dz,
                            2.0f * ray.dy * ray.dz, ray.nqx, ray.nqy, ray.nqz, 1.0f};
   float row[kSlots];
   fill_row_a(a, live ? ray.p_low : 1e30f, row);
-  store_row(s.a_tile, s.row, row);
-  fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+  __syncwarp();
+  tmem_st32(s.a_taddr, row);
+  tmem_st_wait();
+  fence_before_sync();
   mbar_arrive(s.a_ready);
 }
 // SHADE: wait for the bitmaps of round r
 __device__ __forceinline__ void shade_wait(const Shade& s, uint32_t round) { mbar_wait(s.scan_done, round & 1u); }
 
-// SHADE: f(sphere index) for every candidate of this thread's ray, ascending index
+// SHADE: f(sphere index) for every candidate of this thread's ray, ascending index.  WARP-CONVERGENT:
+// all 32 lanes must call it (a lane without a live ray passes live = false).  Every trip of the
+// loop hands one candidate to every lane that still has one (a lane whose current bitmap word is
+// exhausted jumps to its next non-empty word through the summary word), so the warp makes
+// max-over-lanes(candidates) trips and f runs once per trip with the lanes converged.
 template <class F>
-__device__ __forceinline__ void for_each_candidate(const Shade& s, int nwords, F&& f) {
-  for (int w = 0; w < nwords; ++w) {
-    uint32_t m = s.bitmap[w * kShadeThreads];
-    while (m) {
+__device__ __forceinline__ void for_each_candidate(Shade& s, bool live, F&& f) {
+  uint32_t sum = live ? *s.summary : 0u, m = 0u;
+  int w = 0;
+  for (;;) {
+    if (m == 0u && sum != 0u) {
+      w = __clz((int)sum);
+      sum &= ~(0x80000000u >> w);
+      m = s.bitmap[w * kShadeThreads];
+    }
+    if (!__any_sync(0xffffffffu, m != 0u)) return;
+#ifdef UECRT_TC_PROFILE
+    ++s.prof_trips;
+    if (m != 0u) ++s.prof_cands;
+#endif
+    if (m != 0u) {
       const int b = __clz((int)m);
-      f(w * 32 + b);
       m &= ~(0x80000000u >> b);
+      f(w * 32 + b);
     }
   }
 }
@@ -71,10 +89,12 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
   const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]);
   const uint32_t ready0 = smem_addr(&h->a_ready[0]), done0 = smem_addr(&h->scan_done[0]);
   uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw + lay.bitmap);
+  uint32_t* summary = reinterpret_cast<uint32_t*>(smem_raw + lay.summary);
   uint32_t seq = 0;
   for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
       uint32_t* out = bitmap + g * kGroupThreads + row;       // word w of this ray at out[w * kShadeThreads]
+      uint32_t sum = 0;                                       // bit (31 - w): word w is non-zero
       for (int j = 0; j < nchunks; ++j, ++seq) {
         const uint32_t slot = seq % kRing, use = seq / kRing;
         mbar_wait(full0 + 8u * slot, use & 1u);
@@ -86,17 +106,23 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         tmem_ld32(t0, va);
         tmem_ld32(t0 + 32, vb);
         tmem_ld_wait();
-        o[0] = sign_word(va);
+        const uint32_t w0 = sign_word(va);
         tmem_ld32(t0 + 64, va);
-        o[kShadeThreads] = sign_word(vb);
+        const uint32_t w1 = sign_word(vb);
         tmem_ld32(t0 + 96, vb);
+        o[0] = w0;
+        o[kShadeThreads] = w1;
         tmem_ld_wait();
         fence_before_sync();                              // the whole slot is in registers: hand it back
         if (lane == 0) mbar_arrive(empty0 + 8u * slot);
-        o[2 * kShadeThreads] = sign_word(va);
-        o[3 * kShadeThreads] = sign_word(vb);
+        const uint32_t w2 = sign_word(va), w3 = sign_word(vb);
+        o[2 * kShadeThreads] = w2;
+        o[3 * kShadeThreads] = w3;
+        const uint32_t nz = (w0 ? 8u : 0u) | (w1 ? 4u : 0u) | (w2 ? 2u : 0u) | (w3 ? 1u : 0u);
+        sum |= nz << (28 - 4 * j);
         UECRT_TCS(pl)
       }
+      summary[g * kGroupThreads + row] = sum;
       mbar_arrive(done0 + 8u * g);
 #ifdef UECRT_TC_PROFILE
       ++ptiles;

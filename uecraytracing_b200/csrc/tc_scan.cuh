@@ -18,8 +18,13 @@
 // (scene_pack.hpp): the sphere part raises -k, the ray part lowers P, so {f >= P} stays a SUPERSET
 // of the reference's "discriminant >= 0" and the resolve phase (closest_hit.cuh) is unchanged.
 //
-// Shared-memory operand layout (K-major, no swizzle; the UMMA "interleaved" canonical layout):
-//   a row (ray or sphere) has 32 FP32 slots = 8 chunks of 16 B; rows are grouped by 8;
+// The RAY operand (A) lives in TMEM: thread t of a shade group writes its 32 slots to TMEM lane t with
+// one tcgen05.st.32x32b.x32 (no shared-memory staging, no proxy fence), and the MMAs read it from
+// there, so the only shared-memory traffic of an MMA is its 4 KB slice of the sphere operand
+// (with both operands in shared memory an M=128, N=128, K=8 TF32 MMA reads 8 KB = 64 cycles of the
+// SM's 128 B/clk, i.e. the tensor pipe was shared-memory-bound: tools/microbench/tc_probe.cu T3).
+// Shared-memory layout of the SPHERE operand (K-major, no swizzle; the UMMA "interleaved" canonical layout):
+//   a row (sphere) has 32 FP32 slots = 8 chunks of 16 B; rows are grouped by 8;
 //   byte offset of (row, chunk) = (row / 8) * 1024 + chunk * 128 + (row % 8) * 16
 //   -> core matrix = 8 rows x 16 B contiguous (128 B); LBO (next core matrix along K) = 128 B;
 //      SBO (next 8-row group) = 1024 B.  One MMA step consumes 8 slots = 2 chunks.
@@ -97,6 +102,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in TMEM (lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all tcgen05 operations issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -147,6 +160,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 registers -> 32 consecutive TMEM columns of this thread's lane (warp-collective)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+      "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+      "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+      "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // write one 32-slot row (8 x 16 B) into the canonical layout; `base` = shared address of the
 // operand tile, row = row within the tile
@@ -163,6 +189,12 @@ __device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_smem, uin
   for (uint32_t s = 0; s < 4; ++s)
     mma_tf32(d_tmem, make_smem_desc(a_smem + s * 256u), make_smem_desc(b_smem + s * 256u), idesc, s);
 }
+// the same with A in TMEM columns [a_tmem, a_tmem + 32)
+__device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem, uint32_t n) {
+  const uint32_t idesc = make_idesc_tf32(128, n);
+#pragma unroll
+  for (uint32_t s = 0; s < 4; ++s) mma_tf32_ts(d_tmem, a_tmem + s * 8u, make_smem_desc(b_smem + s * 256u), idesc, s);
+}
 // ---------------------------------------------------------------------------------------
 // Warp-specialised pipeline of one CTA (kThreads = 768 threads = 6 warpgroups, 1 CTA per SM; launched
 // at 80 registers per thread, then setmaxnreg moves registers from the issuer warpgroup (-> 32) to
@@ -172,7 +204,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_smem, uin
 //           candidate lists, resolves the closest hit and shades.
 //   ISSUER  lane 0 of warp 20 (warps 21-23 only donate their registers): for round r = 0, 1, ... and group g = 0..3 IN THAT FIXED ORDER it waits
 //           for the group's A tile and issues the MMAs of every sphere chunk into a ring of kRing
-//           TMEM slots of kNC columns (4 x 128 = all 512 columns).
+//           TMEM slots of kNC columns (3 x 128 columns; the other 128 columns hold the four A tiles).
 //   SCAN    warps 16-19 (warp 16+q owns TMEM lanes 32q..32q+31): consume the ring in the same fixed
 //           order; thread t reads the f values of ray row t of the current group with
 //           tcgen05.ld.32x32b (two loads in flight) and packs the 32 sign bits of every load into
@@ -197,9 +229,10 @@ constexpr int kScanThreads = 128;
 constexpr int kThreads = kShadeThreads + kScanThreads + 128; // 768: + the issuer warpgroup (one working warp)
 constexpr int kScanRegs = 128, kIssuerRegs = 32;             // setmaxnreg targets (launch allocation: 80)
 constexpr int kNC = 128;                                     // spheres (TMEM columns) per ring slot
-constexpr int kRing = 4;                                     // ring slots
+constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kATileBytes = 128u * kSlots * 4u;         // 16 KB per group
+constexpr uint32_t kATmemCol = kRing * kNC;                  // A tile of group g: TMEM columns [384 + 32g, 384 + 32g + 32)
+constexpr int kMaxRows = 1024;                               // one 32-bit summary word per ray: at most 32 bitmap words
 constexpr uint32_t kHeaderBytes = 1024;
 
 struct Header {               // first kHeaderBytes of dynamic shared memory
@@ -213,16 +246,17 @@ struct Header {               // first kHeaderBytes of dynamic shared memory
   uint8_t done_flags[8][16];  // [round & 7][shade warp]
 };
 
-// smem layout: [Header][B: rows * 128 B][A: kGroups tiles][bitmap: rows/32 words x 512 rays]
-// bitmap word w of ray i lives at bitmap[w * 512 + i] (the 32 lanes of a warp touch consecutive words)
+// smem layout: [Header][B: rows * 128 B][summary: 512 words][bitmap: rows/32 words x 512 rays]
+// bitmap word w of ray i lives at bitmap[w * 512 + i] (the 32 lanes of a warp touch consecutive words);
+// summary[i] has bit (31 - w) set iff bitmap word w of ray i is non-zero.
 struct Layout {
-  uint32_t b, a, bitmap, total;
+  uint32_t b, summary, bitmap, total;
 };
 __host__ __device__ inline Layout make_layout(uint32_t b_rows) {
   Layout l;
   l.b = kHeaderBytes;
-  l.a = l.b + b_rows * 128u;
-  l.bitmap = l.a + (uint32_t)kGroups * kATileBytes;
+  l.summary = l.b + b_rows * 128u;
+  l.bitmap = l.summary + (uint32_t)kShadeThreads * 4u;
   l.total = l.bitmap + (b_rows / 32u) * (uint32_t)kShadeThreads * 4u;
   return l;
 }
@@ -287,7 +321,7 @@ __device__ __forceinline__ bool round_continues(const Header* h, uint32_t r, int
 __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC);
-  const uint32_t b_smem = smem_addr(smem_raw + lay.b), a_smem0 = smem_addr(smem_raw + lay.a);
+  const uint32_t b_smem = smem_addr(smem_raw + lay.b);
   const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), ready0 = smem_addr(&h->a_ready[0]);
   mbar_wait(smem_addr(&h->b_loaded), 0);
   uint32_t seq = 0;
@@ -298,7 +332,7 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
         const uint32_t slot = seq % kRing, use = seq / kRing;
         if (use >= 1u) mbar_wait(empty0 + 8u * slot, (use - 1u) & 1u);      // the scanners have read the previous contents
         fence_after_sync();
-        issue_tile(tmem_base + slot * kNC, a_smem0 + g * kATileBytes, b_smem + (uint32_t)j * (kNC * 128u), kNC);
+        issue_tile_ts(tmem_base + slot * kNC, tmem_base + kATmemCol + g * (uint32_t)kSlots, b_smem + (uint32_t)j * (kNC * 128u), kNC);
         mma_commit(full0 + 8u * slot);
       }
     }
@@ -308,19 +342,22 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
 // SHADE side of one thread
 struct Shade {
   uint32_t a_ready, scan_done;       // shared addresses of the group's barriers
-  unsigned char* a_tile;             // the group's A tile
+  uint32_t a_taddr;                  // TMEM address of this thread's A row: its warp's lane quarter | the group's A columns
+  const uint32_t* summary;           // this ray's summary word
   const uint32_t* bitmap;            // this ray's candidate bitmap: word w at bitmap[w * kShadeThreads]
-  uint32_t row;
+#ifdef UECRT_TC_PROFILE
+  unsigned long long prof_trips = 0, prof_steps = 0, prof_cands = 0;
+#endif
 };
-__device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, int nchunks) {
+__device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC);
   const uint32_t g = threadIdx.x / kGroupThreads;
   Shade s;
   s.a_ready = smem_addr(&h->a_ready[g]); s.scan_done = smem_addr(&h->scan_done[g]);
-  s.a_tile = smem_raw + lay.a + g * kATileBytes;
+  s.a_taddr = tmem_base + kATmemCol + g * (uint32_t)kSlots + (((threadIdx.x >> 5) & 3u) * 32u << 16);
+  s.summary = reinterpret_cast<const uint32_t*>(smem_raw + lay.summary) + threadIdx.x;
   s.bitmap = reinterpret_cast<const uint32_t*>(smem_raw + lay.bitmap) + threadIdx.x;
-  s.row = threadIdx.x % kGroupThreads;
   return s;
 }
 #endif  // __CUDACC__

@@ -226,8 +226,8 @@ int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* ca
   }
   cudaError_t e;
   if (!c->configured) {
-    if ((e = cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long))) != cudaSuccess ||
+    if ((e = cudaMalloc(&c->d_counters, 32 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_counters, 0, 32 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess)
       return fail(UECRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
@@ -341,7 +341,7 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.accum = reinterpret_cast<float4*>(d_accum);
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
-  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), st));
   const bool exact = (p->flags & UECRT_FLAG_EXACT_HITS) != 0;
   int mode = 0;
   if ((rc_mode(p->flags, ctx, &mode))) return UECRT_ERR_INVALID;
@@ -379,13 +379,15 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   out->rays_traced = h[1]; out->paths = h[2]; out->sphere_tests = h[1] * (unsigned long long)ctx->n;
 #ifdef UECRT_TC_PROFILE
   {   // phase clocks of the tensor-scan K1 shade warps (SM cycles per warp-round), debugging builds only
-    unsigned long long q[16];
+    unsigned long long q[32];
     CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
     if (q[4]) {
       const char* nm[7] = {"refill", "-", "submit", "wait_scan", "resolve", "shade", "total"};
       fprintf(stderr, "[tc profile] warp-rounds %llu:", q[4]);
       for (int i = 0; i < 7; ++i) fprintf(stderr, " %s %.0f", nm[i], (double)q[5 + i] / (double)q[4]);
       fprintf(stderr, " cycles/round\n");
+      fprintf(stderr, "[tc profile] per warp-round: candidate trips %.2f, inner word steps %.2f, candidates (lane sum) %.2f\n", (double)q[16] / q[4],
+              (double)q[17] / q[4], (double)q[18] / q[4]);
       if (q[12]) fprintf(stderr, "[tc profile] scan warps: tiles %llu, per tile: wait_full %.0f ld+pack %.0f arrive %.0f cycles\n", q[12],
                          (double)q[13] / q[12], (double)q[14] / q[12], (double)q[15] / q[12]);
     }
