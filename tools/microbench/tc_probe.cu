@@ -21,15 +21,15 @@ using namespace uecrt::tc;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
   printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
-constexpr int kNC = 128;          // TMEM columns (spheres) per MMA tile
-constexpr int kGroupThreads = 128;
+constexpr int kPNC = 128;          // TMEM columns (spheres) per MMA tile
+constexpr int kPGroupThreads = 128;
 
 struct ProbeArgs {
   const float* a_rows;       // [n_groups_total * 128][32] pre-filled K-slot rows (T1/T2) or null (T3: synthesised)
   const unsigned char* b;    // canonical layout, n_spheres/8 row groups of 1024 B
   float* d_out;              // [n_groups_total * 128][n_spheres] or null
   unsigned long long* sink;  // T3: keeps the reduction alive
-  int n_spheres;             // multiple of kNC
+  int n_spheres;             // multiple of kPNC
   int rounds;                // T3
   int mode;                  // 0: full, 1: MMA only (no readout), 2: readout only (no MMA)
   uint32_t lbo, sbo;         // descriptor fields under test
@@ -47,14 +47,14 @@ __device__ __forceinline__ void issue_tile_ex(uint32_t d_tmem, uint32_t a_smem, 
 
 // smem: [0,64) barriers + tmem ptr | B (n_spheres * 128 B) | A (groups * 16 KB)
 template <int GROUPS>
-__global__ void __launch_bounds__(GROUPS * kGroupThreads, 1) k_probe(const ProbeArgs p) {
+__global__ void __launch_bounds__(GROUPS * kPGroupThreads, 1) k_probe(const ProbeArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // GROUPS barriers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 48);
   unsigned char* sB = smem + 1024;
   unsigned char* sA = sB + (size_t)p.n_spheres * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = tid / kGroupThreads, tg = tid % kGroupThreads;
+  const int g = tid / kPGroupThreads, tg = tid % kPGroupThreads;
 
   if (tid == 0) {
     for (int i = 0; i < GROUPS; ++i) mbar_init(smem_addr(bars + i), 1);
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(GROUPS * kGroupThreads, 1) k_probe(const Probe
   unsigned char* myA = sA + (size_t)g * 128 * 128;
   const uint32_t a_smem = smem_addr(myA), b_smem = smem_addr(sB);
   const uint32_t bar = smem_addr(bars + g);
-  const uint32_t d_tmem = tmem_base + (uint32_t)g * kNC;
+  const uint32_t d_tmem = tmem_base + (uint32_t)g * kPNC;
   const uint32_t my_taddr = d_tmem + ((uint32_t)(warp & 3) * 32u << 16);
   const bool elected = (tg == 0);
-  const int nchunks = p.n_spheres / kNC;
+  const int nchunks = p.n_spheres / kPNC;
   const size_t grow = ((size_t)blockIdx.x * GROUPS + g) * 128 + tg;   // global ray row
   uint32_t phase = 0;
   unsigned long long acc = 0;
@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(GROUPS * kGroupThreads, 1) k_probe(const Probe
       float a[kTerms];
 #pragma unroll
       for (int i = 0; i < kTerms; ++i) a[i] = __uint_as_float(0x3f000000u + ((uint32_t)(tid * 977 + r * 131 + i * 7919) & 0x7fffffu));
-      fill_row_a(a, row);
+      fill_row_a(a, 0.0f, row);
     }
     store_row(myA, tg, row);
     fence_proxy_async_smem();
     fence_before_sync();
-    group_bar(1 + g, kGroupThreads);
+    group_bar(1 + g, kPGroupThreads);
     if (p.mode != 2 && elected) {
       fence_after_sync();
-      issue_tile_ex(d_tmem, a_smem, b_smem, kNC, p.lbo, p.sbo);
+      issue_tile_ex(d_tmem, a_smem, b_smem, kPNC, p.lbo, p.sbo);
       mma_commit(bar);
     }
     for (int j = 0; j < nchunks; ++j) {
@@ -111,13 +111,13 @@ __global__ void __launch_bounds__(GROUPS * kGroupThreads, 1) k_probe(const Probe
       fence_after_sync();
       if (p.mode != 1) {
 #pragma unroll
-        for (int c = 0; c < kNC / 32; ++c) {
+        for (int c = 0; c < kPNC / 32; ++c) {
           int v[32];
           tmem_ld32(my_taddr + c * 32, v);
           tmem_ld_wait();
           if (p.d_out) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p.d_out[grow * p.n_spheres + j * kNC + c * 32 + i] = __int_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) p.d_out[grow * p.n_spheres + j * kPNC + c * 32 + i] = __int_as_float(v[i]);
           } else {
             int m = v[0];
 #pragma unroll
@@ -128,10 +128,10 @@ __global__ void __launch_bounds__(GROUPS * kGroupThreads, 1) k_probe(const Probe
       }
       if (j + 1 < nchunks) {
         fence_before_sync();
-        group_bar(1 + g, kGroupThreads);
+        group_bar(1 + g, kPGroupThreads);
         if (p.mode != 2 && elected) {
           fence_after_sync();
-          issue_tile_ex(d_tmem, a_smem, b_smem + (uint32_t)(j + 1) * (kNC / 8) * kRowGroupBytes, kNC, p.lbo, p.sbo);
+          issue_tile_ex(d_tmem, a_smem, b_smem + (uint32_t)(j + 1) * (kPNC / 8) * kRowGroupBytes, kPNC, p.lbo, p.sbo);
           mma_commit(bar);
         }
       }
@@ -141,6 +141,62 @@ __global__ void __launch_bounds__(GROUPS * kGroupThreads, 1) k_probe(const Probe
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- T4: tensor-pipe issue patterns.  One thread issues `count` MMAs (M=128, N=n, K=8 TF32, B from shared
+// memory, A from shared memory or TMEM), either all accumulating into ONE D tile (a dependent chain) or
+// round-robin over `nacc` D tiles, then commits and waits.  Cycles per MMA by clock64.
+template <bool ELECT>
+__global__ void __launch_bounds__(128, 1) k_mma_pattern(int n, int nacc, int count, int a_in_tmem, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 16);
+  unsigned char* sA = smem + 1024;            // 128 rows x 32 slots
+  unsigned char* sB = sA + 16384;             // 256 rows x 32 slots
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(smem_addr(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid < 32) tmem_alloc(smem_addr(tmem_ptr), 512);
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(sA)[i] = 0.001f * (float)(i % 97);
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (a_in_tmem) {      // A rows into TMEM columns [480, 512)
+    float row[32];
+    for (int i = 0; i < 32; ++i) row[i] = 0.001f * (float)((tid * 32 + i) % 97);
+    tmem_st32(tmem_base + 480 + (((uint32_t)tid >> 5) * 32u << 16), row);
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  bool issuer;
+  if (ELECT) {
+    issuer = false;
+    if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) issuer = elect_one();
+  } else {
+    issuer = (tid == 0);
+  }
+  if (issuer) {
+    const uint32_t idesc = make_idesc_tf32(128, n);
+    const uint32_t a_smem = smem_addr(sA), b_smem = smem_addr(sB);
+    const long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      const uint32_t d = tmem_base + (uint32_t)(i % nacc) * (uint32_t)n;
+      const uint32_t ks = (uint32_t)(i & 3);
+      if (a_in_tmem) mma_tf32_ts(d, tmem_base + 480 + ks * 8u, make_smem_desc(b_smem + ks * 256u), idesc, 1);
+      else mma_tf32(d, make_smem_desc(a_smem + ks * 256u), make_smem_desc(b_smem + ks * 256u), idesc, 1);
+    }
+    const long long t1 = clock64();
+    mma_commit(smem_addr(bar));
+    mbar_wait(smem_addr(bar), 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
 }
 
 static void pack_b(const std::vector<float>& rows, int n, std::vector<unsigned char>& out) {
@@ -157,7 +213,7 @@ static float run(const ProbeArgs& a, int blocks) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0));
-  k_probe<GROUPS><<<blocks, GROUPS * kGroupThreads, smem>>>(a);
+  k_probe<GROUPS><<<blocks, GROUPS * kPGroupThreads, smem>>>(a);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -236,7 +292,7 @@ int main(int argc, char** argv) {
       const float od = fmaf(oz, dz, fmaf(oy, dy, ox * dx));
       const float qx = -2.0f * fmaf(od, dx, -ox), qy = -2.0f * fmaf(od, dy, -oy), qz = -2.0f * fmaf(od, dz, -oz);
       float a[kTerms] = {dx * dx, dy * dy, dz * dz, 2.0f * dx * dy, 2.0f * dx * dz, 2.0f * dy * dz, qx, qy, qz, 1.0f};
-      float row[kSlots]; fill_row_a(a, row);
+      float row[kSlots]; fill_row_a(a, 0.0f, row);
       for (int k = 0; k < kSlots; ++k) arow[(size_t)i * kSlots + k] = row[k];
       for (int k = 0; k < kTerms; ++k) avec[(size_t)i * kTerms + k] = a[k];
       osq[i] = ox * ox + oy * oy + oz * oz;
@@ -295,6 +351,30 @@ int main(int argc, char** argv) {
              names[mode], ms, cyc, N, cyc / (4.0 * N), (double)blocks * 512.0 * N * rounds / (ms * 1e-3) * 1e-9);
     }
     cudaFree(dB); cudaFree(sink);
+  }
+  // ------------------------------------------------------------------ T4 MMA issue patterns
+  if (which & 8) {
+    long long* dout; CK(cudaMalloc(&dout, 16));
+    const size_t smem = 1024 + 16384 + 32768;
+    CK(cudaFuncSetAttribute(k_mma_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_mma_pattern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int count = 4096;
+    for (int use_elect = 0; use_elect < 2; ++use_elect)
+    for (int a_tmem = 0; a_tmem < 2; ++a_tmem)
+      for (int n : {64, 128, 256})
+        for (int nacc : {1, 2, 3}) {
+          if (n * nacc > 480) continue;
+          long long h[2];
+          for (int rep = 0; rep < 2; ++rep) {
+            if (use_elect) k_mma_pattern<true><<<1, 128, smem>>>(n, nacc, count, a_tmem, dout);
+            else k_mma_pattern<false><<<1, 128, smem>>>(n, nacc, count, a_tmem, dout);
+            CK(cudaDeviceSynchronize());
+          }
+          CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+          printf("T4 mma     %s, A in %s, N=%3d, %d accumulator(s): issue %.1f cycles/MMA, issue+execute %.1f cycles/MMA\n", use_elect ? "elect.sync" : "if (tid==0)", a_tmem ? "TMEM" : "smem",
+                 n, nacc, (double)h[0] / count, (double)h[1] / count);
+        }
+    cudaFree(dout);
   }
   return 0;
 }

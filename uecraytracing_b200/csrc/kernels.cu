@@ -637,11 +637,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   const unsigned lane = threadIdx.x & 31u;
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
-    if (threadIdx.x == tc::kShadeThreads + tc::kScanThreads) tc::issuer_role(smem_raw, tmem_base, nchunks, -1);
+    if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
+      if (tc::elect_one()) tc::issuer_role(smem_raw, tmem_base, nchunks, -1);
+    }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role(smem_raw, tmem_base, nchunks, -1, a.counters);
   } else {
+    if (tc::kShadeRegs < 80) tc::reg_dealloc<tc::kShadeRegs>();
     tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
     const unsigned long long n_pixels = a.n_slots;
@@ -718,11 +721,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
   const int batches = (int)((n_rays + stride - 1) / stride);
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
-    if (threadIdx.x == tc::kShadeThreads + tc::kScanThreads) tc::issuer_role(smem_raw, tmem_base, nchunks, batches);
+    if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
+      if (tc::elect_one()) tc::issuer_role(smem_raw, tmem_base, nchunks, batches);
+    }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role(smem_raw, tmem_base, nchunks, batches);
   } else {
+    if (tc::kShadeRegs < 80) tc::reg_dealloc<tc::kShadeRegs>();
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
     for (int b = 0; b < batches; ++b) {
       const unsigned long long i = (unsigned long long)b * stride + (unsigned long long)blockIdx.x * tc::kShadeThreads + threadIdx.x;

@@ -114,6 +114,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// true in exactly one lane of a CONVERGED warp.  ptxas knows the code under it runs in a single thread,
+// so tcgen05.mma operands go to uniform registers directly; under a plain `if (lane == 0)` it wraps
+// every MMA in a divergence loop (R2UR.BROADCAST + BRA.U.ANY), measured at 208 cycles per MMA against
+// 74 with elect.sync (M=128, N=128, K=8 TF32, A in TMEM; tools/microbench/tc_probe.cu T4).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -202,7 +215,7 @@ __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, 
 //   SHADE   4 groups x 128 threads (warps 0-15): each thread owns one path; per round it publishes
 //           its lifted ray as row t of the group's A tile (+ its threshold P), waits for the group's
 //           candidate lists, resolves the closest hit and shades.
-//   ISSUER  lane 0 of warp 20 (warps 21-23 only donate their registers): for round r = 0, 1, ... and group g = 0..3 IN THAT FIXED ORDER it waits
+//   ISSUER  one elected lane of warp 20 (warps 21-23 only donate their registers): for round r = 0, 1, ... and group g = 0..3 IN THAT FIXED ORDER it waits
 //           for the group's A tile and issues the MMAs of every sphere chunk into a ring of kRing
 //           TMEM slots of kNC columns (3 x 128 columns; the other 128 columns hold the four A tiles).
 //   SCAN    warps 16-19 (warp 16+q owns TMEM lanes 32q..32q+31): consume the ring in the same fixed
@@ -227,7 +240,11 @@ constexpr int kGroupThreads = 128;
 constexpr int kShadeThreads = kGroups * kGroupThreads;       // 512
 constexpr int kScanThreads = 128;
 constexpr int kThreads = kShadeThreads + kScanThreads + 128; // 768: + the issuer warpgroup (one working warp)
-constexpr int kScanRegs = 128, kIssuerRegs = 32;             // setmaxnreg targets (launch allocation: 80)
+#ifndef UECRT_TC_SHADE_REGS
+#define UECRT_TC_SHADE_REGS 72
+#endif
+constexpr int kShadeRegs = UECRT_TC_SHADE_REGS, kIssuerRegs = 24;   // setmaxnreg targets (launch allocation: 80 x 768)
+constexpr int kScanRegs = 80 + (80 - kShadeRegs) * 4 + (80 - kIssuerRegs);
 constexpr int kNC = 128;                                     // spheres (TMEM columns) per ring slot
 constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
