@@ -7,7 +7,7 @@ tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if 'kernels' in f][0]
 dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split('\n')
-start = next(i for i, l in enumerate(dis) if ('.text._ZN5uecrt14' + kern) in l and l.startswith('//---'))
+start = next(i for i, l in enumerate(dis) if ('.text._ZN5uecrt' + kern) in l and l.startswith('//---'))
 cur = None; seq = []
 for l in dis[start + 1:]:
     if l.startswith('//---'): break
@@ -25,7 +25,7 @@ by = collections.defaultdict(lambda: [0, 0, 0])
 for (loc, txt), r in zip(seq, data):
     by[loc][0] += int(r[ii]); by[loc][1] += int(r[si]); by[loc][2] += int(r[ti])
 src = {}
-for f in ('kernels.cu', 'closest_hit.cuh', 'materials.cuh', 'philox.cuh'):
+for f in ('kernels.cu', 'closest_hit.cuh', 'materials.cuh', 'philox.cuh', 'tc_scan.cuh', 'tc_collect.cuh'):
     src[f] = open('uecraytracing_b200/csrc/' + f).read().split('\n')
 agg = collections.defaultdict(lambda: [0, 0, 0])
 for loc, v in by.items():

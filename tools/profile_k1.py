@@ -2,8 +2,9 @@
 import sys
 sys.path.insert(0, '.')
 import uecraytracing_b200 as u
-exact = len(sys.argv) > 1 and sys.argv[1] == 'exact'
+exact = 'exact' in sys.argv[1:]
+scan = 'tensor' if 'tensor' in sys.argv[1:] else ('fp32' if 'fp32' in sys.argv[1:] else None)
 sc, cam = u.Scene.named('final', seed=1), u.Camera.named('final')
 for _ in range(3):
-    rgb, _, st = u.render(sc, cam, 1200, 60, 50, seed=1, exact=exact)
+    rgb, _, st = u.render(sc, cam, 1200, 60, 50, seed=1, exact=exact, scan=scan)
 print(st['kernel_ms'], st['rays_traced'])
