@@ -1,0 +1,199 @@
+"""-m gpu: the tensor-core candidate scan (tcgen05 TF32 x3 + TMEM, csrc/tc_scan.cuh) against the oracle
+and against the FP32 scan.  Both scans only PRE-FILTER spheres (a superset of the reference's
+"discriminant >= 0", sphere.hpp:32); the resolve phase is shared, so every closest hit must be the
+same sphere: indices bit-exact against the oracle in the FP64-resolved mode, and the two scans
+bit-identical to each other in every mode."""
+import numpy as np
+import pytest
+
+from conftest import golden, primary_rays, unhex
+from test_gpu_hits import T_REL_EXACT, _check_exact
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tensor(u):
+    u.set_scan_mode("tensor")
+    yield u
+    u.set_scan_mode("auto")
+
+
+def _same(a, b, what):
+    for x, y, nm in zip(a, b, ("t", "n", "id", "ff")):
+        assert np.array_equal(x, y), f"{what}: {nm} differs between the tensor and the FP32 scan"
+
+
+@pytest.mark.parametrize("name,cam,W", [("ref4", "ref", 400), ("ref4d", "ref", 400), ("final", "final", 1200)])
+def test_primary_rays_exact(tensor, oracle, name, cam, W):
+    u = tensor
+    sc, c = u.Scene.named(name, seed=1), u.Camera.named(cam)
+    o, d = primary_rays(c, W, u.image_height(W))
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    got = u.primary_hits(sc, o, d, exact=True)
+    _check_exact(got, want, name + " tensor")
+    fast = u.primary_hits(sc, o, d, exact=False)
+    u.set_scan_mode("fp32")
+    _same(got, u.primary_hits(sc, o, d, exact=True), name + " exact")
+    _same(fast, u.primary_hits(sc, o, d, exact=False), name + " fast")
+
+
+@pytest.mark.parametrize("name,span", [("ref4", 3.0), ("final", 14.0)])
+def test_random_and_golden_rays_exact(tensor, oracle, name, span):
+    u = tensor
+    sc = u.Scene.named(name, seed=1)
+    g = golden("random_ray_hits.json")[name]
+    o = np.array(g["o"], np.float32).reshape(-1, 3); d = np.array(g["d"], np.float32).reshape(-1, 3)
+    want = (unhex(g["t"]), unhex(g["n"], (-1, 3)), np.array(g["id"], np.int32), np.array(g["ff"], np.uint8))
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, name + " golden")
+    rng = np.random.default_rng(12)
+    o = rng.uniform(-span, span, (200000, 3)).astype(np.float32)
+    d = (rng.normal(size=(200000, 3)) * rng.uniform(0.05, 5, (200000, 1))).astype(np.float32)
+    _check_exact(u.primary_hits(sc, o, d, exact=True), oracle.hits(sc, o.astype(np.float64), d.astype(np.float64)), name)
+
+
+def test_secondary_rays_from_surfaces_exact(tensor, oracle):
+    """Bounce-like rays with origins ON sphere surfaces (incl. the r=1000 ground): the discriminant of the
+    sphere a ray leaves is ~0, exactly where a pre-filter must not lose the candidate."""
+    u = tensor
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    o, d = primary_rays(c, 400, 225)
+    t, n, i, f = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    hit = i >= 0
+    p = (o[hit].astype(np.float64) + d[hit].astype(np.float64) * t[hit][:, None]).astype(np.float32)
+    rng = np.random.default_rng(6)
+    v = rng.normal(size=p.shape); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    d2 = (n[hit] + v).astype(np.float32)
+    want = oracle.hits(sc, p.astype(np.float64), d2.astype(np.float64))
+    _check_exact(u.primary_hits(sc, p, d2, exact=True), want, "secondary tensor")
+    # tangent rays: direction perpendicular to the normal, grazing the sphere they start on
+    tang = np.cross(n[hit], v); tang /= np.linalg.norm(tang, axis=1, keepdims=True)
+    d3 = tang.astype(np.float32)
+    _check_exact(u.primary_hits(sc, p, d3, exact=True), oracle.hits(sc, p.astype(np.float64), d3.astype(np.float64)), "tangent tensor")
+
+
+@pytest.mark.parametrize("shift", [(300.0, 0.0, 300.0), (3000.0, 50.0, -2000.0)])
+def test_far_from_origin_stays_exact(tensor, oracle, shift):
+    """The error bound of the TF32-split product grows with |o|^2 and |c|^2; far from the origin the
+    bitmaps fill up with false candidates, and the resolve must still return the reference's sphere."""
+    u = tensor
+    base, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    g = base.geom.copy(); g[:, :3] += np.array(shift, np.float32)
+    sc = u.Scene(g, base.mat_type, base.mat_param)
+    o, d = primary_rays(c, 240, 135)
+    o = o + np.array(shift, np.float32)
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, f"shift {shift} tensor")
+
+
+def test_edge_cases_golden(tensor):
+    u = tensor
+    for c in golden("hit_edge_cases.json")["cases"]:
+        g = np.array(c["spheres"], np.float32)
+        sc = u.Scene(g, np.zeros(len(g), np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (len(g), 1)))
+        tmax = float("inf") if c["tmax"] == "inf" else float.fromhex(c["tmax"])
+        t, n, i, f = u.primary_hits(sc, [c["o"]], [c["d"]], float.fromhex(c["tmin"]), tmax, exact=True)
+        assert int(i[0]) == c["id"], c["name"]
+        if c["id"] >= 0:
+            assert int(f[0]) == c["ff"], c["name"]
+            assert abs(t[0] - unhex(c["t"])[0]) <= T_REL_EXACT * abs(unhex(c["t"])[0]), c["name"]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 500, 1023, 1024])
+def test_scene_sizes_around_the_chunk_and_row_limits(tensor, oracle, n):
+    """Sphere counts around the 128-column MMA chunk and the 1024-row residency limit (pad rows never hit)."""
+    u = tensor
+    rng = np.random.default_rng(100 + n)
+    geom = np.concatenate([rng.uniform(-6, 6, (n, 3)), rng.uniform(0.1, 0.6, (n, 1))], axis=1).astype(np.float32)
+    sc = u.Scene(geom, np.zeros(n, np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (n, 1)))
+    o = rng.uniform(-8, 8, (20000, 3)).astype(np.float32)
+    d = rng.normal(size=(20000, 3)).astype(np.float32)
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, f"n={n}")
+    if n > 8:
+        assert (want[2] >= 0).any() and want[2].max() >= n - 1 - n // 4      # the last spheres (next to the pad rows) do get hit
+
+
+def test_tie_rule_later_index_wins(tensor):
+    """Coincident spheres in different 32-sphere bitmap words and MMA chunks: the LAST one wins (hittable_list.hpp:32-58)."""
+    u = tensor
+    n = 300
+    geom = np.tile(np.array([[50.0, 50.0, 50.0, 0.1]], np.float32), (n, 1))
+    for k in (3, 40, 131, 299):
+        geom[k] = (0, 0, -1, 0.5)
+    sc = u.Scene(geom, np.zeros(n, np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (n, 1)))
+    for exact in (True, False):
+        t, nn, i, f = u.primary_hits(sc, [[0, 0, 0]], [[0, 0, -1]], exact=exact)
+        assert int(i[0]) == 299 and abs(t[0] - 0.5) < 1e-6
+
+
+def test_too_large_scene_falls_back_or_fails_loudly(u, oracle):
+    lim = u.tensor_scan_max_spheres()
+    assert lim == 1024
+    n = lim + 1
+    rng = np.random.default_rng(5)
+    geom = np.concatenate([rng.uniform(-6, 6, (n, 3)), rng.uniform(0.1, 0.4, (n, 1))], axis=1).astype(np.float32)
+    sc = u.Scene(geom, np.zeros(n, np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (n, 1)))
+    cam = u.Camera.named("ref")
+    _, _, st = u.render(sc, cam, 64, 4, 5, seed=1)                      # automatic: FP32 scan
+    assert st["scan_mode"] == 1
+    with pytest.raises(u.UecrtError):
+        u.render(sc, cam, 64, 4, 5, seed=1, scan="tensor")              # forced: refuses, never substitutes
+    u.set_scan_mode("tensor")
+    try:
+        with pytest.raises(u.UecrtError):
+            u.primary_hits(sc, [[0, 0, 0]], [[0, 0, -1]])
+    finally:
+        u.set_scan_mode("auto")
+
+
+@pytest.mark.parametrize("name,cam,W,spp", [("ref4", "ref", 400, 32), ("ref4d", "ref", 400, 32), ("final", "final", 400, 32)])
+@pytest.mark.parametrize("exact", [False, True])
+def test_render_identical_to_fp32_scan(u, name, cam, W, spp, exact):
+    """Same Philox streams, same candidates after the resolve: every path takes the same bounces.  The two
+    kernels add the finished paths into the accumulation buffer in a different order, so the float
+    sums may differ in the last bits; ray counts, path counts and sample counts must be equal."""
+    sc, c = u.Scene.named(name, seed=1), u.Camera.named(cam)
+    ra, aa, sa = u.render(sc, c, W, spp, 50, seed=9, exact=exact, return_accum=True, scan="tensor")
+    rb, ab, sb = u.render(sc, c, W, spp, 50, seed=9, exact=exact, return_accum=True, scan="fp32")
+    assert sa["scan_mode"] == 2 and sb["scan_mode"] == 1
+    assert sa["rays_traced"] == sb["rays_traced"] and sa["paths"] == sb["paths"] == W * u.image_height(W) * spp
+    assert np.array_equal(aa[..., 3], ab[..., 3]) and np.all(aa[..., 3] == spp)
+    assert np.abs(aa[..., :3] - ab[..., :3]).max() <= 1e-4 * spp
+    assert (ra != rb).mean() < 1e-4                                        # 8-bit pixels on a rounding edge
+
+
+def test_auto_mode_uses_tensor_scan_and_stats(u):
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    _, _, st = u.render(sc, c, 200, 8, 50, seed=2)
+    assert st["scan_mode"] == 2 and st["k1_threads"] == 768 and st["k1_blocks"] == st["sm_count"]
+    assert st["rays_traced"] > st["paths"] == 200 * u.image_height(200) * 8
+    u.set_tile_spheres(64)                 # forced shared-memory tiles are a request for the FP32 scan's ring
+    try:
+        _, _, st = u.render(sc, c, 200, 8, 50, seed=2)
+        assert st["scan_mode"] == 1 and st["tiles"] > 1
+    finally:
+        u.set_tile_spheres(0)
+
+
+@pytest.mark.parametrize("W", [2, 7, 33, 250])
+def test_ragged_edges_and_tiny_frames(u, W):
+    """Frames smaller than one shade group and ragged 8x4 tile edges: dead rows of an MMA tile carry P = +1e30."""
+    sc, c = u.Scene.named("ref4d", seed=1), u.Camera.named("ref")
+    ra, aa, sa = u.render(sc, c, W, 16, 50, seed=4, return_accum=True, scan="tensor")
+    rb, ab, sb = u.render(sc, c, W, 16, 50, seed=4, return_accum=True, scan="fp32")
+    assert sa["rays_traced"] == sb["rays_traced"] and sa["paths"] == sb["paths"]
+    assert np.all(aa[..., 3] == 16) and np.abs(aa[..., :3] - ab[..., :3]).max() <= 2e-3
+
+
+def test_depth_and_sample_shards(u):
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    for depth in (0, 1, 2):
+        _, aa, sa = u.render(sc, c, 120, 8, depth, seed=3, return_accum=True, scan="tensor")
+        _, ab, sb = u.render(sc, c, 120, 8, depth, seed=3, return_accum=True, scan="fp32")
+        assert sa["rays_traced"] == sb["rays_traced"] and np.abs(aa - ab).max() <= 1e-3
+        if depth == 0:
+            assert sa["rays_traced"] == 0 and np.all(aa[..., :3] == 0)
+    _, whole, _ = u.render(sc, c, 160, 24, 50, seed=5, return_accum=True, scan="tensor")
+    parts = [u.render(sc, c, 160, 24, 50, seed=5, return_accum=True, scan="tensor", sample_begin=b, sample_count=8)[1] for b in (0, 8, 16)]
+    assert np.abs(sum(parts) - whole).max() <= 1e-3

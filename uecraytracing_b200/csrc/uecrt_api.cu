@@ -132,7 +132,7 @@ namespace {
 std::atomic<uint32_t> g_tile_spheres{0};   // 0 = automatic (uecrt_set_tile_spheres)
 std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
 #ifndef UECRT_AUTO_SCAN
-#define UECRT_AUTO_SCAN UECRT_SCAN_FP32   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
+#define UECRT_AUTO_SCAN UECRT_SCAN_TENSOR   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
 #endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
 constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists = 73 KB -> 3 CTAs per SM
@@ -314,7 +314,9 @@ void release_workspaces() {
 int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
   int want = (flags & UECRT_FLAG_SCAN_TENSOR) ? UECRT_SCAN_TENSOR : (flags & UECRT_FLAG_SCAN_FP32) ? UECRT_SCAN_FP32 : g_scan_mode.load();
   const bool forced = want != UECRT_SCAN_AUTO;
-  if (want == UECRT_SCAN_AUTO) want = UECRT_AUTO_SCAN;
+  // automatic: the tensor-core scan whenever the scene fits it, unless the caller forced shared-memory
+  // tiles (uecrt_set_tile_spheres), which is a request for the FP32 scan's tile ring
+  if (want == UECRT_SCAN_AUTO) want = g_tile_spheres.load() ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
   if (want == UECRT_SCAN_TENSOR && !ctx->sc.tc_rows) {
     if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but the scene has %u spheres (resident limit %d)", ctx->n, uecrt::tc_max_spheres());
     want = UECRT_SCAN_FP32;
