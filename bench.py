@@ -14,8 +14,12 @@ BASELINE configs[1]: RTIOW final scene (484 spheres), 1200x675, 500 spp, depth 5
   e2e   : the same through the host-buffer C ABI call uecrt_render (scene + camera H2D, render,
           resolve, RGB + accumulation buffer D2H inside the timed region), on rank 0's GPU when N=1
           and through the per-rank path + pinned-host copies when N>1
-  roofline : FP32 pipe. algorithmic FLOPs = 18 per ray-sphere test (sphere.hpp:27-31) x N_spheres x
-          rays traced (counted by the kernel), over the K1 duration from CUDA events
+  roofline : FP32 pipe (the roofline north_star names). algorithmic FLOPs = 18 per ray-sphere test
+          (sphere.hpp:27-31) x N_spheres x rays traced (counted by the kernel), over the K1 duration from
+          CUDA events.  K1's default candidate scan runs on the TENSOR cores (tcgen05 TF32 x3, TMEM), so the
+          algorithmic rate can exceed the FP32-pipe peak; `roofline.tensor_pipe` gives the executed TF32
+          rate against the tensor peak and `fp32_scan` the same step with the FP32-pipe scan (--scan fp32
+          makes that the measured path)
   cpu_baseline : the oracle (the unmodified reference headers when oracle/_ref is prebuilt, else the
           restatement) rendering a bounded crop of the same workload on all host threads
 --impl reference times that CPU path alone, same metric/config.
@@ -130,6 +134,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="final", choices=sorted(WORKLOADS))
     ap.add_argument("--exact-hits", action="store_true")
+    ap.add_argument("--scan", default="auto", choices=["auto", "fp32", "tensor"], help="K1 candidate scan (auto: tensor cores when the scene fits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -187,7 +192,9 @@ def main():
     accum = torch.zeros(H, W, 4, device=dev)
     rgb = torch.zeros(H, W, 3, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    flags = u.FLAG_EXACT_HITS if args.exact_hits else 0
+    scan_flag = {"auto": 0, "fp32": u.FLAG_SCAN_FP32, "tensor": u.FLAG_SCAN_TENSOR}[args.scan]
+    flags = (u.FLAG_EXACT_HITS if args.exact_hits else 0) | scan_flag
+    u.set_scan_mode(args.scan)                                           # uecrt_render (e2e) follows the same choice
     pin_rgb = torch.empty(H, W, 3, dtype=torch.uint8).pin_memory()
     launches_per_step = 0
 
@@ -232,11 +239,21 @@ def main():
             ke.append(s_["kernel_ms"]); rays += s_["rays_traced"]; tests += s_["sphere_tests"]
     torch.cuda.synchronize()
     k1_avg = sum(ke) / len(ke) if ke else 0.0
-    t = torch.tensor([total_ms, k1_avg, float(rays), float(tests)], dtype=torch.float64, device=dev)
+    # the same K1 launches with the FP32-pipe scan (the design north_star names), for the side-by-side figure
+    alt_ms = []
+    if cnt and st["scan_mode"] == 2:
+        for _ in range(max(2, min(args.steps, 3))):
+            accum.zero_()
+            ctx.accumulate(accum.data_ptr(), W, H, spp, depth, 2026, lo, cnt, stream.cuda_stream,
+                           (flags & ~u.FLAG_SCAN_TENSOR) | u.FLAG_SCAN_FP32)
+            alt_ms.append(ctx.stats()["kernel_ms"])
+        alt_ms = alt_ms[1:]
+    fp32_k1 = sum(alt_ms) / len(alt_ms) if alt_ms else 0.0
+    t = torch.tensor([total_ms, k1_avg, float(rays), float(tests), fp32_k1], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, k1_avg = float(tmax[0]), float(tmax[1])
+        total_ms, k1_avg, fp32_k1 = float(tmax[0]), float(tmax[1]), float(tmax[4])
         rays, tests = float(tsum[2]), float(tsum[3])
     ms_per_step = total_ms / args.steps
     value = samples_per_step / (ms_per_step * 1e-3)
@@ -283,12 +300,15 @@ def main():
         peak = 2 * 128 * st["sm_count"] * sm_max * 1e6 / 1e12
         rays_per_launch = rays / max(args.steps, 1) / max(world, 1)
         achieved = FLOP_PER_TEST * scene.n * rays_per_launch / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
+        tensor_scan = st["scan_mode"] == 2
+        config["scan"] = "tensor cores (tcgen05 TF32 x3 split, TMEM accumulators)" if tensor_scan else "FP32 pipe (packed FFMA2 from shared memory)"
+        kernel_name = "k_render_paths_tc" if tensor_scan else "k_render_paths"
         out = {"metric": "path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "e2e": {"value": samples_per_step / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": args.steps * (2 if rank == 0 else 1),
-               "roofline": {"bound": "fp32", "kernel": "k_render_paths", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+               "roofline": {"bound": "fp32", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": traffic,
                             "peak_source": f"2 FLOP x 128 lanes x {st['sm_count']} SMs x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                            "FFMA microbenchmark measured 73.3 TFLOP/s (profiles/ubench_r1.log)",
@@ -297,6 +317,23 @@ def main():
                             "hbm_framebuffer_gbs": (W * H * 16 * 2 + W * H * 3) / (ms_per_step * 1e-3) / 1e9},
                "kernel": {"regs": st["k1_regs"], "blocks": st["k1_blocks"], "threads": st["k1_threads"], "smem_bytes": st["k1_smem_bytes"]},
                "clocks": clocks}
+        if tensor_scan:
+            # executed tensor work: every 128-ray tile x 128-sphere chunk is four M=128, N=128, K=8 TF32 MMAs
+            rows = (scene.n + 127) // 128 * 128
+            tiles = rays_per_launch / 128.0                     # lower bound: tiles also carry dead rows
+            tf32 = 2.0 * 128 * rows * 32 * tiles / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
+            bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 2250.0
+            out["roofline"]["tensor_pipe"] = {"bound": "tensor", "achieved": tf32, "peak": bf16_peak / 2.0, "unit": "TFLOP/s",
+                                              "frac": tf32 / (bf16_peak / 2.0),
+                                              "note": "executed TF32 FLOPs (K = 32 slots: 10-term lifted product x 3 TF32 splits + P); "
+                                                      "peak = half the measured dense bf16 rate of MEASURED_PEAKS.json"}
+            out["roofline"]["note"] = ("the pair tests run on the tensor cores, so the algorithmic 18-FLOP-per-test rate is not capped by "
+                                       "the FP32 pipe; fp32_scan is the same step with the FP32-pipe scan")
+            if fp32_k1 > 0:
+                a32 = FLOP_PER_TEST * scene.n * rays_per_launch / (fp32_k1 * 1e-3) / 1e12
+                out["fp32_scan"] = {"k1_ms_per_launch": fp32_k1, "value": samples_per_step / ((ms_per_step - k1_avg + fp32_k1) * 1e-3),
+                                    "unit": "samples/s", "roofline": {"bound": "fp32", "kernel": "k_render_paths", "achieved": a32,
+                                                                      "peak": peak, "unit": "TFLOP/s", "frac": a32 / peak}}
         if not args.no_cpu_baseline:
             kind, threads, rows, spp_s, cstep = cpu_reference_arm(args, scene, cam, W, H, spp, depth)
             dt, _ = cstep()
