@@ -3,7 +3,7 @@
 // stdout lines "rendering...", "rendering finished", "write to file : <f>", "success";
 // a failed write prints "error" and exits 1; an unknown option aborts (uncaught exception).
 // New, additive flags (north_star): --width --spp --depth --seed, plus --gpus --scene --dense-n
-// --exact-hits --dump-accum.  Defaults equal the reference's macros (400 / 100 / 50).
+// --exact-hits --scan --dump-accum.  Defaults equal the reference's macros (400 / 100 / 50).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +36,7 @@ int main(int argc, char* argv[]) {
       .add(0, "scene-seed", "seed of the random scene generator (default 1)", true)
       .add(0, "dense-n", "sphere count of --scene dense (default 10000)", true)
       .add(0, "exact-hits", "resolve every closest hit in FP64", false)
+      .add(0, "scan", "candidate scan: auto | fp32 | tensor (default auto: tensor cores when the scene fits)", true)
       .add(0, "dump-accum", "also write the linear float image (.pfm) or the raw W*H*4 f32 accumulation buffer", true);
   options.positional("output");
   options.parse(argc, argv);
@@ -56,6 +57,12 @@ int main(int argc, char* argv[]) {
                                    : (std::uint64_t(std::random_device{}()) << 32) ^ std::random_device{}();   // source.cpp:159
   if (options.count("gpus")) cfg.gpus = options.as<int>("gpus");
   cfg.exact_hits = options.count("exact-hits") != 0;
+  if (options.count("scan")) {
+    const std::string m = options.last("scan");
+    if (m == "fp32") cfg.scan = UECRT_SCAN_FP32;
+    else if (m == "tensor") cfg.scan = UECRT_SCAN_TENSOR;
+    else if (m != "auto") { std::cout << "error" << std::endl; std::cerr << "--scan must be auto, fp32 or tensor" << std::endl; std::exit(EXIT_FAILURE); }
+  }
   const std::string scene = options.count("scene") ? options.last("scene") : "ref4";
   const std::uint32_t scene_seed = options.count("scene-seed") ? options.as<std::uint32_t>("scene-seed") : 1u;
   const std::uint32_t dense_n = options.count("dense-n") ? options.as<std::uint32_t>("dense-n") : 10000u;

@@ -43,6 +43,7 @@ struct render_config {
   std::uint64_t seed = 0;
   int gpus = 1;
   bool exact_hits = false;
+  int scan = UECRT_SCAN_AUTO;           // candidate scan of K1: tensor cores when the scene fits, else the FP32 pipe
 };
 
 struct image_t {
@@ -64,13 +65,15 @@ inline image_t render(const hittable_list<double>& world, const camera<double>& 
   const uecrt_camera c = cam.flatten();
   uecrt_params p{};
   p.width = img.width; p.height = img.height; p.spp = cfg.spp; p.max_depth = cfg.max_depth;
-  p.seed = cfg.seed; p.num_gpus = cfg.gpus; p.flags = cfg.exact_hits ? UECRT_FLAG_EXACT_HITS : 0;
+  p.seed = cfg.seed; p.num_gpus = cfg.gpus; p.flags = (cfg.exact_hits ? UECRT_FLAG_EXACT_HITS : 0u) |
+      (cfg.scan == UECRT_SCAN_FP32 ? UECRT_FLAG_SCAN_FP32 : cfg.scan == UECRT_SCAN_TENSOR ? UECRT_FLAG_SCAN_TENSOR : 0u);
   static_assert(sizeof(color3b) == 3, "color3b must be 3 packed bytes");
   if (uecrt_render(&sc, &c, &p, reinterpret_cast<std::uint8_t*>(img.pixels.data()), keep_accum ? img.accum.data() : nullptr, &img.stats) != UECRT_OK)
     throw std::runtime_error(std::string("uecrt_render: ") + uecrt_last_error());
   if (verbose) {
     const double samples = (double)img.width * img.height * cfg.spp;
-    std::cout << "K1 render_paths " << img.stats.kernel_ms << " ms, reduce " << img.stats.reduce_ms << " ms, K3 resolve "
+    std::cout << "K1 render_paths (" << (img.stats.scan_mode == UECRT_SCAN_TENSOR ? "tensor-core" : "FP32-pipe") << " scan) "
+              << img.stats.kernel_ms << " ms, reduce " << img.stats.reduce_ms << " ms, K3 resolve "
               << img.stats.resolve_ms << " ms; " << samples / (img.stats.kernel_ms * 1e-3) << " samples/s; rays "
               << img.stats.rays_traced << ", sphere tests " << img.stats.sphere_tests << std::endl;
   }
