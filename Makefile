@@ -12,7 +12,7 @@ CSRC = $(PKG)/csrc
 HOST = $(PKG)/host
 BUILD = build
 
-all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface
+all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface $(BUILD)/test_tc_pack
 
 $(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh $(CSRC)/tc_scan.cuh $(CSRC)/tc_collect.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
@@ -34,6 +34,11 @@ $(PKG)/bin/raytrace: $(HOST)/raytrace.cpp $(HOST)/cli_options.hpp $(HOST)/png_wr
 # C++ test of the yk:: host surface (run by tests/test_cpp_surface.py)
 $(BUILD)/test_yk_surface: tests/cpp/test_yk_surface.cpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so
 	$(HOSTCXX) -std=c++20 -O1 -I$(HOST) $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
+# host-only check of the tensor-scan operand packing and its error bound (run by tests/test_cpp_surface.py)
+$(BUILD)/test_tc_pack: tests/cpp/test_tc_pack.cpp $(CSRC)/scene_pack.hpp $(CSRC)/tc_scan.cuh include/uecrt.h
+	@mkdir -p $(BUILD)
+	$(HOSTCXX) -std=c++20 -O1 $< -o $@
 
 oracle:
 	$(MAKE) -C oracle all

@@ -19,3 +19,14 @@ def test_yk_surface_cpu():
 def test_yk_surface_gpu():
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.split("\n")[:2] == ["cpu checks ok", "gpu checks ok"], r.stdout + r.stderr
+
+
+TC = os.path.join(ROOT, "build", "test_tc_pack")
+
+
+@pytest.mark.skipif(not os.path.exists(TC), reason="build/test_tc_pack not built (make)")
+def test_tensor_scan_operand_packing_and_bound():
+    """Host emulation of what the tensor cores are given (tests/cpp/test_tc_pack.cpp): TF32-exact slots, the UMMA
+    canonical layout, and the conservative-superset margin against the reference's double discriminant."""
+    r = subprocess.run([TC], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("tc pack ok"), r.stdout + r.stderr

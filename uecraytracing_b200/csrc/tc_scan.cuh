@@ -31,7 +31,12 @@
 // TMEM: D tile = 128 lanes (rays) x NC columns (spheres) of FP32; thread t of warp w reads lane
 // 32*(w%4)+t with tcgen05.ld.32x32b, i.e. each thread reads the f values of ITS OWN ray.
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#else                       // host-only users (tests/cpp/test_tc_pack.cpp): the packing helpers need no CUDA header
+#define __host__
+#define __device__
+#endif
 #include <stdint.h>
 
 namespace uecrt {
