@@ -631,7 +631,7 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t round, co
 
 template <bool EXACT>
 __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const RenderArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nchunks = a.sc.tc_nrows / tc::kNC;
   const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, (uint32_t)a.sc.tc_nrows * 128u);
   const unsigned lane = threadIdx.x & 31u;
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
                                                                      double tmin, double tmax, double* __restrict__ t_out,
                                                                      double* __restrict__ n_out, int32_t* __restrict__ id_out,
                                                                      uint8_t* __restrict__ ff_out) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nchunks = sc.tc_nrows / tc::kNC;
   const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, (uint32_t)sc.tc_nrows * 128u);
   const unsigned long long stride = (unsigned long long)gridDim.x * tc::kShadeThreads;

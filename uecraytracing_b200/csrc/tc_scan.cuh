@@ -100,6 +100,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// both operands in shared memory (the probe's layout test; the product keeps A in TMEM, see below)
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -162,6 +163,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       ::"r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
 }
+// named barrier of `nthreads` threads (tools/microbench/tc_probe.cu only)
 __device__ __forceinline__ void group_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -202,14 +204,7 @@ __device__ __forceinline__ void store_row(unsigned char* base, uint32_t row, con
     *reinterpret_cast<float4*>(base + row_chunk_offset(row, ch)) = make_float4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
 }
 
-// issue D[128 x n] (+)= A[128 x 32] . B[n x 32]^T as four K=8 steps.  One thread.
-__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, uint32_t n) {
-  const uint32_t idesc = make_idesc_tf32(128, n);
-#pragma unroll
-  for (uint32_t s = 0; s < 4; ++s)
-    mma_tf32(d_tmem, make_smem_desc(a_smem + s * 256u), make_smem_desc(b_smem + s * 256u), idesc, s);
-}
-// the same with A in TMEM columns [a_tmem, a_tmem + 32)
+// issue D[128 x n] (+)= A[128 x 32] . B[n x 32]^T as four K=8 steps; A in TMEM columns [a_tmem, a_tmem + 32).  One thread.
 __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem, uint32_t n) {
   const uint32_t idesc = make_idesc_tf32(128, n);
 #pragma unroll
