@@ -12,12 +12,12 @@ CSRC = $(PKG)/csrc
 HOST = $(PKG)/host
 BUILD = build
 
-all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface $(BUILD)/test_tc_pack
+all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface $(BUILD)/test_tc_pack $(BUILD)/test_grid_build
 
-$(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh $(CSRC)/tc_scan.cuh $(CSRC)/tc_collect.cuh include/uecrt.h
+$(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh $(CSRC)/tc_scan.cuh $(CSRC)/tc_collect.cuh $(CSRC)/grid_walk.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/kernels.ptxas.log || (cat $(BUILD)/kernels.ptxas.log; false)
-$(BUILD)/uecrt_api.o: $(CSRC)/uecrt_api.cu $(CSRC)/kernels.cuh $(CSRC)/scene_pack.hpp $(CSRC)/tc_scan.cuh include/uecrt.h
+$(BUILD)/uecrt_api.o: $(CSRC)/uecrt_api.cu $(CSRC)/kernels.cuh $(CSRC)/scene_pack.hpp $(CSRC)/grid_build.hpp $(CSRC)/tc_scan.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(BUILD)/host_api.o: $(HOST)/host_api.cpp $(wildcard $(HOST)/yk/*.hpp) $(HOST)/png_writer.hpp include/uecrt_host.h include/uecrt.h
@@ -36,7 +36,12 @@ $(BUILD)/test_yk_surface: tests/cpp/test_yk_surface.cpp $(wildcard $(HOST)/yk/*.
 	$(HOSTCXX) -std=c++20 -O1 -I$(HOST) $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/../$(PKG)'
 
 # host-only check of the tensor-scan operand packing and its error bound (run by tests/test_cpp_surface.py)
-$(BUILD)/test_tc_pack: tests/cpp/test_tc_pack.cpp $(CSRC)/scene_pack.hpp $(CSRC)/tc_scan.cuh include/uecrt.h
+$(BUILD)/test_tc_pack: tests/cpp/test_tc_pack.cpp $(CSRC)/scene_pack.hpp $(CSRC)/grid_build.hpp $(CSRC)/tc_scan.cuh include/uecrt.h
+	@mkdir -p $(BUILD)
+	$(HOSTCXX) -std=c++20 -O1 $< -o $@
+
+# host-only check of the uniform grid builder (run by tests/test_cpp_surface.py)
+$(BUILD)/test_grid_build: tests/cpp/test_grid_build.cpp $(CSRC)/grid_build.hpp include/uecrt.h
 	@mkdir -p $(BUILD)
 	$(HOSTCXX) -std=c++20 -O1 $< -o $@
 

@@ -73,18 +73,25 @@ enum {
   UECRT_FLAG_EXACT_HITS = 1u, /* resolve every closest hit in FP64 (reference-exact index) inside K1 */
   UECRT_FLAG_NO_COUNTERS = 2u, /* do not count rays/sphere tests (saves two atomics per CTA)         */
   UECRT_FLAG_SCAN_FP32 = 4u,   /* force the FP32-pipe candidate scan (packed FFMA2 from shared memory) */
-  UECRT_FLAG_SCAN_TENSOR = 8u  /* force the tensor-core candidate scan (tcgen05 TF32 x3, TMEM); fails
+  UECRT_FLAG_SCAN_TENSOR = 8u, /* force the tensor-core candidate scan (tcgen05 TF32 x3, TMEM); fails
                                   with UECRT_ERR_INVALID when the scene is too large for it           */
+  UECRT_FLAG_SCAN_GRID = 16u   /* walk a uniform grid instead of scanning every sphere (opt-in spatial
+                                  index: same closest hit, different algorithmic work)                */
 };
 /* scan used by a render / hit call: the all-pairs discriminant test of hittable_list::hit_impl
  * (hittable_list.hpp:32-58) runs either on the FP32 pipe or on the tensor cores; both produce a
  * superset of the reference's "discriminant >= 0" spheres and share the resolve phase, so the
  * closest hit is the same. */
-enum { UECRT_SCAN_AUTO = 0, UECRT_SCAN_FP32 = 1, UECRT_SCAN_TENSOR = 2 };
+enum { UECRT_SCAN_AUTO = 0, UECRT_SCAN_FP32 = 1, UECRT_SCAN_TENSOR = 2, UECRT_SCAN_GRID = 3 };
+/* UECRT_SCAN_GRID replaces "test every object" (hittable_list.hpp:32-58) by a uniform grid over the spheres:
+ * a ray tests the spheres listed in the cells it passes (3-D DDA) plus the spheres too large for the
+ * grid, with the same per-sphere test and the same tie rule, so the closest hit is the same sphere.  It
+ * is never chosen automatically: the brute-force scans are the path north_star measures, and the
+ * grid's work is not 18 FLOP x N x rays.  uecrt_stats.sphere_tests counts the tests actually executed. */
 
 typedef struct {
   uint64_t rays_traced;  /* closest-hit scans executed (one per path segment)          */
-  uint64_t sphere_tests; /* rays_traced * n                                            */
+  uint64_t sphere_tests; /* rays_traced * n (brute-force scans); executed tests (grid)  */
   uint64_t paths;        /* (pixel,sample) paths finished                              */
   double kernel_ms;      /* K1 render_paths, CUDA events on the launch stream          */
   double reduce_ms;      /* NCCL reduce (uecrt_render with num_gpus>1), else 0         */
@@ -93,7 +100,7 @@ typedef struct {
   int32_t sm_count, sm_clock_khz;
   int32_t k1_blocks, k1_threads, k1_smem_bytes, k1_regs;
   int32_t tiles, tile_spheres; /* 1 tile = scene resident in shared memory */
-  int32_t scan_mode;           /* UECRT_SCAN_FP32 or UECRT_SCAN_TENSOR: what K1 ran with */
+  int32_t scan_mode;           /* UECRT_SCAN_FP32, _TENSOR or _GRID: what K1 ran with */
   int32_t reserved_;
 } uecrt_stats;
 

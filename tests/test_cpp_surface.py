@@ -30,3 +30,13 @@ def test_tensor_scan_operand_packing_and_bound():
     canonical layout, and the conservative-superset margin against the reference's double discriminant."""
     r = subprocess.run([TC], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.startswith("tc pack ok"), r.stdout + r.stderr
+
+
+GRID = os.path.join(ROOT, "build", "test_grid_build")
+
+
+@pytest.mark.skipif(not os.path.exists(GRID), reason="build/test_grid_build not built (make)")
+def test_uniform_grid_builder_invariants():
+    """Every surface point of every sphere lies in a cell that lists it (tests/cpp/test_grid_build.cpp)."""
+    r = subprocess.run([GRID], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("grid build ok"), r.stdout + r.stderr

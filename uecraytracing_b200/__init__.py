@@ -8,7 +8,7 @@ and the ``bin/raytrace`` drop-in CLI.  There is no CPU fallback: importing works
 from ._lib import (  # noqa: F401
     UecrtError, lib, lib_path, Float4, SceneStruct, CameraStruct, ParamsStruct, StatsStruct,
     MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, FLAG_EXACT_HITS, FLAG_NO_COUNTERS,
-    FLAG_SCAN_FP32, FLAG_SCAN_TENSOR,
+    FLAG_SCAN_FP32, FLAG_SCAN_TENSOR, FLAG_SCAN_GRID,
 )
 from .api import (  # noqa: F401
     Scene, Camera, Context, image_height, render, primary_hits, scatter, philox, resolve_device,
@@ -20,5 +20,5 @@ __all__ = [
     "UecrtError", "lib", "lib_path", "Scene", "Camera", "Context", "image_height", "render",
     "primary_hits", "scatter", "philox", "resolve_device", "write_png", "device_count",
     "stats_to_dict", "MAT_LAMBERTIAN", "MAT_METAL", "MAT_DIELECTRIC", "FLAG_EXACT_HITS",
-    "FLAG_NO_COUNTERS", "FLAG_SCAN_FP32", "FLAG_SCAN_TENSOR", "set_scan_mode", "tensor_scan_max_spheres",
+    "FLAG_NO_COUNTERS", "FLAG_SCAN_FP32", "FLAG_SCAN_TENSOR", "FLAG_SCAN_GRID", "set_scan_mode", "tensor_scan_max_spheres",
 ]

@@ -3,8 +3,8 @@ import ctypes as C
 import os
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
-FLAG_EXACT_HITS, FLAG_NO_COUNTERS, FLAG_SCAN_FP32, FLAG_SCAN_TENSOR = 1, 2, 4, 8
-SCAN_AUTO, SCAN_FP32, SCAN_TENSOR = 0, 1, 2
+FLAG_EXACT_HITS, FLAG_NO_COUNTERS, FLAG_SCAN_FP32, FLAG_SCAN_TENSOR, FLAG_SCAN_GRID = 1, 2, 4, 8, 16
+SCAN_AUTO, SCAN_FP32, SCAN_TENSOR, SCAN_GRID = 0, 1, 2, 3
 
 
 class UecrtError(RuntimeError):

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import (CameraStruct, ParamsStruct, SceneStruct, StatsStruct, UecrtError, check, lib,
-                   FLAG_EXACT_HITS, FLAG_SCAN_FP32, FLAG_SCAN_TENSOR, SCAN_AUTO, SCAN_FP32, SCAN_TENSOR)
+                   FLAG_EXACT_HITS, FLAG_SCAN_FP32, FLAG_SCAN_TENSOR, FLAG_SCAN_GRID, SCAN_AUTO, SCAN_FP32, SCAN_TENSOR, SCAN_GRID)
 
 
 def _ptr(a):
@@ -104,7 +104,7 @@ def _params(width, height, spp, max_depth, seed, sample_begin=0, sample_count=0,
     return ParamsStruct(width, height, spp, max_depth, seed, sample_begin, sample_count, num_gpus, flags)
 
 
-_SCAN_FLAGS = {None: 0, "auto": 0, "fp32": FLAG_SCAN_FP32, "tensor": FLAG_SCAN_TENSOR}
+_SCAN_FLAGS = {None: 0, "auto": 0, "fp32": FLAG_SCAN_FP32, "tensor": FLAG_SCAN_TENSOR, "grid": FLAG_SCAN_GRID}
 
 
 def render(scene, camera, width=400, spp=100, max_depth=50, seed=0, gpus=1, exact=False, return_accum=False,
@@ -219,8 +219,8 @@ def set_rays_per_thread(n):
 
 
 def set_scan_mode(mode):
-    """'auto' | 'fp32' | 'tensor': process default of the candidate scan (include/uecrt.h UECRT_SCAN_*)."""
-    lib.uecrt_set_scan_mode({"auto": SCAN_AUTO, "fp32": SCAN_FP32, "tensor": SCAN_TENSOR}[mode])
+    """'auto' | 'fp32' | 'tensor' | 'grid': process default of the candidate scan (include/uecrt.h UECRT_SCAN_*)."""
+    lib.uecrt_set_scan_mode({"auto": SCAN_AUTO, "fp32": SCAN_FP32, "tensor": SCAN_TENSOR, "grid": SCAN_GRID}[mode])
 
 
 def tensor_scan_max_spheres():

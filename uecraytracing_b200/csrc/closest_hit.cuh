@@ -106,7 +106,11 @@ struct CandList {
 // t is the distance along the UNIT direction; tmin is 0.001*|d| in those units.
 struct FastBest { float t; int id; };
 
-// one candidate sphere j against the running best (sphere.hpp:32-39 + hittable_list.hpp:37-44)
+// one candidate sphere j against the running best (sphere.hpp:32-39 + hittable_list.hpp:37-44).
+// ORDERED = true: candidates arrive in ascending index order, so accepting t <= best is the reference's
+// "later index wins"; ORDERED = false (grid walk: arbitrary order, a sphere may come twice): the same rule
+// spelled out, t < best or (t == best and j > best.id).
+template <bool ORDERED = true>
 __device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j, float ox, float oy, float oz, float dx,
                                           float dy, float dz, float tmin, int self_id, FastBest& best) {
   const float4 g = __ldg(&geom[j]);
@@ -129,7 +133,7 @@ __device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j
       if (t < tmin) return;
     }
   }
-  if (t <= best.t) { best.t = t; best.id = j; }       // closed interval: later index wins ties
+  if (ORDERED ? (t <= best.t) : (t < best.t || (t == best.t && j > best.id))) { best.t = t; best.id = j; }   // closed interval: later index wins ties
 }
 
 template <int STRIDE>
@@ -144,6 +148,7 @@ __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, co
 // reference's root; the unit direction inside K1).
 struct ExactBest { double t; int id; };
 
+template <bool ORDERED = true>
 __device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int j, double ox, double oy, double oz, double dx,
                                            double dy, double dz, double a, double tmin, ExactBest& best) {
   const float4 g = __ldg(&geom[j]);
@@ -160,6 +165,7 @@ __device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int 
     root = __ddiv_rn(__dadd_rn(-half_b, sqrtd), a);                                            // :37
     if (root < tmin || best.t < root) return;                                                   // :38
   }
+  if (!ORDERED && root == best.t && j <= best.id) return;   // unordered candidates: an equal root only wins with a LATER index
   best.t = root;                                                                                // hittable_list.hpp:40-41
   best.id = j;
 }

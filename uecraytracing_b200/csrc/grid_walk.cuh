@@ -1,0 +1,74 @@
+// grid_walk.cuh -- device traversal of the uniform grid (grid_build.hpp): 3-D DDA (Amanatides & Woo) from
+// the point where the ray enters the grid box, testing the spheres listed in every cell it passes with the
+// SAME per-sphere test as the brute-force scans (closest_hit.cuh test_fast / test_exact, unordered tie rule),
+// and stopping once the closest hit so far lies before the exit of the current cell.  Spheres too large
+// for the grid (the `always` list: e.g. the r = 1000 ground) are tested first for every ray.
+//
+// Why no hit is lost: a sphere is listed in every cell its bounding box, inflated by eps = 1e-4 x scene extent,
+// overlaps; the ray's true path through the grid and the DDA's FP32 cell sequence differ only within
+// ~1e-6 x coordinates of a cell boundary, where both neighbouring cells list the sphere.  The stop test keeps
+// a relative margin of 1e-4 on the cell's exit distance, so candidates with (nearly) equal t in the next cell
+// -- where the later-index-wins tie rule could still change the winner -- are tested too.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace uecrt {
+
+// test(j) runs the per-sphere test; best_t() returns the current closest distance along the UNIT direction
+template <class Test, class BestT>
+__device__ __forceinline__ void grid_walk(const DeviceGrid& G, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          Test&& test, BestT&& best_t, unsigned& n_tests) {
+  for (int e = 0; e < G.n_always; ++e) { test((int)__ldg(&G.always[e])); ++n_tests; }
+  if (!G.cell_start) return;
+  const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+  // slab test against the grid box
+  float t0 = 0.0f, t1 = best_t();
+  float inv[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lo = G.org[a], hi = fmaf((float)G.dim[a], G.cell[a], G.org[a]);
+    if (fabsf(d[a]) > 1e-20f) {
+      inv[a] = 1.0f / d[a];
+      const float ta = (lo - o[a]) * inv[a], tb = (hi - o[a]) * inv[a];
+      t0 = fmaxf(t0, fminf(ta, tb));
+      t1 = fminf(t1, fmaxf(ta, tb));
+    } else {
+      inv[a] = CUDART_INF_F;
+      if (o[a] < lo || o[a] > hi) return;
+    }
+  }
+  if (!(t0 <= t1)) return;
+  int idx[3], step[3];
+  float tmax[3], tdelta[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float p = fmaf(d[a], t0, o[a]);
+    int i = (int)floorf((p - G.org[a]) * G.inv_cell[a]);
+    i = max(0, min(G.dim[a] - 1, i));
+    idx[a] = i;
+    if (fabsf(d[a]) > 1e-20f) {
+      step[a] = d[a] > 0.0f ? 1 : -1;
+      const float boundary = fmaf((float)(i + (d[a] > 0.0f ? 1 : 0)), G.cell[a], G.org[a]);
+      tmax[a] = (boundary - o[a]) * inv[a];
+      tdelta[a] = G.cell[a] * fabsf(inv[a]);
+    } else {
+      step[a] = 0; tmax[a] = CUDART_INF_F; tdelta[a] = CUDART_INF_F;
+    }
+  }
+  for (;;) {
+    const uint32_t c = ((uint32_t)idx[2] * (uint32_t)G.dim[1] + (uint32_t)idx[1]) * (uint32_t)G.dim[0] + (uint32_t)idx[0];
+    const uint32_t b = __ldg(&G.cell_start[c]), e = __ldg(&G.cell_start[c + 1]);
+    for (uint32_t k = b; k < e; ++k) { test((int)__ldg(&G.items[k])); ++n_tests; }
+    const float t_exit = fminf(tmax[0], fminf(tmax[1], tmax[2]));
+    if (best_t() < t_exit - 1e-4f * (1.0f + fabsf(t_exit))) return;      // the closest hit lies inside the cells visited so far
+    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) { idx[0] += step[0]; if ((unsigned)idx[0] >= (unsigned)G.dim[0]) return; tmax[0] += tdelta[0]; }
+    else if (tmax[1] <= tmax[2]) { idx[1] += step[1]; if ((unsigned)idx[1] >= (unsigned)G.dim[1]) return; tmax[1] += tdelta[1]; }
+    else { idx[2] += step[2]; if ((unsigned)idx[2] >= (unsigned)G.dim[2]) return; tmax[2] += tdelta[2]; }
+  }
+}
+
+}  // namespace uecrt

@@ -31,6 +31,7 @@
 #include "kernels.cuh"
 #include "materials.cuh"
 #include "philox.cuh"
+#include "grid_walk.cuh"
 #include "tc_collect.cuh"
 
 namespace uecrt {
@@ -782,6 +783,134 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
 }
 
 // ---------------------------------------------------------------------------------------
+// K1 / K2 behind the uniform grid (grid_build.hpp, grid_walk.cuh).  Same path loop,
+// same per-sphere test, same shading; a ray tests only the spheres listed in the cells it passes (plus the
+// always-list).  Opt-in: the algorithmic work is no longer 18 FLOP x N x rays, so it is reported separately.
+template <bool EXACT>
+__device__ __forceinline__ void grid_closest_hit(const DeviceScene& sc, const RayQuery& q, Hit& h, unsigned& n_tests) {
+  h.id = -1;
+  if (!q.live) return;
+  if (!EXACT) {
+    FastBest best{CUDART_INF_F, -1};
+    grid_walk(sc.grid, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz,
+              [&](int j) { test_fast<false>(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); },
+              [&]() { return best.t; }, n_tests);
+    if (best.id >= 0) {
+      h.id = best.id;
+      h.t = best.t;
+      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+    }
+  } else {
+    ExactBest best{(double)CUDART_INF, -1};
+    const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
+    const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
+    grid_walk(sc.grid, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz,
+              [&](int j) { test_exact<false>(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); },
+              [&]() { return (float)best.t; }, n_tests);
+    if (best.id >= 0) {
+      const float4 g = __ldg(&sc.geom[best.id]);
+      const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
+      const double rad = g.w;
+      double nx = (px - (double)g.x) / rad, ny = (py - (double)g.y) / rad, nz = (pz - (double)g.z) / rad;   // sphere.hpp:44
+      const bool front = (Dx * nx + Dy * ny + Dz * nz) < 0;                                     // hittable.hpp:25
+      if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+      h.id = best.id; h.t = (float)best.t; h.front = front;
+      h.px = (float)px; h.py = (float)py; h.pz = (float)pz;
+      h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
+    }
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kRenderThreads, 2) k_render_paths_grid(const RenderArgs a) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long n_pixels = a.n_slots;
+  const double inv_np = 1.0 / (double)n_pixels;
+  const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
+  PathState st{};
+  st.dz = 1.f; st.dlen = 1.f; st.self_id = -1;
+  unsigned n_rays = 0, n_paths = 0, n_tests = 0;
+  WorkPool pool;
+  pool_init(pool, a, lane);
+  for (;;) {
+    slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+    if (__all_sync(0xffffffffu, st.done)) break;
+    const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
+    Hit h;
+    grid_closest_hit<EXACT>(a.sc, q, h, n_tests);
+    if (st.active) {
+      ++n_rays;
+      slot_shade(st, h, a, n_paths);
+    }
+  }
+  if (a.count_stats) {
+    unsigned r = n_rays, p = n_paths;
+    unsigned long long t = n_tests;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r += __shfl_xor_sync(0xffffffffu, r, o); p += __shfl_xor_sync(0xffffffffu, p, o); t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    if (lane == 0) {
+      atomicAdd(a.counters + 1, (unsigned long long)r);
+      atomicAdd(a.counters + 2, (unsigned long long)p);
+      atomicAdd(a.counters + 3, t);
+    }
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kHitsThreads) k_primary_hits_grid(const DeviceScene sc, unsigned long long n_rays,
+                                                                    const float* __restrict__ o, const float* __restrict__ d,
+                                                                    double tmin, double tmax, double* __restrict__ t_out,
+                                                                    double* __restrict__ n_out, int32_t* __restrict__ id_out,
+                                                                    uint8_t* __restrict__ ff_out) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += stride) {
+    const float ox = o[3 * i], oy = o[3 * i + 1], oz = o[3 * i + 2];
+    const float rx = d[3 * i], ry = d[3 * i + 1], rz = d[3 * i + 2];
+    const float dlen = sqrtf(fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
+    const float inv = 1.0f / dlen;
+    const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
+    double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
+    int id = -1;
+    bool front = false;
+    unsigned n_tests = 0;
+    if (!EXACT) {
+      const float tmin_w = (float)tmin * dlen;
+      FastBest best{(float)tmax * dlen, -1};
+      grid_walk(sc.grid, ox, oy, oz, dx, dy, dz, [&](int j) { test_fast<false>(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); },
+                [&]() { return best.t; }, n_tests);
+      if (best.id >= 0) {
+        Hit h; h.id = best.id; h.t = best.t;
+        finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
+        id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
+      }
+    } else {
+      const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
+      const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
+      ExactBest best{tmax, -1};
+      // the walk measures distance along the unit direction: root * |D|
+      grid_walk(sc.grid, ox, oy, oz, dx, dy, dz, [&](int j) { test_exact<false>(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); },
+                [&]() { return (float)(best.t * (double)dlen); }, n_tests);
+      if (best.id >= 0) {
+        const float4 g = __ldg(&sc.geom[best.id]);
+        const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
+                     pz = __dadd_rn(Oz, __dmul_rn(Dz, best.t));                                   // ray.hpp:16-19
+        const double r = g.w;
+        nx = __ddiv_rn(__dsub_rn(px, (double)g.x), r);                                             // sphere.hpp:44
+        ny = __ddiv_rn(__dsub_rn(py, (double)g.y), r);
+        nz = __ddiv_rn(__dsub_rn(pz, (double)g.z), r);
+        front = __dadd_rn(__dadd_rn(__dmul_rn(Dx, nx), __dmul_rn(Dy, ny)), __dmul_rn(Dz, nz)) < 0;  // hittable.hpp:25
+        if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+        id = best.id; t = best.t;
+      }
+    }
+    t_out[i] = t; n_out[3 * i] = nx; n_out[3 * i + 1] = ny; n_out[3 * i + 2] = nz;
+    id_out[i] = id; ff_out[i] = front ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // K3: to_color3b (source.cpp:73-83): sum / spp -> sqrt -> clamp [0, 0.999] -> * 256 -> truncate.
 // Done in double like the reference (the input is an FP32 sum); NaN / negative -> 0.
 __global__ void k_resolve(const float4* __restrict__ accum, uint32_t n_pixels, uint32_t spp, uint8_t* __restrict__ rgb) {
@@ -898,6 +1027,33 @@ void launch_primary_hits(const DeviceScene& sc, unsigned long long n_rays, const
   else if (exact) k_primary_hits<true, false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
   else if (tiled) k_primary_hits<false, true><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
   else k_primary_hits<false, false><<<blocks, kHitsThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+}
+
+// ---- uniform-grid variants
+cudaError_t configure_kernels_grid(int* regs_render, int* max_blocks_per_sm) {
+  cudaError_t e;
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, k_render_paths_grid<false>)) != cudaSuccess) return e;
+  if (regs_render) *regs_render = fa.numRegs;
+  for (int exact = 0; exact < 2; ++exact) {
+    int n1 = 0;
+    e = exact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths_grid<true>, kRenderThreads, 0)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths_grid<false>, kRenderThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (max_blocks_per_sm) max_blocks_per_sm[exact] = n1;
+  }
+  return cudaSuccess;
+}
+void launch_render_paths_grid(const RenderArgs& a, bool exact, int blocks, cudaStream_t st) {
+  if (exact) k_render_paths_grid<true><<<blocks, kRenderThreads, 0, st>>>(a);
+  else k_render_paths_grid<false><<<blocks, kRenderThreads, 0, st>>>(a);
+}
+void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
+                              double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, cudaStream_t st) {
+  unsigned long long want = (n_rays + kHitsThreads - 1) / kHitsThreads;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148ull * 16 ? 148ull * 16 : want));
+  if (exact) k_primary_hits_grid<true><<<blocks, kHitsThreads, 0, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  else k_primary_hits_grid<false><<<blocks, kHitsThreads, 0, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
 }
 
 // ---- tensor-core scan variants

@@ -5,6 +5,17 @@
 
 namespace uecrt {
 
+// uniform grid over the spheres (grid_build.hpp): cell (x, y, z) lists items[cell_start[c] .. cell_start[c+1]),
+// c = (z * dim[1] + y) * dim[0] + x; `always` spheres are tested for every ray
+struct DeviceGrid {
+  float org[3], cell[3], inv_cell[3];
+  int dim[3];
+  const uint32_t* cell_start;     // null: no grid uploaded
+  const uint32_t* items;
+  const uint32_t* always;
+  int n_always;
+};
+
 struct DeviceScene {
   const ulonglong2* pairs;   // global copy of the packed pairs (2 x 16 B per pair), staged to smem by TMA
   int npairs;                // pairs per TILE (multiple of 8); every tile is stored with npairs + 2 (prefetch pad)
@@ -15,6 +26,7 @@ struct DeviceScene {
   const float4* mat_param;
   const unsigned char* tc_rows;   // tensor-core scan operand (scene_pack.hpp pack_scene_tc), or null when the scene is too large
   int tc_nrows;                   // rows (spheres padded to a multiple of tc::kNC)
+  DeviceGrid grid;
 };
 
 struct DeviceCamera {
@@ -56,6 +68,13 @@ void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4
                     uint8_t* scattered, float* att, float* o_out, float* d_out, cudaStream_t st);
 void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st);
 cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled, int rays);
+
+// ---- uniform-grid variants (grid_walk.cuh): counters[3] receives the sphere tests actually executed
+void launch_render_paths_grid(const RenderArgs& a, bool exact, int blocks, cudaStream_t st);
+void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,
+                              double tmin, double tmax, bool exact, double* t, double* nrm, int32_t* id,
+                              uint8_t* ff, cudaStream_t st);
+cudaError_t configure_kernels_grid(int* regs_render, int* max_blocks_per_sm);
 
 // ---- tensor-core scan variants (tc_scan.cuh): resident scenes of up to tc_max_spheres() spheres
 int tc_max_spheres();

@@ -22,6 +22,7 @@
 
 #include "../../include/uecrt.h"
 #include "kernels.cuh"
+#include "grid_build.hpp"
 #include "scene_pack.hpp"
 
 #ifndef UECRT_DEFAULT_RAYS
@@ -123,6 +124,12 @@ struct uecrt_ctx {
   size_t cap_tc = 0;
   size_t smem_tc = 0;
   int regs_tc = 0;
+  // uniform grid (grid_build.hpp): built and uploaded on first use of UECRT_SCAN_GRID with the current scene
+  std::vector<uecrt_float4> h_geom;
+  void *d_cell_start = nullptr, *d_items = nullptr, *d_always = nullptr;
+  size_t cap_cells = 0, cap_items = 0, cap_always = 0;
+  bool grid_ready = false;
+  int regs_grid = 0, blocks_grid[2] = {0, 0};
   int last_scan_mode = UECRT_SCAN_FP32, last_threads = uecrt::kRenderThreads, last_regs = 0;
   size_t last_smem = 0;
 };
@@ -187,6 +194,9 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     c->sc.tc_nrows = (int)pt.rows;
     c->smem_tc = uecrt::tc_smem_bytes((int)pt.rows);
   }
+  c->h_geom.assign(scene->geom, scene->geom + scene->n);
+  c->grid_ready = false;
+  c->sc.grid = uecrt::DeviceGrid{};
   c->n = scene->n;
   c->sc.pairs = static_cast<const ulonglong2*>(c->d_pairs);
   c->sc.npairs = (int)ps.tile_pairs;
@@ -205,6 +215,7 @@ void ctx_free(uecrt_ctx* c) {
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc);
+  cudaFree(c->d_cell_start); cudaFree(c->d_items); cudaFree(c->d_always);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   cudaSetDevice(prev);
@@ -310,9 +321,42 @@ void release_workspaces() {
   cudaSetDevice(prev);
 }
 
+// build + upload the uniform grid of the context's current scene (first grid call after a scene load)
+int ctx_ensure_grid(uecrt_ctx* c) {
+  if (c->grid_ready) return UECRT_OK;
+  uecrt_scene sc{c->n, c->h_geom.data(), nullptr, nullptr};
+  const uecrt::HostGrid g = uecrt::build_grid(sc);
+  auto up = [&](void*& dptr, size_t& cap, const std::vector<uint32_t>& v) -> int {
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(uint32_t);
+    if (bytes > cap) {
+      cudaFree(dptr); dptr = nullptr; cap = 0;
+      CUDA_TRY(cudaMalloc(&dptr, bytes));
+      cap = bytes;
+    }
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(dptr, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return UECRT_OK;
+  };
+  int rc;
+  if ((rc = up(c->d_cell_start, c->cap_cells, g.cell_start)) || (rc = up(c->d_items, c->cap_items, g.items)) ||
+      (rc = up(c->d_always, c->cap_always, g.always)))
+    return rc;
+  uecrt::DeviceGrid& d = c->sc.grid;
+  for (int a = 0; a < 3; ++a) { d.org[a] = g.org[a]; d.cell[a] = g.cell[a]; d.inv_cell[a] = g.inv_cell[a]; d.dim[a] = g.dim[a]; }
+  d.cell_start = g.items.empty() ? nullptr : static_cast<const uint32_t*>(c->d_cell_start);
+  d.items = static_cast<const uint32_t*>(c->d_items);
+  d.always = static_cast<const uint32_t*>(c->d_always);
+  d.n_always = (int)g.always.size();
+  cudaError_t e = uecrt::configure_kernels_grid(&c->regs_grid, c->blocks_grid);
+  if (e != cudaSuccess || c->blocks_grid[0] < 1 || c->blocks_grid[1] < 1)
+    return fail(UECRT_ERR_CUDA, "grid kernel configuration failed: %s", cudaGetErrorString(e));
+  c->grid_ready = true;
+  return UECRT_OK;
+}
+
 // which scan a call runs with: forced by flag, else the process default, else UECRT_AUTO_SCAN when the scene fits
 int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
-  int want = (flags & UECRT_FLAG_SCAN_TENSOR) ? UECRT_SCAN_TENSOR : (flags & UECRT_FLAG_SCAN_FP32) ? UECRT_SCAN_FP32 : g_scan_mode.load();
+  int want = (flags & UECRT_FLAG_SCAN_GRID) ? UECRT_SCAN_GRID : (flags & UECRT_FLAG_SCAN_TENSOR) ? UECRT_SCAN_TENSOR
+             : (flags & UECRT_FLAG_SCAN_FP32) ? UECRT_SCAN_FP32 : g_scan_mode.load();
   const bool forced = want != UECRT_SCAN_AUTO;
   // automatic: the tensor-core scan whenever the scene fits it, unless the caller forced shared-memory
   // tiles (uecrt_set_tile_spheres), which is a request for the FP32 scan's tile ring
@@ -347,15 +391,21 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   const bool exact = (p->flags & UECRT_FLAG_EXACT_HITS) != 0;
   int mode = 0;
   if ((rc_mode(p->flags, ctx, &mode))) return UECRT_ERR_INVALID;
-  const bool tensor = mode == UECRT_SCAN_TENSOR;
-  const int blocks = tensor ? ctx->sm_count : ctx->sm_count * ctx->blocks_per_sm[exact ? 1 : 0];
+  const bool tensor = mode == UECRT_SCAN_TENSOR, grid = mode == UECRT_SCAN_GRID;
+  if (grid) {
+    int rc = ctx_ensure_grid(ctx);
+    if (rc) return rc;
+    a.sc = ctx->sc;
+  }
+  const int blocks = tensor ? ctx->sm_count : ctx->sm_count * (grid ? ctx->blocks_grid[exact ? 1 : 0] : ctx->blocks_per_sm[exact ? 1 : 0]);
   ctx->last_blocks = blocks;
   ctx->last_scan_mode = mode;
   ctx->last_threads = tensor ? uecrt::tc_threads() : uecrt::kRenderThreads;
-  ctx->last_smem = tensor ? ctx->smem_tc : ctx->smem;
-  ctx->last_regs = tensor ? ctx->regs_tc : ctx->regs;
+  ctx->last_smem = tensor ? ctx->smem_tc : grid ? 0 : ctx->smem;
+  ctx->last_regs = tensor ? ctx->regs_tc : grid ? ctx->regs_grid : ctx->regs;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
   if (tensor) uecrt::launch_render_paths_tc(a, exact, blocks, ctx->smem_tc, st);
+  else if (grid) uecrt::launch_render_paths_grid(a, exact, blocks, st);
   else uecrt::launch_render_paths(a, exact, ctx->rays, blocks, uecrt::kRenderThreads, ctx->smem, st);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
@@ -368,7 +418,8 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   std::memset(out, 0, sizeof *out);
   out->sm_count = ctx->sm_count; out->sm_clock_khz = ctx->sm_clock_khz;
   out->k1_blocks = ctx->last_blocks; out->k1_threads = ctx->last_threads;
-  out->k1_smem_bytes = (int32_t)(ctx->last_smem ? ctx->last_smem : ctx->smem); out->k1_regs = ctx->last_regs ? ctx->last_regs : ctx->regs;
+  out->k1_smem_bytes = (int32_t)(ctx->last_scan_mode == UECRT_SCAN_GRID ? 0 : ctx->last_smem ? ctx->last_smem : ctx->smem);
+  out->k1_regs = ctx->last_regs ? ctx->last_regs : ctx->regs;
   out->scan_mode = ctx->last_scan_mode;
   out->tiles = ctx->sc.ntiles; out->tile_spheres = ctx->sc.npairs * 2;
   if (!ctx->timed) return UECRT_OK;
@@ -378,7 +429,8 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   out->kernel_ms = ms;
   unsigned long long h[4];
   CUDA_TRY(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-  out->rays_traced = h[1]; out->paths = h[2]; out->sphere_tests = h[1] * (unsigned long long)ctx->n;
+  out->rays_traced = h[1]; out->paths = h[2];
+  out->sphere_tests = ctx->last_scan_mode == UECRT_SCAN_GRID ? h[3] : h[1] * (unsigned long long)ctx->n;
 #ifdef UECRT_TC_PROFILE
   {   // phase clocks of the tensor-scan K1 shade warps (SM cycles per warp-round), debugging builds only
     unsigned long long q[32];
@@ -619,7 +671,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 
 void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
-void uecrt_set_scan_mode(int m) { g_scan_mode.store((m == UECRT_SCAN_FP32 || m == UECRT_SCAN_TENSOR) ? m : UECRT_SCAN_AUTO); }
+void uecrt_set_scan_mode(int m) { g_scan_mode.store((m == UECRT_SCAN_FP32 || m == UECRT_SCAN_TENSOR || m == UECRT_SCAN_GRID) ? m : UECRT_SCAN_AUTO); }
 int uecrt_tensor_scan_max_spheres(void) { return uecrt::tc_max_spheres(); }
 void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store((rays == 2 && uecrt::max_rays_per_thread() == 2) ? 2 : 1); }
 
@@ -643,7 +695,11 @@ int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o
     CUDA_TRY(cudaMemcpy(d_d, d_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
     int mode = 0;
     if (rc_mode(0, c, &mode)) return UECRT_ERR_INVALID;
-    if (mode == UECRT_SCAN_TENSOR) uecrt::launch_primary_hits_tc(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, c->sm_count, 0);
+    if (mode == UECRT_SCAN_GRID) {
+      int r = ctx_ensure_grid(c);
+      if (r) return r;
+      uecrt::launch_primary_hits_grid(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
+    } else if (mode == UECRT_SCAN_TENSOR) uecrt::launch_primary_hits_tc(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, c->sm_count, 0);
     else uecrt::launch_primary_hits(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(t, d_t, n_rays * sizeof(double), cudaMemcpyDeviceToHost));

@@ -36,7 +36,7 @@ int main(int argc, char* argv[]) {
       .add(0, "scene-seed", "seed of the random scene generator (default 1)", true)
       .add(0, "dense-n", "sphere count of --scene dense (default 10000)", true)
       .add(0, "exact-hits", "resolve every closest hit in FP64", false)
-      .add(0, "scan", "candidate scan: auto | fp32 | tensor (default auto: tensor cores when the scene fits)", true)
+      .add(0, "scan", "closest-hit search: auto | fp32 | tensor | grid (default auto: brute force on the tensor cores when the scene fits; grid = opt-in spatial index)", true)
       .add(0, "dump-accum", "also write the linear float image (.pfm) or the raw W*H*4 f32 accumulation buffer", true);
   options.positional("output");
   options.parse(argc, argv);
@@ -61,7 +61,8 @@ int main(int argc, char* argv[]) {
     const std::string m = options.last("scan");
     if (m == "fp32") cfg.scan = UECRT_SCAN_FP32;
     else if (m == "tensor") cfg.scan = UECRT_SCAN_TENSOR;
-    else if (m != "auto") { std::cout << "error" << std::endl; std::cerr << "--scan must be auto, fp32 or tensor" << std::endl; std::exit(EXIT_FAILURE); }
+    else if (m == "grid") cfg.scan = UECRT_SCAN_GRID;
+    else if (m != "auto") { std::cout << "error" << std::endl; std::cerr << "--scan must be auto, fp32, tensor or grid" << std::endl; std::exit(EXIT_FAILURE); }
   }
   const std::string scene = options.count("scene") ? options.last("scene") : "ref4";
   const std::uint32_t scene_seed = options.count("scene-seed") ? options.as<std::uint32_t>("scene-seed") : 1u;

@@ -66,13 +66,14 @@ inline image_t render(const hittable_list<double>& world, const camera<double>& 
   uecrt_params p{};
   p.width = img.width; p.height = img.height; p.spp = cfg.spp; p.max_depth = cfg.max_depth;
   p.seed = cfg.seed; p.num_gpus = cfg.gpus; p.flags = (cfg.exact_hits ? UECRT_FLAG_EXACT_HITS : 0u) |
-      (cfg.scan == UECRT_SCAN_FP32 ? UECRT_FLAG_SCAN_FP32 : cfg.scan == UECRT_SCAN_TENSOR ? UECRT_FLAG_SCAN_TENSOR : 0u);
+      (cfg.scan == UECRT_SCAN_FP32 ? UECRT_FLAG_SCAN_FP32 : cfg.scan == UECRT_SCAN_TENSOR ? UECRT_FLAG_SCAN_TENSOR
+       : cfg.scan == UECRT_SCAN_GRID ? UECRT_FLAG_SCAN_GRID : 0u);
   static_assert(sizeof(color3b) == 3, "color3b must be 3 packed bytes");
   if (uecrt_render(&sc, &c, &p, reinterpret_cast<std::uint8_t*>(img.pixels.data()), keep_accum ? img.accum.data() : nullptr, &img.stats) != UECRT_OK)
     throw std::runtime_error(std::string("uecrt_render: ") + uecrt_last_error());
   if (verbose) {
     const double samples = (double)img.width * img.height * cfg.spp;
-    std::cout << "K1 render_paths (" << (img.stats.scan_mode == UECRT_SCAN_TENSOR ? "tensor-core" : "FP32-pipe") << " scan) "
+    std::cout << "K1 render_paths (" << (img.stats.scan_mode == UECRT_SCAN_TENSOR ? "tensor-core scan" : img.stats.scan_mode == UECRT_SCAN_GRID ? "uniform grid" : "FP32-pipe scan") << ") "
               << img.stats.kernel_ms << " ms, reduce " << img.stats.reduce_ms << " ms, K3 resolve "
               << img.stats.resolve_ms << " ms; " << samples / (img.stats.kernel_ms * 1e-3) << " samples/s; rays "
               << img.stats.rays_traced << ", sphere tests " << img.stats.sphere_tests << std::endl;
