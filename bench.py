@@ -134,7 +134,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="final", choices=sorted(WORKLOADS))
     ap.add_argument("--exact-hits", action="store_true")
-    ap.add_argument("--scan", default="auto", choices=["auto", "fp32", "tensor"], help="K1 candidate scan (auto: tensor cores when the scene fits)")
+    ap.add_argument("--scan", default="auto", choices=["auto", "fp32", "tensor", "grid"],
+                    help="K1 closest-hit search (auto: brute force on the tensor cores when the scene fits; grid: opt-in spatial index, reported separately)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +193,7 @@ def main():
     accum = torch.zeros(H, W, 4, device=dev)
     rgb = torch.zeros(H, W, 3, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    scan_flag = {"auto": 0, "fp32": u.FLAG_SCAN_FP32, "tensor": u.FLAG_SCAN_TENSOR}[args.scan]
+    scan_flag = {"auto": 0, "fp32": u.FLAG_SCAN_FP32, "tensor": u.FLAG_SCAN_TENSOR, "grid": u.FLAG_SCAN_GRID}[args.scan]
     flags = (u.FLAG_EXACT_HITS if args.exact_hits else 0) | scan_flag
     u.set_scan_mode(args.scan)                                           # uecrt_render (e2e) follows the same choice
     pin_rgb = torch.empty(H, W, 3, dtype=torch.uint8).pin_memory()
@@ -300,9 +301,13 @@ def main():
         peak = 2 * 128 * st["sm_count"] * sm_max * 1e6 / 1e12
         rays_per_launch = rays / max(args.steps, 1) / max(world, 1)
         achieved = FLOP_PER_TEST * scene.n * rays_per_launch / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
-        tensor_scan = st["scan_mode"] == 2
-        config["scan"] = "tensor cores (tcgen05 TF32 x3 split, TMEM accumulators)" if tensor_scan else "FP32 pipe (packed FFMA2 from shared memory)"
-        kernel_name = "k_render_paths_tc" if tensor_scan else "k_render_paths"
+        tensor_scan, grid_scan = st["scan_mode"] == 2, st["scan_mode"] == 3
+        config["scan"] = ("tensor cores (tcgen05 TF32 x3 split, TMEM accumulators)" if tensor_scan else
+                          "uniform grid (opt-in spatial index; NOT the brute-force 18 x N x rays figure)" if grid_scan else
+                          "FP32 pipe (packed FFMA2 from shared memory)")
+        kernel_name = "k_render_paths_tc" if tensor_scan else "k_render_paths_grid" if grid_scan else "k_render_paths"
+        if grid_scan:       # executed tests, not N per ray
+            achieved = FLOP_PER_TEST * (tests / max(args.steps, 1) / max(world, 1)) / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
         out = {"metric": "path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -317,6 +322,10 @@ def main():
                             "hbm_framebuffer_gbs": (W * H * 16 * 2 + W * H * 3) / (ms_per_step * 1e-3) / 1e9},
                "kernel": {"regs": st["k1_regs"], "blocks": st["k1_blocks"], "threads": st["k1_threads"], "smem_bytes": st["k1_smem_bytes"]},
                "clocks": clocks}
+        if grid_scan:
+            out["roofline"]["algorithmic"] = "18 FLOP per EXECUTED ray-sphere test (kernel counter); the grid walk is latency-bound, not FP32-bound"
+            out["roofline"]["tests_per_ray"] = tests / rays if rays else None
+            out["roofline"]["rays_per_second"] = rays_per_launch * max(world, 1) / (k1_avg * 1e-3) if k1_avg > 0 else None
         if tensor_scan:
             # executed tensor work: every 128-ray tile x 128-sphere chunk is four M=128, N=128, K=8 TF32 MMAs
             rows = (scene.n + 127) // 128 * 128
