@@ -4,8 +4,8 @@
 //     f = (c.d)^2 + q.c - k          (candidate iff f >= P; sphere.hpp:27-32 with |d| = 1)
 // which is BILINEAR in a lifted ray vector and a lifted sphere vector:
 //     f = sum_{i<=j} (d_i d_j)(c_i c_j) + q.c + 1*(-k)
-//       = a . b,   a = [dx^2, dy^2, dz^2, 2dxdy, 2dxdz, 2dydz, qx, qy, qz, 1]      (per ray)
-//                  b = [cx^2, cy^2, cz^2, cxcy,  cxcz,  cycz,  cx, cy, cz, -k]     (per sphere)
+//       = a . b,   a = [dx^2, dy^2, dz^2, 2dxdy, 2dxdz, 2dydz, -qx, -qy, -qz, 1]      (per ray)
+//                  b = [cx^2, cy^2, cz^2, cxcy,  cxcz,  cycz,  -cx, -cy, -cz, -k]     (per sphere)
 // so the all-pairs test of 128 rays against N spheres is a 128 x N x 10 matrix product.  It runs on
 // the 5th-generation tensor cores as tcgen05.mma.kind::tf32 with FP32 accumulation in TMEM.  TF32
 // keeps 11 significand bits, so every operand is split a = a_hi + a_lo (each exactly representable
@@ -22,14 +22,15 @@
 // one tcgen05.st.32x32b.x32 (no shared-memory staging, no proxy fence), and the MMAs read it from
 // there, so the only shared-memory traffic of an MMA is its 4 KB slice of the sphere operand
 // (with both operands in shared memory an M=128, N=128, K=8 TF32 MMA reads 8 KB = 64 cycles of the
-// SM's 128 B/clk, i.e. the tensor pipe was shared-memory-bound: tools/microbench/tc_probe.cu T3).
+// SM's 128 B/clk, i.e. the tensor pipe was shared-memory-bound: 107 cycles per MMA against 74 with A in TMEM,
+// tools/microbench/tc_probe.cu T4, profiles/tc_probe_mma_patterns_r1.log).
 // Shared-memory layout of the SPHERE operand (K-major, no swizzle; the UMMA "interleaved" canonical layout):
 //   a row (sphere) has 32 FP32 slots = 8 chunks of 16 B; rows are grouped by 8;
 //   byte offset of (row, chunk) = (row / 8) * 1024 + chunk * 128 + (row % 8) * 16
 //   -> core matrix = 8 rows x 16 B contiguous (128 B); LBO (next core matrix along K) = 128 B;
 //      SBO (next 8-row group) = 1024 B.  One MMA step consumes 8 slots = 2 chunks.
-// TMEM: D tile = 128 lanes (rays) x NC columns (spheres) of FP32; thread t of warp w reads lane
-// 32*(w%4)+t with tcgen05.ld.32x32b, i.e. each thread reads the f values of ITS OWN ray.
+// TMEM: D tile = 128 lanes (rays) x kNC columns (spheres) of FP32; thread t of a warp w with w % 4 == q
+// reads lane 32q + t with tcgen05.ld.32x32b: one thread reads the accumulators of one ray.
 #pragma once
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
@@ -222,7 +223,7 @@ __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, 
 //           TMEM slots of kNC columns (3 x 128 columns; the other 128 columns hold the four A tiles).
 //   SCAN    warps 16-19 (warp 16+q owns TMEM lanes 32q..32q+31): consume the ring in the same fixed
 //           order; thread t reads the f values of ray row t of the current group with
-//           tcgen05.ld.32x32b (two loads in flight) and packs the 32 sign bits of every load into
+//           tcgen05.ld.32x32b.x32 (the four loads of a slot in flight) and packs the 32 sign bits of every load into
 //           one word of that ray's candidate BITMAP in shared memory (funnel shifts: no compare,
 //           no branch, no divergence; bit 31 of word w = sphere 32w).
 // Barriers (all mbarriers with deterministic phase parity):
@@ -251,7 +252,7 @@ constexpr int kNC = 128;                                     // spheres (TMEM co
 constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kATmemCol = kRing * kNC;                  // A tile of group g: TMEM columns [384 + 32g, 384 + 32g + 32)
-constexpr int kMaxRows = 1024;                               // one 32-bit summary word per ray: at most 32 bitmap words
+constexpr int kMaxRows = 1024;                               // one 32-bit summary word per ray: at most 32 bitmap words of 32 spheres
 constexpr uint32_t kHeaderBytes = 1024;
 
 struct Header {               // first kHeaderBytes of dynamic shared memory
