@@ -133,8 +133,9 @@ void uecrt_set_tile_spheres(uint32_t spheres_per_tile);
  * 2 is honoured only by builds with -DUECRT_ENABLE_RAYS2 (measured slower on B200; see kernels.cu). */
 void uecrt_set_rays_per_thread(int rays);
 
-/* Process default for calls that force neither scan (UECRT_SCAN_AUTO picks the tensor-core scan when
- * the scene fits its shared-memory residency limit, uecrt_tensor_scan_max_spheres(), else FP32). */
+/* Process default for calls that force neither scan.  UECRT_SCAN_AUTO picks the tensor-core scan for scenes of
+ * 96 .. uecrt_tensor_scan_max_spheres() spheres (its shared-memory residency limit) and the FP32 scan
+ * otherwise (smaller scenes: faster there; larger ones and forced tiles: swept through shared memory). */
 void uecrt_set_scan_mode(int uecrt_scan_mode);
 int uecrt_tensor_scan_max_spheres(void);
 

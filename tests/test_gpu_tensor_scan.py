@@ -168,6 +168,8 @@ def test_auto_mode_uses_tensor_scan_and_stats(u):
     _, _, st = u.render(sc, c, 200, 8, 50, seed=2)
     assert st["scan_mode"] == 2 and st["k1_threads"] == 768 and st["k1_blocks"] == st["sm_count"]
     assert st["rays_traced"] > st["paths"] == 200 * u.image_height(200) * 8
+    _, _, st4 = u.render(u.Scene.named("ref4", seed=1), u.Camera.named("ref"), 200, 8, 50, seed=2)
+    assert st4["scan_mode"] == 1           # below 96 spheres the FP32 scan is faster and the automatic mode uses it
     u.set_tile_spheres(64)                 # forced shared-memory tiles are a request for the FP32 scan's ring
     try:
         _, _, st = u.render(sc, c, 200, 8, 50, seed=2)

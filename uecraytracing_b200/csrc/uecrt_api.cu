@@ -142,6 +142,7 @@ std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
 #define UECRT_AUTO_SCAN UECRT_SCAN_TENSOR   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
 #endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
+constexpr uint32_t kTensorScanMinSpheres = 96;   // automatic mode: smaller scenes use the FP32 scan
 constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists = 73 KB -> 3 CTAs per SM
 constexpr size_t kSmemOptin = 232448;
 
@@ -360,7 +361,9 @@ int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
   const bool forced = want != UECRT_SCAN_AUTO;
   // automatic: the tensor-core scan whenever the scene fits it, unless the caller forced shared-memory
   // tiles (uecrt_set_tile_spheres), which is a request for the FP32 scan's tile ring
-  if (want == UECRT_SCAN_AUTO) want = g_tile_spheres.load() ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
+  // and below ~100 spheres the FP32 scan is faster (one 128-column MMA chunk per tile is the tensor scan's floor;
+  // measured crossover between 64 and 128 spheres, profiles/README.md)
+  if (want == UECRT_SCAN_AUTO) want = (g_tile_spheres.load() || ctx->n < kTensorScanMinSpheres) ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
   if (want == UECRT_SCAN_TENSOR && !ctx->sc.tc_rows) {
     if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but the scene has %u spheres (resident limit %d)", ctx->n, uecrt::tc_max_spheres());
     want = UECRT_SCAN_FP32;
