@@ -35,7 +35,11 @@ __device__ __forceinline__ void shade_wait(const Shade& s, uint32_t round) { mba
 // max-over-lanes(candidates) trips and f runs once per trip with the lanes converged.
 template <class F>
 __device__ __forceinline__ void for_each_candidate(Shade& s, bool live, F&& f) {
-  uint32_t sum = live ? *s.summary : 0u, m = 0u;
+  uint32_t sum = 0u, m = 0u;
+  if (live) {
+#pragma unroll
+    for (int sg = 0; sg < kScanGroups; ++sg) sum |= s.summary[sg * kShadeThreads];
+  }
   int w = 0;
   for (;;) {
     if (m == 0u && sum != 0u) {
@@ -84,18 +88,19 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
 #endif
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC);
-  const uint32_t row = threadIdx.x - kShadeThreads, lane = row & 31u;
+  const uint32_t st = threadIdx.x - kShadeThreads, sg = st >> 7, row = st & 127u, lane = row & 31u;
   const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
   const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]);
   const uint32_t ready0 = smem_addr(&h->a_ready[0]), done0 = smem_addr(&h->scan_done[0]);
   uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw + lay.bitmap);
-  uint32_t* summary = reinterpret_cast<uint32_t*>(smem_raw + lay.summary);
+  uint32_t* summary = reinterpret_cast<uint32_t*>(smem_raw + lay.summary) + sg * kShadeThreads;
   uint32_t seq = 0;
   for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
       uint32_t* out = bitmap + g * kGroupThreads + row;       // word w of this ray at out[w * kShadeThreads]
       uint32_t sum = 0;                                       // bit (31 - w): word w is non-zero
       for (int j = 0; j < nchunks; ++j, ++seq) {
+        if (kScanGroups > 1 && (uint32_t)(j % kScanGroups) != sg) continue;      // another warpgroup's chunk
         const uint32_t slot = seq % kRing, use = seq / kRing;
         mbar_wait(full0 + 8u * slot, use & 1u);
         fence_after_sync();

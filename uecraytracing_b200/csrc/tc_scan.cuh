@@ -238,16 +238,25 @@ __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, 
 // round r-2 are set.  All roles are within two rounds of each other and the flags of round r-2
 // are ordered before anything a role does in round r by the barrier chain, so all roles read the
 // same values and leave at the same round.  (fixed_rounds >= 0: exactly that many rounds, K2.)
-constexpr int kGroups = 4;
-constexpr int kGroupThreads = 128;
-constexpr int kShadeThreads = kGroups * kGroupThreads;       // 512
-constexpr int kScanThreads = 128;
-constexpr int kThreads = kShadeThreads + kScanThreads + 128; // 768: + the issuer warpgroup (one working warp)
+#ifndef UECRT_TC_GROUPS
+#define UECRT_TC_GROUPS 4          // shade groups of 128 paths
+#endif
+#ifndef UECRT_TC_SCAN_WGS
+#define UECRT_TC_SCAN_WGS 1        // scan warpgroups; 2: they split the chunks of every tile by parity
+#endif
 #ifndef UECRT_TC_SHADE_REGS
 #define UECRT_TC_SHADE_REGS 72
 #endif
-constexpr int kShadeRegs = UECRT_TC_SHADE_REGS, kIssuerRegs = 24;   // setmaxnreg targets (launch allocation: 80 x 768)
-constexpr int kScanRegs = 80 + (80 - kShadeRegs) * 4 + (80 - kIssuerRegs);
+constexpr int kGroups = UECRT_TC_GROUPS;
+constexpr int kGroupThreads = 128;
+constexpr int kShadeThreads = kGroups * kGroupThreads;
+constexpr int kScanGroups = UECRT_TC_SCAN_WGS;
+constexpr int kScanThreads = kScanGroups * 128;
+constexpr int kThreads = kShadeThreads + kScanThreads + 128; // + the issuer warpgroup (one working warp); 768 in both supported shapes
+static_assert(kThreads == 768, "24 warps of 80 registers fill the SM's register file: 4 shade groups + 1 scan warpgroup, or 3 + 2");
+// setmaxnreg targets (launch allocation: 80 x 768 registers)
+constexpr int kShadeRegs = UECRT_TC_SHADE_REGS, kIssuerRegs = 24;
+constexpr int kScanRegs = ((768 * 80 - kShadeThreads * kShadeRegs - 128 * kIssuerRegs) / kScanThreads) / 8 * 8;
 constexpr int kNC = 128;                                     // spheres (TMEM columns) per ring slot
 constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
@@ -263,12 +272,13 @@ struct Header {               // first kHeaderBytes of dynamic shared memory
   uint64_t b_loaded;          // the sphere operand has landed (cp.async.bulk)
   uint32_t tmem_base;
   uint32_t pad_;
-  uint8_t done_flags[8][16];  // [round & 7][shade warp]
+  uint8_t done_flags[8][16];  // [round & 7][shade warp] (kShadeThreads / 32 of the 16 are used)
 };
 
 // smem layout: [Header][B: rows * 128 B][summary: 512 words][bitmap: rows/32 words x 512 rays]
 // bitmap word w of ray i lives at bitmap[w * 512 + i] (the 32 lanes of a warp touch consecutive words);
-// summary[i] has bit (31 - w) set iff bitmap word w of ray i is non-zero.
+// summary[sg * kShadeThreads + i] has bit (31 - w) set iff bitmap word w of ray i is non-zero (sg = the scan
+// warpgroup that packed word w; the shade thread ORs the warpgroups' words).
 struct Layout {
   uint32_t b, summary, bitmap, total;
 };
@@ -276,7 +286,7 @@ __host__ __device__ inline Layout make_layout(uint32_t b_rows) {
   Layout l;
   l.b = kHeaderBytes;
   l.summary = l.b + b_rows * 128u;
-  l.bitmap = l.summary + (uint32_t)kShadeThreads * 4u;
+  l.bitmap = l.summary + (uint32_t)kScanGroups * kShadeThreads * 4u;
   l.total = l.bitmap + (b_rows / 32u) * (uint32_t)kShadeThreads * 4u;
   return l;
 }
@@ -298,7 +308,7 @@ __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const voi
     }
     for (int s = 0; s < kRing; ++s) {
       mbar_init(smem_addr(&h->tmem_full[s]), 1);
-      mbar_init(smem_addr(&h->tmem_empty[s]), kScanThreads / 32);
+      mbar_init(smem_addr(&h->tmem_empty[s]), 4);      // the four warps of the scan warpgroup that owns the chunk
     }
     mbar_init(smem_addr(&h->b_loaded), 1);
     for (int i = 0; i < 8 * 16; ++i) (&h->done_flags[0][0])[i] = 0;
@@ -330,7 +340,10 @@ __device__ __forceinline__ void cta_teardown(uint32_t tmem_base) {
 
 __device__ __forceinline__ bool all_done_at(const Header* h, uint32_t r) {
   const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(&h->done_flags[r & 7u][0]);
-  return (f[0] & f[1] & f[2] & f[3]) == 0x01010101u;
+  uint32_t all = 0x01010101u;
+#pragma unroll
+  for (int w = 0; w < kShadeThreads / 128; ++w) all &= f[w];     // four warp flags per word
+  return all == 0x01010101u;
 }
 __device__ __forceinline__ bool round_continues(const Header* h, uint32_t r, int fixed_rounds) {
   if (fixed_rounds >= 0) return r < (uint32_t)fixed_rounds;
