@@ -86,6 +86,32 @@ def test_far_from_origin_stays_exact(tensor, oracle, shift):
     _check_exact(u.primary_hits(sc, o, d, exact=True), want, f"shift {shift} tensor")
 
 
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 1e3])
+def test_scale_invariance_and_mixed_radii(tensor, oracle, scale):
+    """The bound of the TF32-split product is RELATIVE (u * sum|a_i b_i|), so the filter must stay conservative when
+    the whole world is scaled by 10^-3 or 10^3, and when radii span four orders of magnitude in one scene."""
+    u = tensor
+    rng = np.random.default_rng(77)
+    n = 700
+    radii = 10.0 ** rng.uniform(-2, 1.7, n)                     # 0.01 .. 50
+    cen = rng.uniform(-40, 40, (n, 3))
+    geom = (np.concatenate([cen, radii[:, None]], axis=1) * scale).astype(np.float32)
+    sc = u.Scene(geom, np.zeros(n, np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (n, 1)))
+    o = (rng.uniform(-60, 60, (100000, 3)) * scale).astype(np.float32)
+    d = rng.normal(size=(100000, 3)).astype(np.float32)
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64), 0.001 * scale, float("inf"))
+    assert (want[2] >= 0).mean() > 0.3
+    _check_exact(u.primary_hits(sc, o, d, 0.001 * scale, float("inf"), exact=True), want, f"scale {scale}")
+    # rays leaving the surfaces (discriminant of the own sphere ~ 0 at every scale)
+    t, nrm, i, f = want
+    hit = i >= 0
+    p = (o[hit].astype(np.float64) + d[hit].astype(np.float64) * t[hit][:, None]).astype(np.float32)
+    v = rng.normal(size=p.shape); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    d2 = (nrm[hit] + v).astype(np.float32)
+    want2 = oracle.hits(sc, p.astype(np.float64), d2.astype(np.float64), 0.001 * scale, float("inf"))
+    _check_exact(u.primary_hits(sc, p, d2, 0.001 * scale, float("inf"), exact=True), want2, f"scale {scale} secondary")
+
+
 def test_edge_cases_golden(tensor):
     u = tensor
     for c in golden("hit_edge_cases.json")["cases"]:
