@@ -594,13 +594,15 @@ struct TcProf {};
 #endif
 
 // closest hit of one shade thread's ray through the pipeline; every shade thread calls it once per round
-template <bool EXACT>
+template <bool EXACT, class InWindow>
 __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t round, const DeviceScene& sc, const RayQuery& q, Hit& h,
-                                               TcProf& prof) {
+                                               TcProf& prof, InWindow&& in_window) {
   const ScanRay sr = make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz);
   h.id = -1;
   tc::shade_submit(sh, sr, q.live);
   UECRT_TCP(prof, 2)
+  in_window();                                    // work that does not depend on this round's hit
+  UECRT_TCP(prof, 1)
   tc::shade_wait(sh, round);
   UECRT_TCP(prof, 3)
   if (!EXACT) {
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
     if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
-      if (tc::elect_one()) tc::issuer_role(smem_raw, tmem_base, nchunks, -1);
+      if (tc::elect_one()) tc::issuer_role(smem_raw, tmem_base, nchunks, -1, a.counters);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
@@ -660,19 +662,30 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
 #endif
     WorkPool pool;
     pool_init(pool, a, lane);
+    // The NEXT path of every lane is started ahead of time (work item claimed, Philox block, camera ray) in the
+    // window where the warp waits for its tile's scan, so a lane whose path ends only copies it in: the
+    // shade warps' own work per round is what starves the scan pipeline (a closed loop of 4 groups
+    // around one scanner), and this moves a quarter of it off that loop.
+    PathState nx{};
+    nx.dz = 1.f; nx.dlen = 1.f; nx.self_id = -1;
+    slot_refill_pooled(nx, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
     for (uint32_t round = 0; tc::round_continues(hdr, round, -1); ++round) {
 #ifdef UECRT_TC_PROFILE
       prof.last = clock64();
       const long long pc_start = prof.last;
 #endif
-      slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+      if (!st.active && !st.done) {
+        if (nx.active) { st = nx; nx.active = false; }
+        else if (nx.done) st.done = true;
+      }
       // termination vote (tc_scan.cuh): this warp's flag of this round, stored before its a_ready arrive
       const bool warp_done = __all_sync(0xffffffffu, st.done);
       if (lane == 0) hdr->done_flags[round & 7u][threadIdx.x >> 5] = warp_done ? 1 : 0;
       UECRT_TCP(prof, 0)
       const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
       Hit h;
-      tc_closest_hit<EXACT>(sh, round, a.sc, q, h, prof);
+      tc_closest_hit<EXACT>(sh, round, a.sc, q, h, prof,
+                            [&]() { slot_refill_pooled(nx, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths); });
       UECRT_TCP(prof, 4)
       if (st.active) {
         ++n_rays;

@@ -81,7 +81,7 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
                                              unsigned long long* prof_counters = nullptr) {
 #ifdef UECRT_TC_PROFILE
   long long pw = 0, pl = 0, ps = 0, plast = clock64();
-  unsigned long long ptiles = 0;
+  unsigned long long ptiles = 0, p_ready_now = 0, p_blocked = 0;
 #define UECRT_TCS(acc) { const long long now_ = clock64(); acc += now_ - plast; plast = now_; }
 #else
 #define UECRT_TCS(acc)
@@ -102,7 +102,11 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
       for (int j = 0; j < nchunks; ++j, ++seq) {
         if (kScanGroups > 1 && (uint32_t)(j % kScanGroups) != sg) continue;      // another warpgroup's chunk
         const uint32_t slot = seq % kRing, use = seq / kRing;
+#ifdef UECRT_TC_PROFILE
+        if (mbar_test(full0 + 8u * slot, use & 1u)) { ++p_ready_now; } else { mbar_wait(full0 + 8u * slot, use & 1u); ++p_blocked; if (prof_counters && lane == 0 && j < 4) atomicAdd(prof_counters + 26 + j, 1ull); }
+#else
         mbar_wait(full0 + 8u * slot, use & 1u);
+#endif
         fence_after_sync();
         UECRT_TCS(pw)
         const uint32_t t0 = lane_taddr + slot * kNC;
@@ -141,6 +145,8 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
     atomicAdd(prof_counters + 13, (unsigned long long)pw);
     atomicAdd(prof_counters + 14, (unsigned long long)pl);
     atomicAdd(prof_counters + 15, (unsigned long long)ps);
+    atomicAdd(prof_counters + 24, p_ready_now);
+    atomicAdd(prof_counters + 25, p_blocked);
   }
 #endif
 }

@@ -165,6 +165,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 // named barrier of `nthreads` threads (tools/microbench/tc_probe.cu only)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void group_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -351,7 +362,15 @@ __device__ __forceinline__ bool round_continues(const Header* h, uint32_t r, int
 }
 
 // ISSUER: one thread.
-__device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds) {
+__device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds,
+                                            unsigned long long* prof_counters = nullptr) {
+#ifdef UECRT_TC_PROFILE
+  long long p_ready = 0, p_empty = 0, p_issue = 0, p_last = clock64();
+  unsigned long long p_tiles = 0;
+#define UECRT_TCI(acc) { const long long now_ = clock64(); acc += now_ - p_last; p_last = now_; }
+#else
+#define UECRT_TCI(acc)
+#endif
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC);
   const uint32_t b_smem = smem_addr(smem_raw + lay.b);
@@ -360,16 +379,31 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
   uint32_t seq = 0;
   for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
+      UECRT_TCI(p_issue)
       mbar_wait(ready0 + 8u * g, r & 1u);
+      UECRT_TCI(p_ready)
       for (int j = 0; j < nchunks; ++j, ++seq) {
         const uint32_t slot = seq % kRing, use = seq / kRing;
         if (use >= 1u) mbar_wait(empty0 + 8u * slot, (use - 1u) & 1u);      // the scanners have read the previous contents
+        UECRT_TCI(p_empty)
         fence_after_sync();
         issue_tile_ts(tmem_base + slot * kNC, tmem_base + kATmemCol + g * (uint32_t)kSlots, b_smem + (uint32_t)j * (kNC * 128u), kNC);
         mma_commit(full0 + 8u * slot);
+        UECRT_TCI(p_issue)
       }
+#ifdef UECRT_TC_PROFILE
+      ++p_tiles;
+#endif
     }
   }
+#ifdef UECRT_TC_PROFILE
+  if (prof_counters) {
+    atomicAdd(prof_counters + 20, p_tiles);
+    atomicAdd(prof_counters + 21, (unsigned long long)p_ready);
+    atomicAdd(prof_counters + 22, (unsigned long long)p_empty);
+    atomicAdd(prof_counters + 23, (unsigned long long)p_issue);
+  }
+#endif
 }
 
 // SHADE side of one thread

@@ -439,12 +439,16 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
     unsigned long long q[32];
     CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
     if (q[4]) {
-      const char* nm[7] = {"refill", "-", "submit", "wait_scan", "resolve", "shade", "total"};
+      const char* nm[7] = {"take_next", "prepare_next", "submit", "wait_scan", "resolve", "shade", "total"};
       fprintf(stderr, "[tc profile] warp-rounds %llu:", q[4]);
       for (int i = 0; i < 7; ++i) fprintf(stderr, " %s %.0f", nm[i], (double)q[5 + i] / (double)q[4]);
       fprintf(stderr, " cycles/round\n");
       fprintf(stderr, "[tc profile] per warp-round: candidate trips %.2f, inner word steps %.2f, candidates (lane sum) %.2f\n", (double)q[16] / q[4],
               (double)q[17] / q[4], (double)q[18] / q[4]);
+      if (q[20]) fprintf(stderr, "[tc profile] issuer: tiles %llu, per tile: wait a_ready %.0f, wait tmem_empty %.0f, issue %.0f cycles\n", q[20],
+                         (double)q[21] / q[20], (double)q[22] / q[20], (double)q[23] / q[20]);
+      if (q[24] + q[25]) fprintf(stderr, "[tc profile] scan warps: %.1f %% of the chunk waits found the MMAs already complete\n", 100.0 * q[24] / (double)(q[24] + q[25]));
+      fprintf(stderr, "[tc profile] blocked chunk waits by chunk index: %llu %llu %llu %llu (of %llu tiles x 4 warps)\n", q[26], q[27], q[28], q[29], q[20]);
       if (q[12]) fprintf(stderr, "[tc profile] scan warps: tiles %llu, per tile: wait_full %.0f ld+pack %.0f arrive %.0f cycles\n", q[12],
                          (double)q[13] / q[12], (double)q[14] / q[12], (double)q[15] / q[12]);
     }
