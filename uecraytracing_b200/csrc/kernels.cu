@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role(smem_raw, tmem_base, nchunks, -1, a.counters);
   } else {
-    if (tc::kShadeRegs < 80) tc::reg_dealloc<tc::kShadeRegs>();
+    if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
     tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
     const unsigned long long n_pixels = a.n_slots;
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role(smem_raw, tmem_base, nchunks, batches);
   } else {
-    if (tc::kShadeRegs < 80) tc::reg_dealloc<tc::kShadeRegs>();
+    if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
     for (int b = 0; b < batches; ++b) {
       const unsigned long long i = (unsigned long long)b * stride + (unsigned long long)blockIdx.x * tc::kShadeThreads + threadIdx.x;

@@ -263,11 +263,12 @@ constexpr int kGroupThreads = 128;
 constexpr int kShadeThreads = kGroups * kGroupThreads;
 constexpr int kScanGroups = UECRT_TC_SCAN_WGS;
 constexpr int kScanThreads = kScanGroups * 128;
-constexpr int kThreads = kShadeThreads + kScanThreads + 128; // + the issuer warpgroup (one working warp); 768 in both supported shapes
-static_assert(kThreads == 768, "24 warps of 80 registers fill the SM's register file: 4 shade groups + 1 scan warpgroup, or 3 + 2");
-// setmaxnreg targets (launch allocation: 80 x 768 registers)
+constexpr int kThreads = kShadeThreads + kScanThreads + 128; // + the issuer warpgroup (one working warp)
+static_assert(kThreads == 768 || kThreads == 896, "24 warps launch at 80 registers, 28 warps at 72 (7 warps per SM sub-partition x 72 x 32 <= 16 K)");
+// setmaxnreg targets: the launch allocation (80 or 72 registers x kThreads) is redistributed between the roles
+constexpr int kLaunchRegs = kThreads == 768 ? 80 : 72;
 constexpr int kShadeRegs = UECRT_TC_SHADE_REGS, kIssuerRegs = 24;
-constexpr int kScanRegs = ((768 * 80 - kShadeThreads * kShadeRegs - 128 * kIssuerRegs) / kScanThreads) / 8 * 8;
+constexpr int kScanRegs = ((kThreads * kLaunchRegs - kShadeThreads * kShadeRegs - 128 * kIssuerRegs) / kScanThreads) / 8 * 8;
 constexpr int kNC = 128;                                     // spheres (TMEM columns) per ring slot
 constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
