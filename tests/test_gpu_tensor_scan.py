@@ -153,6 +153,17 @@ def test_tie_rule_later_index_wins(tensor):
         assert int(i[0]) == 299 and abs(t[0] - 0.5) < 1e-6
 
 
+def test_non_finite_geometry_is_rejected(u):
+    cam = u.Camera.named("ref")
+    for bad in (np.nan, np.inf, 1e30):
+        geom = np.array([[0, 0, -1, 0.5], [bad, 0, -1, 0.5]], np.float32)
+        sc = u.Scene(geom, np.zeros(2, np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (2, 1)))
+        with pytest.raises(u.UecrtError):
+            u.render(sc, cam, 32, 1, 5, seed=1)
+        with pytest.raises(u.UecrtError):
+            u.primary_hits(sc, [[0, 0, 0]], [[0, 0, -1]])
+
+
 def test_too_large_scene_falls_back_or_fails_loudly(u, oracle):
     lim = u.tensor_scan_max_spheres()
     assert lim == 1024

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -92,8 +93,13 @@ int validate_scene(const uecrt_scene* s) {
   if (!s) return fail(UECRT_ERR_INVALID, "scene is null");
   if (s->n > 65534u) return fail(UECRT_ERR_INVALID, "scene has %u spheres; the candidate lists hold 16-bit indices (max 65534)", s->n);
   if (s->n && (!s->geom || !s->mat_type || !s->mat_param)) return fail(UECRT_ERR_INVALID, "scene arrays are null");
-  for (uint32_t i = 0; i < s->n; ++i)
+  for (uint32_t i = 0; i < s->n; ++i) {
     if (s->mat_type[i] > UECRT_MAT_DIELECTRIC) return fail(UECRT_ERR_INVALID, "sphere %u: unknown material type %u", i, s->mat_type[i]);
+    // the scans square the coordinates (|c|^2 - r^2): beyond ~1e18 that overflows FP32 and the pre-filters lose their guarantee
+    const uecrt_float4 g = s->geom[i];
+    const bool ok = std::fabs(g.x) <= 1e18f && std::fabs(g.y) <= 1e18f && std::fabs(g.z) <= 1e18f && std::fabs(g.w) <= 1e18f;   // false for NaN
+    if (!ok) return fail(UECRT_ERR_INVALID, "sphere %u: centre / radius must be finite and below 1e18 in magnitude", i);
+  }
   return UECRT_OK;
 }
 
