@@ -189,6 +189,23 @@ def test_cli_scene_file_and_pfm(u, tmp_path):
     np.testing.assert_allclose(lin, acc[..., :3] / 32, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")), reason="binary not built")
+def test_cli_scan_flag_three_searches_one_image(tmp_path):
+    """--scan fp32 | tensor | grid: the same seed gives the same image (same paths; float sums differ in the last bits)."""
+    exe = os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")
+    imgs = {}
+    for mode in ("fp32", "tensor", "grid"):
+        out = tmp_path / f"{mode}.png"
+        r = subprocess.run([exe, "-v", "--scene", "final", "--width", "240", "--spp", "16", "--seed", "7", "--scan", mode, str(out)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "success" in r.stdout, r.stdout + r.stderr
+        assert {"fp32": "FP32-pipe scan", "tensor": "tensor-core scan", "grid": "uniform grid"}[mode] in r.stdout
+        imgs[mode] = read_png_rgb(out)
+    assert (imgs["fp32"] != imgs["tensor"]).mean() < 1e-3 and (imgs["fp32"] != imgs["grid"]).mean() < 1e-3
+    r = subprocess.run([exe, "--scan", "bogus", str(tmp_path / "x.png")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and r.stdout.strip().endswith("error")
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "raytrace_dropin")), reason="oracle/_ref/raytrace_dropin not built")
 def test_reference_translation_unit_rehosted_on_the_abi(u, tmp_path):
     """oracle/dropin_demo.cpp: the reference's OWN source.cpp types (tuple hittable_list, camera, image_t,
