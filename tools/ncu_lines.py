@@ -25,7 +25,7 @@ by = collections.defaultdict(lambda: [0, 0, 0])
 for (loc, txt), r in zip(seq, data):
     by[loc][0] += int(r[ii]); by[loc][1] += int(r[si]); by[loc][2] += int(r[ti])
 src = {}
-for f in ('kernels.cu', 'closest_hit.cuh', 'materials.cuh', 'philox.cuh', 'tc_scan.cuh', 'tc_collect.cuh'):
+for f in ('kernels.cu', 'closest_hit.cuh', 'materials.cuh', 'philox.cuh', 'tc_scan.cuh', 'tc_collect.cuh', 'grid_walk.cuh'):
     src[f] = open('uecraytracing_b200/csrc/' + f).read().split('\n')
 agg = collections.defaultdict(lambda: [0, 0, 0])
 for loc, v in by.items():

@@ -593,21 +593,28 @@ struct TcProf {};
 #define UECRT_TCP(p, i)
 #endif
 
-// closest hit of one shade thread's ray through the pipeline; every shade thread calls it once per round
-template <bool EXACT, class InWindow>
-__device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t round, const DeviceScene& sc, const RayQuery& q, Hit& h,
-                                               TcProf& prof, InWindow&& in_window) {
+// closest hit of one shade thread's ray through the pipeline; every shade thread calls it once per round.
+// `m` is the pipeline's pass counter (tc_scan.cuh PassIter): one pass per round when the sphere operand is
+// resident; SWEEP: npasses passes of pass_rows spheres each, folded into one running closest hit in
+// ascending sphere index, so the later-index-wins tie rule holds across passes as it does inside one.
+template <bool EXACT, bool SWEEP, class InWindow>
+__device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint32_t npasses, int pass_rows, const DeviceScene& sc,
+                                               const RayQuery& q, Hit& h, TcProf& prof, InWindow&& in_window) {
   const ScanRay sr = make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz);
   h.id = -1;
   tc::shade_submit(sh, sr, q.live);
   UECRT_TCP(prof, 2)
   in_window();                                    // work that does not depend on this round's hit
   UECRT_TCP(prof, 1)
-  tc::shade_wait(sh, round);
-  UECRT_TCP(prof, 3)
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    tc::for_each_candidate(sh, q.live, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+    for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+      tc::shade_wait(sh, m++);
+      UECRT_TCP(prof, 3)
+      tc::for_each_candidate(sh, q.live, [&](int j) { test_fast(sc.geom, (int)base + j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+      if (!SWEEP || ++p == npasses) break;
+      tc::shade_next_pass(sh);
+    }
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
@@ -617,7 +624,13 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t round, co
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    tc::for_each_candidate(sh, q.live, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+    for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+      tc::shade_wait(sh, m++);
+      UECRT_TCP(prof, 3)
+      tc::for_each_candidate(sh, q.live, [&](int j) { test_exact(sc.geom, (int)base + j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+      if (!SWEEP || ++p == npasses) break;
+      tc::shade_next_pass(sh);
+    }
     if (best.id >= 0) {
       const float4 g = __ldg(&sc.geom[best.id]);
       const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
@@ -632,24 +645,27 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t round, co
   }
 }
 
-template <bool EXACT>
+template <bool EXACT, bool SWEEP>
 __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const RenderArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nchunks = a.sc.tc_nrows / tc::kNC;
-  const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, (uint32_t)a.sc.tc_nrows * 128u);
+  const uint32_t npasses = SWEEP ? (uint32_t)a.sc.tc_npasses : 1u;
+  const int pass_rows = a.sc.tc_nrows / (int)npasses;
+  const int nchunks = pass_rows / tc::kNC;
+  const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, SWEEP ? 0u : (uint32_t)a.sc.tc_nrows * 128u);
   const unsigned lane = threadIdx.x & 31u;
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
     if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
-      if (tc::elect_one()) tc::issuer_role(smem_raw, tmem_base, nchunks, -1, a.counters);
+      if (tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, a.sc.tc_rows, -1, a.counters);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
-    tc::scanner_role(smem_raw, tmem_base, nchunks, -1, a.counters);
+    tc::scanner_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, -1, a.counters);
   } else {
     if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
     tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
-    tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
+    tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, SWEEP ? 2u : 1u);
+    uint32_t pass_m = 0;
     const unsigned long long n_pixels = a.n_slots;
     const double inv_np = 1.0 / (double)n_pixels;
     const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
@@ -684,8 +700,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
       UECRT_TCP(prof, 0)
       const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
       Hit h;
-      tc_closest_hit<EXACT>(sh, round, a.sc, q, h, prof,
-                            [&]() { slot_refill_pooled(nx, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths); });
+      tc_closest_hit<EXACT, SWEEP>(sh, pass_m, npasses, pass_rows, a.sc, q, h, prof,
+                                   [&]() { slot_refill_pooled(nx, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths); });
       UECRT_TCP(prof, 4)
       if (st.active) {
         ++n_rays;
@@ -722,28 +738,31 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
 
 // K2 on the tensor-core scan: every shade thread takes one caller ray per round; all CTAs run the
 // same number of rounds (threads past the end of the ray array carry has_ray = false).
-template <bool EXACT>
+template <bool EXACT, bool SWEEP>
 __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const DeviceScene sc, unsigned long long n_rays,
                                                                      const float* __restrict__ o, const float* __restrict__ d,
                                                                      double tmin, double tmax, double* __restrict__ t_out,
                                                                      double* __restrict__ n_out, int32_t* __restrict__ id_out,
                                                                      uint8_t* __restrict__ ff_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nchunks = sc.tc_nrows / tc::kNC;
-  const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, (uint32_t)sc.tc_nrows * 128u);
+  const uint32_t npasses = SWEEP ? (uint32_t)sc.tc_npasses : 1u;
+  const int pass_rows = sc.tc_nrows / (int)npasses;
+  const int nchunks = pass_rows / tc::kNC;
+  const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, SWEEP ? 0u : (uint32_t)sc.tc_nrows * 128u);
   const unsigned long long stride = (unsigned long long)gridDim.x * tc::kShadeThreads;
   const int batches = (int)((n_rays + stride - 1) / stride);
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
     if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
-      if (tc::elect_one()) tc::issuer_role(smem_raw, tmem_base, nchunks, batches);
+      if (tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, sc.tc_rows, batches);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
-    tc::scanner_role(smem_raw, tmem_base, nchunks, batches);
+    tc::scanner_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, batches);
   } else {
     if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
-    tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks);
+    tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, SWEEP ? 2u : 1u);
+    uint32_t pass_m = 0;
     for (int b = 0; b < batches; ++b) {
       const unsigned long long i = (unsigned long long)b * stride + (unsigned long long)blockIdx.x * tc::kShadeThreads + threadIdx.x;
       const bool has_ray = i < n_rays;
@@ -755,14 +774,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
       const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
       const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
       tc::shade_submit(sh, sr, has_ray);
-      tc::shade_wait(sh, (uint32_t)b);
       double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
       int id = -1;
       bool front = false;
       if (!EXACT) {
         const float tmin_w = (float)tmin * dlen;
         FastBest best{(float)tmax * dlen, -1};
-        tc::for_each_candidate(sh, has_ray, [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+        for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+          tc::shade_wait(sh, pass_m++);
+          tc::for_each_candidate(sh, has_ray, [&](int j) { test_fast(sc.geom, (int)base + j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+          if (!SWEEP || ++p == npasses) break;
+          tc::shade_next_pass(sh);
+        }
         if (best.id >= 0) {
           Hit h; h.id = best.id; h.t = best.t;
           finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
@@ -772,7 +795,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
         const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
         ExactBest best{tmax, -1};
-        tc::for_each_candidate(sh, has_ray, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+        for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+          tc::shade_wait(sh, pass_m++);
+          tc::for_each_candidate(sh, has_ray, [&](int j) { test_exact(sc.geom, (int)base + j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+          if (!SWEEP || ++p == npasses) break;
+          tc::shade_next_pass(sh);
+        }
         if (best.id >= 0) {
           const float4 g = __ldg(&sc.geom[best.id]);
           const double px = __dadd_rn(Ox, __dmul_rn(Dx, best.t)), py = __dadd_rn(Oy, __dmul_rn(Dy, best.t)),
@@ -1070,14 +1098,20 @@ void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, 
 }
 
 // ---- tensor-core scan variants
-int tc_max_spheres() {
+int tc_resident_max_spheres() {
   const size_t fixed = tc::make_layout(0).total;
   const int fit = (int)((232448 - fixed) / (128 + 64) / tc::kNC * tc::kNC);   // 128 B operand + 64 B bitmap per sphere row
   return fit < tc::kMaxRows ? fit : tc::kMaxRows;
 }
+#ifndef UECRT_TC_SWEEP_ROWS
+#define UECRT_TC_SWEEP_ROWS 512      // two operand buffers of 64 KB + 32 KB of bitmaps
+#endif
+int tc_sweep_rows() { return UECRT_TC_SWEEP_ROWS; }
 int tc_threads() { return tc::kThreads; }
 int tc_chunk() { return tc::kNC; }
-size_t tc_smem_bytes(int tc_nrows) { return tc::make_layout((uint32_t)tc_nrows).total; }
+size_t tc_smem_bytes(int tc_nrows, int tc_npasses) {
+  return tc_npasses > 1 ? tc::make_layout((uint32_t)(tc_nrows / tc_npasses), 2u).total : tc::make_layout((uint32_t)tc_nrows).total;
+}
 
 cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
   cudaError_t e;
@@ -1087,32 +1121,45 @@ cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
   if (dev < 16 && !attrs_set[dev]) {
     const int optin = 232448;
 #define UECRT_SET(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
-    UECRT_SET(k_render_paths_tc<false>) UECRT_SET(k_render_paths_tc<true>)
-    UECRT_SET(k_primary_hits_tc<false>) UECRT_SET(k_primary_hits_tc<true>)
+    UECRT_SET((k_render_paths_tc<false, false>)) UECRT_SET((k_render_paths_tc<true, false>))
+    UECRT_SET((k_primary_hits_tc<false, false>)) UECRT_SET((k_primary_hits_tc<true, false>))
+    UECRT_SET((k_render_paths_tc<false, true>)) UECRT_SET((k_render_paths_tc<true, true>))
+    UECRT_SET((k_primary_hits_tc<false, true>)) UECRT_SET((k_primary_hits_tc<true, true>))
 #undef UECRT_SET
     attrs_set[dev] = true;
   }
   cudaFuncAttributes fa;
-  if ((e = cudaFuncGetAttributes(&fa, k_render_paths_tc<false>)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, k_render_paths_tc<false, false>)) != cudaSuccess) return e;
   if (regs_render) *regs_render = fa.numRegs;
   int n1 = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths_tc<false>, tc::kThreads, smem)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_render_paths_tc<false, false>, tc::kThreads, smem)) != cudaSuccess) return e;
   return n1 >= 1 ? cudaSuccess : cudaErrorInvalidConfiguration;
 }
 
 void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t smem, cudaStream_t st) {
-  if (exact) k_render_paths_tc<true><<<blocks, tc::kThreads, smem, st>>>(a);
-  else k_render_paths_tc<false><<<blocks, tc::kThreads, smem, st>>>(a);
+  const bool sweep = a.sc.tc_npasses > 1;
+  if (sweep) {
+    if (exact) k_render_paths_tc<true, true><<<blocks, tc::kThreads, smem, st>>>(a);
+    else k_render_paths_tc<false, true><<<blocks, tc::kThreads, smem, st>>>(a);
+  } else {
+    if (exact) k_render_paths_tc<true, false><<<blocks, tc::kThreads, smem, st>>>(a);
+    else k_render_paths_tc<false, false><<<blocks, tc::kThreads, smem, st>>>(a);
+  }
 }
 
 void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
                             double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, int sm_count,
                             cudaStream_t st) {
-  const size_t smem = tc_smem_bytes(sc.tc_nrows);
+  const size_t smem = tc_smem_bytes(sc.tc_nrows, sc.tc_npasses);
   unsigned long long want = (n_rays + tc::kShadeThreads - 1) / tc::kShadeThreads;
   const int blocks = (int)(want < 1 ? 1 : (want > (unsigned long long)sm_count ? (unsigned long long)sm_count : want));
-  if (exact) k_primary_hits_tc<true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
-  else k_primary_hits_tc<false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  if (sc.tc_npasses > 1) {
+    if (exact) k_primary_hits_tc<true, true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+    else k_primary_hits_tc<false, true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  } else {
+    if (exact) k_primary_hits_tc<true, false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+    else k_primary_hits_tc<false, false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+  }
 }
 
 void launch_resolve(const float4* accum, uint32_t n_pixels, uint32_t spp, uint8_t* rgb, cudaStream_t st) {

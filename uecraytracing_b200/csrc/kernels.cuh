@@ -24,8 +24,9 @@ struct DeviceScene {
   const float4* geom;        // {cx,cy,cz,r}
   const uint32_t* mat_type;
   const float4* mat_param;
-  const unsigned char* tc_rows;   // tensor-core scan operand (scene_pack.hpp pack_scene_tc), or null when the scene is too large
-  int tc_nrows;                   // rows (spheres padded to a multiple of tc::kNC)
+  const unsigned char* tc_rows;   // tensor-core scan operand (scene_pack.hpp pack_scene_tc), or null
+  int tc_nrows;                   // rows (spheres padded to a multiple of tc::kNC, or of the pass size when swept)
+  int tc_npasses;                 // 1: the operand is resident in shared memory; > 1: swept in that many equal slices
   DeviceGrid grid;
 };
 
@@ -76,11 +77,13 @@ void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, 
                               uint8_t* ff, cudaStream_t st);
 cudaError_t configure_kernels_grid(int* regs_render, int* max_blocks_per_sm);
 
-// ---- tensor-core scan variants (tc_scan.cuh): resident scenes of up to tc_max_spheres() spheres
-int tc_max_spheres();
+// ---- tensor-core scan variants (tc_scan.cuh): the sphere operand is resident in shared memory up to
+// tc_resident_max_spheres() spheres and swept through it in slices of tc_sweep_rows() rows above that
+int tc_resident_max_spheres();
+int tc_sweep_rows();
 int tc_threads();
 int tc_chunk();
-size_t tc_smem_bytes(int tc_nrows);
+size_t tc_smem_bytes(int tc_nrows, int tc_npasses);
 cudaError_t configure_kernels_tc(int* regs_render, size_t smem);
 void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t smem, cudaStream_t st);
 void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,

@@ -25,8 +25,12 @@ __device__ __forceinline__ void shade_submit(const Shade& s, const ScanRay& ray,
   fence_before_sync();
   mbar_arrive(s.a_ready);
 }
-// SHADE: wait for the bitmaps of round r
-__device__ __forceinline__ void shade_wait(const Shade& s, uint32_t round) { mbar_wait(s.scan_done, round & 1u); }
+// SHADE: wait for the bitmaps of pass m (tc_scan.cuh PassIter: m = the round when the operand is resident)
+__device__ __forceinline__ void shade_wait(const Shade& s, uint32_t m) { mbar_wait(s.scan_done, m & 1u); }
+// SHADE, swept operand: this thread has consumed its bitmap of the current pass; the ray tile in TMEM stays
+// as it is and takes part in the next pass (the arrive releases the bitmap to the scan warps: they only
+// write it again behind MMAs the issuer launches after this barrier's phase completes)
+__device__ __forceinline__ void shade_next_pass(const Shade& s) { mbar_arrive(s.a_ready); }
 
 // SHADE: f(sphere index) for every candidate of this thread's ray, ascending index.  WARP-CONVERGENT:
 // all 32 lanes must call it (a lane without a live ray passes live = false).  Every trip of the
@@ -77,7 +81,8 @@ __device__ __forceinline__ uint32_t sign_word(const int (&v)[32]) {
 }
 
 // SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
-__device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds,
+template <bool SWEEP>
+__device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses, int fixed_rounds,
                                              unsigned long long* prof_counters = nullptr) {
 #ifdef UECRT_TC_PROFILE
   long long pw = 0, pl = 0, ps = 0, plast = clock64();
@@ -87,7 +92,7 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
 #define UECRT_TCS(acc)
 #endif
   Header* h = reinterpret_cast<Header*>(smem_raw);
-  const Layout lay = make_layout((uint32_t)nchunks * kNC);
+  const Layout lay = make_layout((uint32_t)nchunks * kNC, SWEEP ? 2u : 1u);
   const uint32_t st = threadIdx.x - kShadeThreads, sg = st >> 7, row = st & 127u, lane = row & 31u;
   const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
   const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]);
@@ -95,7 +100,7 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
   uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw + lay.bitmap);
   uint32_t* summary = reinterpret_cast<uint32_t*>(smem_raw + lay.summary) + sg * kShadeThreads;
   uint32_t seq = 0;
-  for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
+  for (PassIter it; it.begin(h, fixed_rounds); it.next(npasses)) {
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
       uint32_t* out = bitmap + g * kGroupThreads + row;       // word w of this ray at out[w * kShadeThreads]
       uint32_t sum = 0;                                       // bit (31 - w): word w is non-zero

@@ -282,22 +282,25 @@ struct Header {               // first kHeaderBytes of dynamic shared memory
   uint64_t tmem_full[kRing];
   uint64_t tmem_empty[kRing];
   uint64_t b_loaded;          // the sphere operand has landed (cp.async.bulk)
+  uint64_t b_full[2];         // swept operand: the pass in buffer i has landed (expect_tx + cp.async.bulk)
+  uint64_t b_free[2];         // swept operand: every MMA that reads buffer i has completed (tcgen05.commit)
   uint32_t tmem_base;
   uint32_t pad_;
   uint8_t done_flags[8][16];  // [round & 7][shade warp] (kShadeThreads / 32 of the 16 are used)
 };
 
-// smem layout: [Header][B: rows * 128 B][summary: 512 words][bitmap: rows/32 words x 512 rays]
+// smem layout: [Header][B: nbuf x rows * 128 B][summary: 512 words][bitmap: rows/32 words x 512 rays]
+// (nbuf = 1: the whole sphere operand is resident; nbuf = 2: it is swept through two buffers of `rows` rows, see issuer_role)
 // bitmap word w of ray i lives at bitmap[w * 512 + i] (the 32 lanes of a warp touch consecutive words);
 // summary[sg * kShadeThreads + i] has bit (31 - w) set iff bitmap word w of ray i is non-zero (sg = the scan
 // warpgroup that packed word w; the shade thread ORs the warpgroups' words).
 struct Layout {
   uint32_t b, summary, bitmap, total;
 };
-__host__ __device__ inline Layout make_layout(uint32_t b_rows) {
+__host__ __device__ inline Layout make_layout(uint32_t b_rows, uint32_t nbuf = 1u) {
   Layout l;
   l.b = kHeaderBytes;
-  l.summary = l.b + b_rows * 128u;
+  l.summary = l.b + nbuf * b_rows * 128u;
   l.bitmap = l.summary + (uint32_t)kScanGroups * kShadeThreads * 4u;
   l.total = l.bitmap + (b_rows / 32u) * (uint32_t)kShadeThreads * 4u;
   return l;
@@ -310,7 +313,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// CTA-wide setup: barriers, TMEM, the bulk copy of the sphere operand.  Every thread calls it.
+// bulk copy global -> shared in pieces, completing `bytes` on the mbarrier (one thread)
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  const uint32_t kPiece = 32768;
+  for (uint32_t off = 0; off < bytes; off += kPiece) {
+    const uint32_t sz = bytes - off < kPiece ? bytes - off : kPiece;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem + off),
+                 "l"((const char*)src + off), "r"(sz), "r"(bar)
+                 : "memory");
+  }
+}
+
+// CTA-wide setup: barriers, TMEM, the bulk copy of the (resident) sphere operand; b_bytes = 0: the operand
+// is swept, the issuer loads it pass by pass.  Every thread calls it.
 __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const void* b_global, uint32_t b_bytes) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
   if (threadIdx.x == 0) {
@@ -323,6 +339,7 @@ __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const voi
       mbar_init(smem_addr(&h->tmem_empty[s]), 4);      // the four warps of the scan warpgroup that owns the chunk
     }
     mbar_init(smem_addr(&h->b_loaded), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_addr(&h->b_full[i]), 1); mbar_init(smem_addr(&h->b_free[i]), 1); }
     for (int i = 0; i < 8 * 16; ++i) (&h->done_flags[0][0])[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -330,18 +347,7 @@ __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const voi
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (threadIdx.x == 0) {
-    const uint32_t bar = smem_addr(&h->b_loaded);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bytes) : "memory");
-    const uint32_t kChunk = 32768;
-    for (uint32_t off = 0; off < b_bytes; off += kChunk) {
-      const uint32_t sz = b_bytes - off < kChunk ? b_bytes - off : kChunk;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_addr(smem_raw + kHeaderBytes + off)),
-                   "l"((const char*)b_global + off), "r"(sz), "r"(bar)
-                   : "memory");
-    }
-  }
+  if (threadIdx.x == 0 && b_bytes) bulk_load(smem_addr(smem_raw + kHeaderBytes), b_global, b_bytes, smem_addr(&h->b_loaded));
   return h->tmem_base;
 }
 __device__ __forceinline__ void cta_teardown(uint32_t tmem_base) {
@@ -362,8 +368,25 @@ __device__ __forceinline__ bool round_continues(const Header* h, uint32_t r, int
   return !(r >= 2u && all_done_at(h, r - 2u));
 }
 
-// ISSUER: one thread.
-__device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, int fixed_rounds,
+// The pipeline's unit of work is a PASS: every group's tile against `nchunks` chunks of the sphere operand.
+// Resident operand (scenes up to kMaxRows rows): one pass per round.  SWEPT operand (larger scenes): a round is
+// `npasses` passes over consecutive slices of the operand, which stream from L2 through two shared-memory
+// buffers; the ray tiles stay in TMEM for the whole round and the shade threads fold every pass's
+// candidates into their running closest hit.  Passes are numbered m = 0, 1, ... across rounds; every
+// per-pass barrier parity below is a function of m only.  The termination vote is per round and read
+// at a round's first pass.
+struct PassIter {
+  uint32_t m = 0, pass = 0, round = 0;
+  __device__ __forceinline__ bool begin(const Header* h, int fixed_rounds) const { return pass != 0u || round_continues(h, round, fixed_rounds); }
+  __device__ __forceinline__ void next(uint32_t npasses) { ++m; if (++pass == npasses) { pass = 0; ++round; } }
+};
+
+// ISSUER: one thread.  SWEEP: it also streams the operand: the slice of pass m+1 is requested at the start
+// of pass m into buffer (m+1) & 1, as soon as the MMAs of pass m-1 (the buffer's previous readers) have
+// completed (b_free, a tcgen05.commit behind that pass's last MMA); pass m starts when its slice has landed (b_full).
+template <bool SWEEP>
+__device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses,
+                                            const unsigned char* b_global, int fixed_rounds,
                                             unsigned long long* prof_counters = nullptr) {
 #ifdef UECRT_TC_PROFILE
   long long p_ready = 0, p_empty = 0, p_issue = 0, p_last = clock64();
@@ -373,15 +396,32 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
 #define UECRT_TCI(acc)
 #endif
   Header* h = reinterpret_cast<Header*>(smem_raw);
-  const Layout lay = make_layout((uint32_t)nchunks * kNC);
-  const uint32_t b_smem = smem_addr(smem_raw + lay.b);
+  const Layout lay = make_layout((uint32_t)nchunks * kNC, SWEEP ? 2u : 1u);
+  const uint32_t b_smem0 = smem_addr(smem_raw + lay.b), pass_bytes = (uint32_t)nchunks * (kNC * 128u);
   const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), ready0 = smem_addr(&h->a_ready[0]);
-  mbar_wait(smem_addr(&h->b_loaded), 0);
+  const uint32_t bfull0 = smem_addr(&h->b_full[0]), bfree0 = smem_addr(&h->b_free[0]);
+  uint32_t load_pass = 0;                                   // the operand slice the next load fetches
+  auto load_slice = [&](uint32_t m) {                       // into buffer m & 1, completing on b_full[m & 1]
+    bulk_load(b_smem0 + (m & 1u) * pass_bytes, b_global + (size_t)load_pass * pass_bytes, pass_bytes, bfull0 + 8u * (m & 1u));
+    if (++load_pass == npasses) load_pass = 0;
+  };
+  if (!SWEEP) mbar_wait(smem_addr(&h->b_loaded), 0);
+  else { load_slice(0); load_slice(1); }
   uint32_t seq = 0;
-  for (uint32_t r = 0; round_continues(h, r, fixed_rounds); ++r) {
+  PassIter it;
+  for (; it.begin(h, fixed_rounds); it.next(npasses)) {
+    const uint32_t m = it.m;
+    if (SWEEP) {
+      if (m >= 1u) {
+        mbar_wait(bfree0 + 8u * ((m - 1u) & 1u), ((m - 1u) >> 1) & 1u);
+        load_slice(m + 1u);
+      }
+      mbar_wait(bfull0 + 8u * (m & 1u), (m >> 1) & 1u);
+    }
+    const uint32_t b_smem = b_smem0 + (SWEEP ? (m & 1u) * pass_bytes : 0u);
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
       UECRT_TCI(p_issue)
-      mbar_wait(ready0 + 8u * g, r & 1u);
+      mbar_wait(ready0 + 8u * g, m & 1u);
       UECRT_TCI(p_ready)
       for (int j = 0; j < nchunks; ++j, ++seq) {
         const uint32_t slot = seq % kRing, use = seq / kRing;
@@ -396,6 +436,12 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
       ++p_tiles;
 #endif
     }
+    if (SWEEP) mma_commit(bfree0 + 8u * (m & 1u));
+  }
+  if (SWEEP) {
+    // loads were requested for passes 0 .. max(1, m_end); those never run: let them land before the CTA goes away
+    const uint32_t last = it.m > 1u ? it.m : 1u;
+    for (uint32_t k = it.m; k <= last; ++k) mbar_wait(bfull0 + 8u * (k & 1u), (k >> 1) & 1u);
   }
 #ifdef UECRT_TC_PROFILE
   if (prof_counters) {
@@ -417,9 +463,9 @@ struct Shade {
   unsigned long long prof_trips = 0, prof_steps = 0, prof_cands = 0;
 #endif
 };
-__device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
+__device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t nbuf = 1u) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
-  const Layout lay = make_layout((uint32_t)nchunks * kNC);
+  const Layout lay = make_layout((uint32_t)nchunks * kNC, nbuf);
   const uint32_t g = threadIdx.x / kGroupThreads;
   Shade s;
   s.a_ready = smem_addr(&h->a_ready[g]); s.scan_done = smem_addr(&h->scan_done[g]);

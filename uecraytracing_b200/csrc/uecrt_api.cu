@@ -148,6 +148,10 @@ std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
 #define UECRT_AUTO_SCAN UECRT_SCAN_TENSOR   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
 #endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
+#ifndef UECRT_AUTO_SWEEP
+#define UECRT_AUTO_SWEEP 0
+#endif
+constexpr bool kAutoSweep = UECRT_AUTO_SWEEP != 0;   // automatic mode: scenes above the residency limit use the swept tensor scan
 constexpr uint32_t kTensorScanMinSpheres = 96;   // automatic mode: smaller scenes use the FP32 scan
 constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists = 73 KB -> 3 CTAs per SM
 constexpr size_t kSmemOptin = 232448;
@@ -187,10 +191,12 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     CUDA_TRY(cudaMemcpy(c->d_mat_type, scene->mat_type, (size_t)scene->n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_mat_param, scene->mat_param, (size_t)scene->n * sizeof(uecrt_float4), cudaMemcpyHostToDevice));
   }
-  // tensor-core scan operand (128 B per sphere, resident): only when the scene fits
-  c->sc.tc_rows = nullptr; c->sc.tc_nrows = 0; c->smem_tc = 0;
-  if ((int)scene->n <= uecrt::tc_max_spheres()) {
-    const uecrt::PackedSceneTc pt = uecrt::pack_scene_tc(*scene, (uint32_t)uecrt::tc_chunk());
+  // tensor-core scan operand (128 B per sphere): resident in shared memory when the scene fits, else padded to
+  // whole slices of tc_sweep_rows() rows that the kernel sweeps through two shared-memory buffers
+  c->sc.tc_rows = nullptr; c->sc.tc_nrows = 0; c->sc.tc_npasses = 1; c->smem_tc = 0;
+  {
+    const bool resident = (int)scene->n <= uecrt::tc_resident_max_spheres();
+    const uecrt::PackedSceneTc pt = uecrt::pack_scene_tc(*scene, (uint32_t)(resident ? uecrt::tc_chunk() : uecrt::tc_sweep_rows()));
     if (pt.bytes.size() > c->cap_tc) {
       cudaFree(c->d_tc); c->d_tc = nullptr; c->cap_tc = 0;
       CUDA_TRY(cudaMalloc(&c->d_tc, pt.bytes.size()));
@@ -199,7 +205,8 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     CUDA_TRY(cudaMemcpy(c->d_tc, pt.bytes.data(), pt.bytes.size(), cudaMemcpyHostToDevice));
     c->sc.tc_rows = static_cast<const unsigned char*>(c->d_tc);
     c->sc.tc_nrows = (int)pt.rows;
-    c->smem_tc = uecrt::tc_smem_bytes((int)pt.rows);
+    c->sc.tc_npasses = resident ? 1 : (int)pt.rows / uecrt::tc_sweep_rows();
+    c->smem_tc = uecrt::tc_smem_bytes((int)pt.rows, c->sc.tc_npasses);
   }
   c->h_geom.assign(scene->geom, scene->geom + scene->n);
   c->grid_ready = false;
@@ -369,9 +376,9 @@ int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
   // tiles (uecrt_set_tile_spheres), which is a request for the FP32 scan's tile ring
   // and below ~100 spheres the FP32 scan is faster (one 128-column MMA chunk per tile is the tensor scan's floor;
   // measured crossover between 64 and 128 spheres, profiles/README.md)
-  if (want == UECRT_SCAN_AUTO) want = (g_tile_spheres.load() || ctx->n < kTensorScanMinSpheres) ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
+  if (want == UECRT_SCAN_AUTO) want = (g_tile_spheres.load() || ctx->n < kTensorScanMinSpheres || (!kAutoSweep && ctx->sc.tc_npasses > 1)) ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
   if (want == UECRT_SCAN_TENSOR && !ctx->sc.tc_rows) {
-    if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but the scene has %u spheres (resident limit %d)", ctx->n, uecrt::tc_max_spheres());
+    if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but the scene has %u spheres (resident limit %d)", ctx->n, uecrt::tc_resident_max_spheres());
     want = UECRT_SCAN_FP32;
   }
   *out = want;
@@ -685,7 +692,8 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
 void uecrt_set_scan_mode(int m) { g_scan_mode.store((m == UECRT_SCAN_FP32 || m == UECRT_SCAN_TENSOR || m == UECRT_SCAN_GRID) ? m : UECRT_SCAN_AUTO); }
-int uecrt_tensor_scan_max_spheres(void) { return uecrt::tc_max_spheres(); }
+int uecrt_tensor_scan_max_spheres(void) { return 65534; }
+int uecrt_tensor_scan_resident_spheres(void) { return uecrt::tc_resident_max_spheres(); }
 void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store((rays == 2 && uecrt::max_rays_per_thread() == 2) ? 2 : 1); }
 
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
