@@ -134,10 +134,13 @@ void uecrt_set_tile_spheres(uint32_t spheres_per_tile);
 void uecrt_set_rays_per_thread(int rays);
 
 /* Process default for calls that force neither scan.  UECRT_SCAN_AUTO picks the tensor-core scan for scenes of
- * 96 .. uecrt_tensor_scan_max_spheres() spheres (its shared-memory residency limit) and the FP32 scan
- * otherwise (smaller scenes: faster there; larger ones and forced tiles: swept through shared memory). */
+ * 96 spheres and more, and the FP32 scan for smaller scenes (faster there) and when tiles were forced with
+ * uecrt_set_tile_spheres.  Up to uecrt_tensor_scan_resident_spheres() spheres the tensor scan keeps its sphere
+ * operand (128 B per sphere) resident in shared memory; above that it sweeps it through shared memory in
+ * 512-sphere slices, up to uecrt_tensor_scan_max_spheres() (the scene size limit). */
 void uecrt_set_scan_mode(int uecrt_scan_mode);
 int uecrt_tensor_scan_max_spheres(void);
+int uecrt_tensor_scan_resident_spheres(void);
 
 /* uecrt_primary_hits replaces hittable_list::hit_impl (hittable_list.hpp:32-58) on caller
  * rays: closest hit in the CLOSED interval [t_min, t_max], later index wins ties.

@@ -125,9 +125,10 @@ def test_edge_cases_golden(tensor):
             assert abs(t[0] - unhex(c["t"])[0]) <= T_REL_EXACT * abs(unhex(c["t"])[0]), c["name"]
 
 
-@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 500, 1023, 1024])
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 500, 1023, 1024, 1025, 1536, 1537, 2049, 3000])
 def test_scene_sizes_around_the_chunk_and_row_limits(tensor, oracle, n):
-    """Sphere counts around the 128-column MMA chunk and the 1024-row residency limit (pad rows never hit)."""
+    """Sphere counts around the 128-column MMA chunk, the 1024-row residency limit and, above it, the 512-row
+    slices of the swept operand (pad rows never hit)."""
     u = tensor
     rng = np.random.default_rng(100 + n)
     geom = np.concatenate([rng.uniform(-6, 6, (n, 3)), rng.uniform(0.1, 0.6, (n, 1))], axis=1).astype(np.float32)
@@ -164,24 +165,79 @@ def test_non_finite_geometry_is_rejected(u):
             u.primary_hits(sc, [[0, 0, 0]], [[0, 0, -1]])
 
 
-def test_too_large_scene_falls_back_or_fails_loudly(u, oracle):
-    lim = u.tensor_scan_max_spheres()
-    assert lim == 1024
-    n = lim + 1
-    rng = np.random.default_rng(5)
-    geom = np.concatenate([rng.uniform(-6, 6, (n, 3)), rng.uniform(0.1, 0.4, (n, 1))], axis=1).astype(np.float32)
-    sc = u.Scene(geom, np.zeros(n, np.uint32), np.tile(np.array([[.5, .5, .5, 0]], np.float32), (n, 1)))
-    cam = u.Camera.named("ref")
-    _, _, st = u.render(sc, cam, 64, 4, 5, seed=1)                      # automatic: FP32 scan
-    assert st["scan_mode"] == 1
-    with pytest.raises(u.UecrtError):
-        u.render(sc, cam, 64, 4, 5, seed=1, scan="tensor")              # forced: refuses, never substitutes
+def _random_scene(u, n, seed, span=6.0):
+    rng = np.random.default_rng(seed)
+    geom = np.concatenate([rng.uniform(-span, span, (n, 3)), rng.uniform(0.1, 0.4, (n, 1))], axis=1).astype(np.float32)
+    mats = rng.integers(0, 3, n).astype(np.uint32)
+    par = np.concatenate([rng.uniform(0.2, 0.9, (n, 3)), np.where(mats[:, None] == 2, 1.5, rng.uniform(0, 0.3, (n, 1)))], axis=1).astype(np.float32)
+    return u.Scene(geom, mats, par)
+
+
+def test_limits_reported(u):
+    assert u.tensor_scan_resident_spheres() == 1024
+    assert u.tensor_scan_max_spheres() == 65534
+
+
+@pytest.mark.parametrize("n", [1025, 2048, 5000])
+@pytest.mark.parametrize("exact", [False, True])
+def test_swept_operand_hits_identical_to_fp32_scan(u, n, exact):
+    """Scenes above the residency limit: the sphere operand is swept in 512-row slices, a ray's candidates
+    arrive pass by pass and fold into one closest hit.  t, normal, id, front_face must equal the FP32 scan's
+    bit for bit, including ties between coincident spheres that sit in different slices (later index wins)."""
+    sc = _random_scene(u, n, 40 + n, span=9.0)
+    g = sc.geom.copy()
+    for k in (7, 600, 1024, n - 1):                       # coincident spheres across slice boundaries
+        g[k] = (0.5, -0.25, -3.0, 0.5)
+    sc = u.Scene(g, sc.mat_type, sc.mat_param)
+    rng = np.random.default_rng(n)
+    o = rng.uniform(-10, 10, (60000, 3)).astype(np.float32)
+    d = (rng.normal(size=(60000, 3)) * rng.uniform(0.05, 5, (60000, 1))).astype(np.float32)
+    o[:100] = 0; d[:100] = (0.5, -0.25, -3.0) + rng.normal(scale=0.02, size=(100, 3))
+    out = {}
+    for mode in ("fp32", "tensor"):
+        u.set_scan_mode(mode)
+        try:
+            out[mode] = u.primary_hits(sc, o, d, exact=exact)
+        finally:
+            u.set_scan_mode("auto")
+    a, b = out["fp32"], out["tensor"]
+    assert (a[2] >= 0).sum() > 1000 and (a[2] == n - 1).sum() > 0 and not np.isin(a[2], [k for k in (7, 600, 1024) if k != n - 1]).any()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_swept_operand_render_takes_the_same_paths(u, oracle):
+    n = 3000
+    sc, cam = u.Scene.named("dense", seed=1, n=n), u.Camera.named("dense")
+    ra, aa, sa = u.render(sc, cam, 320, 8, 50, seed=6, return_accum=True)                  # automatic: swept tensor scan
+    rb, ab, sb = u.render(sc, cam, 320, 8, 50, seed=6, return_accum=True, scan="fp32")
+    assert sa["scan_mode"] == 2 and sb["scan_mode"] == 1 and sa["k1_threads"] == 768
+    assert sa["rays_traced"] == sb["rays_traced"] and sa["paths"] == sb["paths"] == 320 * u.image_height(320) * 8
+    assert np.all(aa[..., 3] == 8) and np.abs(aa[..., :3] - ab[..., :3]).max() <= 1e-3
+    for exact in (True,):
+        _, ae, se = u.render(sc, cam, 160, 4, 50, seed=6, return_accum=True, exact=exact, scan="tensor")
+        _, af, sf = u.render(sc, cam, 160, 4, 50, seed=6, return_accum=True, exact=exact, scan="fp32")
+        assert se["rays_traced"] == sf["rays_traced"] and np.abs(ae - af).max() <= 1e-3
+    # primary hits of the swept scan against the oracle (exact mode: index and front face bit-exact)
+    rng = np.random.default_rng(3)
+    o = np.concatenate([rng.uniform(-50, 50, (20000, 1)), rng.uniform(0.05, 6, (20000, 1)), rng.uniform(-50, 50, (20000, 1))], axis=1).astype(np.float32)
+    d = rng.normal(size=(20000, 3)).astype(np.float32)
     u.set_scan_mode("tensor")
     try:
-        with pytest.raises(u.UecrtError):
-            u.primary_hits(sc, [[0, 0, 0]], [[0, 0, -1]])
+        got = u.primary_hits(sc, o, d, exact=True)
     finally:
         u.set_scan_mode("auto")
+    _check_exact(got, oracle.hits(sc, o.astype(np.float64), d.astype(np.float64)), "dense 3000 swept")
+
+
+def test_forced_tiles_still_select_the_fp32_scan_on_large_scenes(u):
+    sc, cam = _random_scene(u, 1500, 8), u.Camera.named("ref")
+    u.set_tile_spheres(256)
+    try:
+        _, _, st = u.render(sc, cam, 64, 4, 5, seed=1)
+        assert st["scan_mode"] == 1 and st["tiles"] > 1
+    finally:
+        u.set_tile_spheres(0)
 
 
 @pytest.mark.parametrize("name,cam,W,spp", [("ref4", "ref", 400, 32), ("ref4d", "ref", 400, 32), ("final", "final", 400, 32)])

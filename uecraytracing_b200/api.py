@@ -225,3 +225,8 @@ def set_scan_mode(mode):
 
 def tensor_scan_max_spheres():
     return int(lib.uecrt_tensor_scan_max_spheres())
+
+
+def tensor_scan_resident_spheres():
+    """Largest scene whose tensor-scan operand stays resident in shared memory; larger scenes are swept in slices."""
+    return int(lib.uecrt_tensor_scan_resident_spheres())

@@ -108,7 +108,7 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         if (kScanGroups > 1 && (uint32_t)(j % kScanGroups) != sg) continue;      // another warpgroup's chunk
         const uint32_t slot = seq % kRing, use = seq / kRing;
 #ifdef UECRT_TC_PROFILE
-        if (mbar_test(full0 + 8u * slot, use & 1u)) { ++p_ready_now; } else { mbar_wait(full0 + 8u * slot, use & 1u); ++p_blocked; if (prof_counters && lane == 0 && j < 4) atomicAdd(prof_counters + 26 + j, 1ull); }
+        if (mbar_test(full0 + 8u * slot, use & 1u)) { ++p_ready_now; } else { const long long b0_ = clock64(); mbar_wait(full0 + 8u * slot, use & 1u); ++p_blocked; if (prof_counters && lane == 0 && j < 4) { atomicAdd(prof_counters + 26 + j, 1ull); if (j == 0) { atomicAdd(prof_counters + 42 + g, 1ull); atomicAdd(prof_counters + 46 + g, (unsigned long long)(clock64() - b0_)); } } }
 #else
         mbar_wait(full0 + 8u * slot, use & 1u);
 #endif
@@ -150,6 +150,8 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
     atomicAdd(prof_counters + 13, (unsigned long long)pw);
     atomicAdd(prof_counters + 14, (unsigned long long)pl);
     atomicAdd(prof_counters + 15, (unsigned long long)ps);
+    atomicAdd(prof_counters + 32 + ((threadIdx.x >> 5) & 3), (unsigned long long)pw);
+    atomicAdd(prof_counters + 36 + ((threadIdx.x >> 5) & 3), (unsigned long long)pl);
     atomicAdd(prof_counters + 24, p_ready_now);
     atomicAdd(prof_counters + 25, p_blocked);
   }

@@ -164,7 +164,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       ::"r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
 }
-// named barrier of `nthreads` threads (tools/microbench/tc_probe.cu only)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
   uint32_t ok;
   asm volatile(
@@ -176,6 +175,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      
       : "memory");
   return ok != 0;
 }
+// named barrier of `nthreads` threads (tools/microbench/tc_probe.cu only)
 __device__ __forceinline__ void group_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -381,15 +381,15 @@ struct PassIter {
   __device__ __forceinline__ void next(uint32_t npasses) { ++m; if (++pass == npasses) { pass = 0; ++round; } }
 };
 
-// ISSUER: one thread.  SWEEP: it also streams the operand: the slice of pass m+1 is requested at the start
-// of pass m into buffer (m+1) & 1, as soon as the MMAs of pass m-1 (the buffer's previous readers) have
+// ISSUER: one thread.  SWEEP: it also streams the operand: the slice of pass m+1 is requested during pass m
+// (behind its first tile) into buffer (m+1) & 1, once the MMAs of pass m-1 (the buffer's previous readers) have
 // completed (b_free, a tcgen05.commit behind that pass's last MMA); pass m starts when its slice has landed (b_full).
 template <bool SWEEP>
 __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses,
                                             const unsigned char* b_global, int fixed_rounds,
                                             unsigned long long* prof_counters = nullptr) {
 #ifdef UECRT_TC_PROFILE
-  long long p_ready = 0, p_empty = 0, p_issue = 0, p_last = clock64();
+  long long p_ready = 0, p_empty = 0, p_issue = 0, p_bfree = 0, p_bfull = 0, p_last = clock64();
   unsigned long long p_tiles = 0;
 #define UECRT_TCI(acc) { const long long now_ = clock64(); acc += now_ - p_last; p_last = now_; }
 #else
@@ -412,11 +412,9 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
   for (; it.begin(h, fixed_rounds); it.next(npasses)) {
     const uint32_t m = it.m;
     if (SWEEP) {
-      if (m >= 1u) {
-        mbar_wait(bfree0 + 8u * ((m - 1u) & 1u), ((m - 1u) >> 1) & 1u);
-        load_slice(m + 1u);
-      }
+      UECRT_TCI(p_issue)
       mbar_wait(bfull0 + 8u * (m & 1u), (m >> 1) & 1u);
+      UECRT_TCI(p_bfull)
     }
     const uint32_t b_smem = b_smem0 + (SWEEP ? (m & 1u) * pass_bytes : 0u);
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
@@ -435,6 +433,15 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
 #ifdef UECRT_TC_PROFILE
       ++p_tiles;
 #endif
+      if (SWEEP && g == 0u && m >= 1u) {
+        // behind the first tile, not at the pass boundary: by now the previous pass's MMAs have long completed,
+        // so the wait is free, and the ring already holds this pass's first chunks while the copy is set up
+        UECRT_TCI(p_issue)
+        mbar_wait(bfree0 + 8u * ((m - 1u) & 1u), ((m - 1u) >> 1) & 1u);
+        UECRT_TCI(p_bfree)
+        load_slice(m + 1u);
+        UECRT_TCI(p_bfull)
+      }
     }
     if (SWEEP) mma_commit(bfree0 + 8u * (m & 1u));
   }
@@ -449,6 +456,8 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
     atomicAdd(prof_counters + 21, (unsigned long long)p_ready);
     atomicAdd(prof_counters + 22, (unsigned long long)p_empty);
     atomicAdd(prof_counters + 23, (unsigned long long)p_issue);
+    atomicAdd(prof_counters + 40, (unsigned long long)p_bfree);
+    atomicAdd(prof_counters + 41, (unsigned long long)p_bfull);
   }
 #endif
 }

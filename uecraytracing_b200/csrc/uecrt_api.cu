@@ -149,7 +149,7 @@ std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
 #endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
 #ifndef UECRT_AUTO_SWEEP
-#define UECRT_AUTO_SWEEP 0
+#define UECRT_AUTO_SWEEP 1
 #endif
 constexpr bool kAutoSweep = UECRT_AUTO_SWEEP != 0;   // automatic mode: scenes above the residency limit use the swept tensor scan
 constexpr uint32_t kTensorScanMinSpheres = 96;   // automatic mode: smaller scenes use the FP32 scan
@@ -251,8 +251,8 @@ int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* ca
   }
   cudaError_t e;
   if (!c->configured) {
-    if ((e = cudaMalloc(&c->d_counters, 32 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMemset(c->d_counters, 0, 32 * sizeof(unsigned long long))) != cudaSuccess ||
+    if ((e = cudaMalloc(&c->d_counters, 64 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_counters, 0, 64 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess)
       return fail(UECRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
@@ -378,7 +378,7 @@ int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
   // measured crossover between 64 and 128 spheres, profiles/README.md)
   if (want == UECRT_SCAN_AUTO) want = (g_tile_spheres.load() || ctx->n < kTensorScanMinSpheres || (!kAutoSweep && ctx->sc.tc_npasses > 1)) ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
   if (want == UECRT_SCAN_TENSOR && !ctx->sc.tc_rows) {
-    if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but the scene has %u spheres (resident limit %d)", ctx->n, uecrt::tc_resident_max_spheres());
+    if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but no operand was built for this scene (%u spheres)", ctx->n);
     want = UECRT_SCAN_FP32;
   }
   *out = want;
@@ -403,7 +403,7 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.accum = reinterpret_cast<float4*>(d_accum);
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
-  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 64 * sizeof(unsigned long long), st));
   const bool exact = (p->flags & UECRT_FLAG_EXACT_HITS) != 0;
   int mode = 0;
   if ((rc_mode(p->flags, ctx, &mode))) return UECRT_ERR_INVALID;
@@ -449,7 +449,7 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   out->sphere_tests = ctx->last_scan_mode == UECRT_SCAN_GRID ? h[3] : h[1] * (unsigned long long)ctx->n;
 #ifdef UECRT_TC_PROFILE
   {   // phase clocks of the tensor-scan K1 shade warps (SM cycles per warp-round), debugging builds only
-    unsigned long long q[32];
+    unsigned long long q[64];
     CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
     if (q[4]) {
       const char* nm[7] = {"take_next", "prepare_next", "submit", "wait_scan", "resolve", "shade", "total"};
@@ -464,6 +464,12 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
       fprintf(stderr, "[tc profile] blocked chunk waits by chunk index: %llu %llu %llu %llu (of %llu tiles x 4 warps)\n", q[26], q[27], q[28], q[29], q[20]);
       if (q[12]) fprintf(stderr, "[tc profile] scan warps: tiles %llu, per tile: wait_full %.0f ld+pack %.0f arrive %.0f cycles\n", q[12],
                          (double)q[13] / q[12], (double)q[14] / q[12], (double)q[15] / q[12]);
+      if (q[40] + q[41]) fprintf(stderr, "[tc profile] issuer, swept operand, per tile: wait b_free %.0f, load + wait b_full %.0f cycles\n", (double)q[40] / q[20], (double)q[41] / q[20]);
+      fprintf(stderr, "[tc profile] blocked chunk-0 waits by group: count %llu %llu %llu %llu, mean cycles %.0f %.0f %.0f %.0f\n", q[42], q[43], q[44], q[45],
+              q[42] ? (double)q[46] / q[42] : 0.0, q[43] ? (double)q[47] / q[43] : 0.0, q[44] ? (double)q[48] / q[44] : 0.0, q[45] ? (double)q[49] / q[45] : 0.0);
+      if (q[12]) fprintf(stderr, "[tc profile] per scan warp (SM sub-partition 0..3), per tile: wait_full %.0f %.0f %.0f %.0f, ld+pack %.0f %.0f %.0f %.0f\n",
+                         4.0 * q[32] / q[12], 4.0 * q[33] / q[12], 4.0 * q[34] / q[12], 4.0 * q[35] / q[12],
+                         4.0 * q[36] / q[12], 4.0 * q[37] / q[12], 4.0 * q[38] / q[12], 4.0 * q[39] / q[12]);
     }
   }
 #endif
