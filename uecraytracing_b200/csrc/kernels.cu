@@ -585,6 +585,9 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
 // shading as above; only the all-pairs discriminant evaluation moves from the FP32 pipe to
 // tcgen05.mma.kind::tf32 (three-way TF32 split, FP32 accumulation in TMEM), and the CTA is
 // warp-specialised: 4 shade groups of 128 threads, one scan warpgroup, one issuer warp (1 CTA/SM).
+#ifndef UECRT_TC_ISSUER_WARP
+#define UECRT_TC_ISSUER_WARP 0     // which warp of the last warpgroup issues the MMAs (= the SM sub-partition it shares with a scan warp)
+#endif
 #ifdef UECRT_TC_PROFILE
 struct TcProf { long long t[8]; long long last; };
 #define UECRT_TCP(p, i) { __syncwarp(); const long long now_ = clock64(); (p).t[i] += now_ - (p).last; (p).last = now_; }
@@ -610,10 +613,18 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
     FastBest best{CUDART_INF_F, -1};
     for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
       tc::shade_wait(sh, m++);
+#ifdef UECRT_TC_TRACE
+      const uint32_t tile_ = 4u * (m - 1u) + threadIdx.x / 128u;
+      const bool trs_ = sh.trace && blockIdx.x == 0 && (threadIdx.x & 127u) == 0 && tile_ >= 750u && tile_ < 782u;
+      if (trs_) sh.trace[768 + 4 * (tile_ - 750u) + 2] = clock64();
+#endif
       UECRT_TCP(prof, 3)
       tc::for_each_candidate(sh, q.live, [&](int j) { test_fast(sc.geom, (int)base + j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
       if (!SWEEP || ++p == npasses) break;
       tc::shade_next_pass(sh);
+#ifdef UECRT_TC_TRACE
+      if (trs_) sh.trace[768 + 4 * (tile_ - 750u) + 3] = clock64();
+#endif
     }
     if (best.id >= 0) {
       h.id = best.id;
@@ -655,7 +666,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   const unsigned lane = threadIdx.x & 31u;
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
-    if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
+    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - (tc::kShadeThreads + tc::kScanThreads) / 32;   // warp-uniform
+    if (iw == UECRT_TC_ISSUER_WARP) {
       if (tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, a.sc.tc_rows, -1, a.counters);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {
@@ -665,6 +677,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
     if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
     tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, SWEEP ? 2u : 1u);
+#ifdef UECRT_TC_TRACE
+    sh.trace = a.counters;
+#endif
     uint32_t pass_m = 0;
     const unsigned long long n_pixels = a.n_slots;
     const double inv_np = 1.0 / (double)n_pixels;
@@ -753,7 +768,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
   const int batches = (int)((n_rays + stride - 1) / stride);
   if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
     tc::reg_dealloc<tc::kIssuerRegs>();
-    if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == (tc::kShadeThreads + tc::kScanThreads) / 32) {   // warp-uniform
+    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - (tc::kShadeThreads + tc::kScanThreads) / 32;   // warp-uniform
+    if (iw == UECRT_TC_ISSUER_WARP) {
       if (tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, sc.tc_rows, batches);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {

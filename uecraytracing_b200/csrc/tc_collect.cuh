@@ -80,6 +80,23 @@ __device__ __forceinline__ uint32_t sign_word(const int (&v)[32]) {
   return ~__byte_perm(lo, hi, 0x5410);                   // a set sign bit = NOT a candidate
 }
 
+// Same word when the scene is large and candidates are sparse (swept operand): most 32-sphere words are empty for
+// ALL 32 rays of a warp (dense 10 k scene: ~80 %), so first reduce the 32 accumulators with integer max (full
+// issue rate; an accumulator read as a signed integer is >= 0 iff its sign bit is clear) and pack only if some
+// lane of the warp has a candidate in this word.  Same bits as sign_word in every case.  WARP-CONVERGENT.
+__device__ __forceinline__ uint32_t sign_word_sparse(const int (&v)[32]) {
+  int m[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    m[k] = v[8 * k];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m[k] = max(m[k], v[8 * k + i]);
+  }
+  const int mx = max(max(m[0], m[1]), max(m[2], m[3]));
+  if (!__any_sync(0xffffffffu, mx >= 0)) return 0u;
+  return sign_word(v);
+}
+
 // SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
 template <bool SWEEP>
 __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses, int fixed_rounds,
@@ -114,26 +131,37 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
 #endif
         fence_after_sync();
         UECRT_TCS(pw)
+#ifdef UECRT_TC_TRACE
+        const bool tr_ = prof_counters && blockIdx.x == 0 && st == 32u && seq >= 3000u && seq < 3064u;
+        if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 2] = clock64();
+#endif
         const uint32_t t0 = lane_taddr + slot * kNC;
         uint32_t* o = out + (size_t)j * (kNC / 32) * kShadeThreads;
         int va[32], vb[32];
         tmem_ld32(t0, va);
         tmem_ld32(t0 + 32, vb);
         tmem_ld_wait();
-        const uint32_t w0 = sign_word(va);
+        const uint32_t w0 = SWEEP ? sign_word_sparse(va) : sign_word(va);
         tmem_ld32(t0 + 64, va);
-        const uint32_t w1 = sign_word(vb);
+        const uint32_t w1 = SWEEP ? sign_word_sparse(vb) : sign_word(vb);
         tmem_ld32(t0 + 96, vb);
         o[0] = w0;
         o[kShadeThreads] = w1;
         tmem_ld_wait();
         fence_before_sync();                              // the whole slot is in registers: hand it back
         if (lane == 0) mbar_arrive(empty0 + 8u * slot);
-        const uint32_t w2 = sign_word(va), w3 = sign_word(vb);
+#ifdef UECRT_TC_TRACE
+        if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 3] = clock64();
+        if (prof_counters && blockIdx.x == 0 && (st == 0u || st == 96u) && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + (st == 0u ? 6 : 7)] = clock64();
+#endif
+        const uint32_t w2 = SWEEP ? sign_word_sparse(va) : sign_word(va), w3 = SWEEP ? sign_word_sparse(vb) : sign_word(vb);
         o[2 * kShadeThreads] = w2;
         o[3 * kShadeThreads] = w3;
         const uint32_t nz = (w0 ? 8u : 0u) | (w1 ? 4u : 0u) | (w2 ? 2u : 0u) | (w3 ? 1u : 0u);
         sum |= nz << (28 - 4 * j);
+#ifdef UECRT_TC_TRACE
+        if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 4] = clock64();
+#endif
         UECRT_TCS(pl)
       }
       summary[g * kGroupThreads + row] = sum;

@@ -419,15 +419,31 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
     const uint32_t b_smem = b_smem0 + (SWEEP ? (m & 1u) * pass_bytes : 0u);
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
       UECRT_TCI(p_issue)
+#ifdef UECRT_TC_TRACE
+      const bool trt_ = prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u;
+      if (trt_) prof_counters[768 + 4 * (seq / 4u - 750u)] = clock64();
+#endif
       mbar_wait(ready0 + 8u * g, m & 1u);
+#ifdef UECRT_TC_TRACE
+      if (trt_) prof_counters[768 + 4 * (seq / 4u - 750u) + 1] = clock64();
+#endif
       UECRT_TCI(p_ready)
       for (int j = 0; j < nchunks; ++j, ++seq) {
         const uint32_t slot = seq % kRing, use = seq / kRing;
-        if (use >= 1u) mbar_wait(empty0 + 8u * slot, (use - 1u) & 1u);      // the scanners have read the previous contents
+#ifdef UECRT_TC_TRACE
+        if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + 5] = clock64();
+#endif
+        if (use >= 1u) mbar_wait(empty0 + 8u * slot, (use - 1u) & 1u);  // the scanners have read the previous contents
         UECRT_TCI(p_empty)
+#ifdef UECRT_TC_TRACE
+        if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u)] = clock64();
+#endif
         fence_after_sync();
         issue_tile_ts(tmem_base + slot * kNC, tmem_base + kATmemCol + g * (uint32_t)kSlots, b_smem + (uint32_t)j * (kNC * 128u), kNC);
         mma_commit(full0 + 8u * slot);
+#ifdef UECRT_TC_TRACE
+        if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + 1] = clock64();
+#endif
         UECRT_TCI(p_issue)
       }
 #ifdef UECRT_TC_PROFILE
@@ -470,6 +486,9 @@ struct Shade {
   const uint32_t* bitmap;            // this ray's candidate bitmap: word w at bitmap[w * kShadeThreads]
 #ifdef UECRT_TC_PROFILE
   unsigned long long prof_trips = 0, prof_steps = 0, prof_cands = 0;
+#endif
+#ifdef UECRT_TC_TRACE
+  unsigned long long* trace = nullptr;
 #endif
 };
 __device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t nbuf = 1u) {

@@ -148,6 +148,7 @@ std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
 #define UECRT_AUTO_SCAN UECRT_SCAN_TENSOR   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
 #endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
+constexpr int kCounterWords = 1024;      // [0,64): statistics and profile sums; [128, 128 + 5*128): UECRT_TC_TRACE timeline
 #ifndef UECRT_AUTO_SWEEP
 #define UECRT_AUTO_SWEEP 1
 #endif
@@ -251,8 +252,8 @@ int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* ca
   }
   cudaError_t e;
   if (!c->configured) {
-    if ((e = cudaMalloc(&c->d_counters, 64 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMemset(c->d_counters, 0, 64 * sizeof(unsigned long long))) != cudaSuccess ||
+    if ((e = cudaMalloc(&c->d_counters, kCounterWords * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_counters, 0, kCounterWords * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess)
       return fail(UECRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
@@ -403,7 +404,7 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.accum = reinterpret_cast<float4*>(d_accum);
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
-  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, 64 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, kCounterWords * sizeof(unsigned long long), st));
   const bool exact = (p->flags & UECRT_FLAG_EXACT_HITS) != 0;
   int mode = 0;
   if ((rc_mode(p->flags, ctx, &mode))) return UECRT_ERR_INVALID;
@@ -447,9 +448,28 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   CUDA_TRY(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
   out->rays_traced = h[1]; out->paths = h[2];
   out->sphere_tests = ctx->last_scan_mode == UECRT_SCAN_GRID ? h[3] : h[1] * (unsigned long long)ctx->n;
+#ifdef UECRT_TC_TRACE
+  {   // timeline of one CTA's issuer and one scan warp (debugging builds only)
+    static unsigned long long q[kCounterWords];
+    CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
+    if (q[128]) {
+      fprintf(stderr, "[tc trace] tiles from 750 (tile = 4 x pass + group): issuer waits a_ready from, until | shade warp 0 of the group: scan_done seen, bitmap consumed + re-armed (that is the a_ready of tile + 4)\n");
+      for (int i = 0; i < 24; ++i) {
+        const unsigned long long* e = q + 768 + 4 * i, t0 = q[128];
+        fprintf(stderr, "[tc trace] %4d | %7lld %7lld | %7lld %7lld\n", 750 + i, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0), (long long)(e[3] - t0));
+      }
+      fprintf(stderr, "[tc trace] CTA 0, chunk sequence numbers from 3000; cycles relative to the first event\n[tc trace]  seq | issuer: reaches the slot wait, slot free, MMAs+commit issued | scan warp 1: slot full, all loaded (slot released), packed | release by scan warp 0, 3\n");
+      for (int i = 0; i < 40; ++i) {
+        const unsigned long long* e = q + 128 + 8 * i, t0 = q[128];
+        fprintf(stderr, "[tc trace] %4d | %7lld %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld\n", 3000 + i, (long long)(e[5] - t0), (long long)(e[0] - t0), (long long)(e[1] - t0),
+                (long long)(e[2] - t0), (long long)(e[3] - t0), (long long)(e[4] - t0), (long long)(e[6] - t0), (long long)(e[7] - t0));
+      }
+    }
+  }
+#endif
 #ifdef UECRT_TC_PROFILE
   {   // phase clocks of the tensor-scan K1 shade warps (SM cycles per warp-round), debugging builds only
-    unsigned long long q[64];
+    static unsigned long long q[kCounterWords];
     CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
     if (q[4]) {
       const char* nm[7] = {"take_next", "prepare_next", "submit", "wait_scan", "resolve", "shade", "total"};
