@@ -302,7 +302,9 @@ def main():
         rays_per_launch = rays / max(args.steps, 1) / max(world, 1)
         achieved = FLOP_PER_TEST * scene.n * rays_per_launch / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
         tensor_scan, grid_scan = st["scan_mode"] == 2, st["scan_mode"] == 3
-        config["scan"] = ("tensor cores (tcgen05 TF32 x3 split, TMEM accumulators)" if tensor_scan else
+        swept = tensor_scan and scene.n > u.tensor_scan_resident_spheres()
+        config["scan"] = ("tensor cores (tcgen05 TF32 x3 split, TMEM accumulators), sphere operand swept through shared memory in 512-row slices" if swept else
+                          "tensor cores (tcgen05 TF32 x3 split, TMEM accumulators)" if tensor_scan else
                           "uniform grid (opt-in spatial index; NOT the brute-force 18 x N x rays figure)" if grid_scan else
                           "FP32 pipe (packed FFMA2 from shared memory)")
         kernel_name = "k_render_paths_tc" if tensor_scan else "k_render_paths_grid" if grid_scan else "k_render_paths"
@@ -328,7 +330,7 @@ def main():
             out["roofline"]["rays_per_second"] = rays_per_launch * max(world, 1) / (k1_avg * 1e-3) if k1_avg > 0 else None
         if tensor_scan:
             # executed tensor work: every 128-ray tile x 128-sphere chunk is four M=128, N=128, K=8 TF32 MMAs
-            rows = (scene.n + 127) // 128 * 128
+            rows = (scene.n + 511) // 512 * 512 if swept else (scene.n + 127) // 128 * 128
             tiles = rays_per_launch / 128.0                     # lower bound: tiles also carry dead rows
             tf32 = 2.0 * 128 * rows * 32 * tiles / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
             bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 2250.0

@@ -42,6 +42,20 @@ int main() {
     }
   for (float v : brow) if (!tf32_exact(v)) { std::printf("slot not TF32-exact\n"); return 1; }
   for (uint32_t r = sc.n; r < p.rows; ++r) if (brow[(size_t)r * tc::kSlots + 9] > -1e29f) { std::printf("pad row can hit\n"); return 1; }
+  // 2b: the swept form (scenes above the residency limit) pads to whole 512-row slices, and a slice is one contiguous
+  // 64 KB block (rows are stored in 8-row groups of 1024 B), so the kernel can bulk-copy slice p from byte p * 65536
+  {
+    const PackedSceneTc q = pack_scene_tc(sc, 512);
+    if (q.rows % 512 || q.rows < sc.n || q.bytes.size() != (size_t)q.rows * 128) { std::printf("bad swept row count\n"); return 1; }
+    for (uint32_t r = 0; r < q.rows; ++r) {
+      const uint32_t lo = tc::row_chunk_offset(r, 0), hi = tc::row_chunk_offset(r, 7) + 16;
+      if (lo / 65536 != r / 512 || (hi - 1) / 65536 != r / 512) { std::printf("row %u leaves its slice\n", r); return 1; }
+    }
+    if (std::memcmp(q.bytes.data(), p.bytes.data(), p.bytes.size()) != 0) { std::printf("swept packing differs on the shared rows\n"); return 1; }
+    float last[4];
+    std::memcpy(last, &q.bytes[tc::row_chunk_offset(q.rows - 1, 2)], 16);        // slots 8..11: slot 9 = hi(-k + bound)
+    if (last[1] > -1e29f) { std::printf("swept pad row can hit\n"); return 1; }
+  }
   // 3: conservative superset on random rays (camera rays and rays leaving surfaces)
   const double u = std::ldexp(1.0, -24);
   long tested = 0, hits = 0;
