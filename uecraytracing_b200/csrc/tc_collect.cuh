@@ -111,19 +111,20 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC, SWEEP ? 2u : 1u);
   const uint32_t st = threadIdx.x - kShadeThreads, sg = st >> 7, row = st & 127u, lane = row & 31u;
-  const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
-  const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]);
-  const uint32_t ready0 = smem_addr(&h->a_ready[0]), done0 = smem_addr(&h->scan_done[0]);
-  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw + lay.bitmap);
-  uint32_t* summary = reinterpret_cast<uint32_t*>(smem_raw + lay.summary) + sg * kShadeThreads;
-  uint32_t seq = 0;
+  uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
+  uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), done0 = smem_addr(&h->scan_done[0]);
+  // this ray's bitmap word 0 of group 0 / its summary word, as shared addresses (word w of group g: + (w * kShadeThreads + g * 128) * 4)
+  uint32_t bitmap0 = smem_addr(smem_raw + lay.bitmap) + row * 4u;
+  uint32_t summary0 = smem_addr(smem_raw + lay.summary) + (sg * kShadeThreads + row) * 4u;
+  pin(lane_taddr); pin(full0); pin(empty0); pin(done0); pin(bitmap0); pin(summary0);
+  uint32_t seq = 0, slot = 0, parity = 0;                     // slot = seq % kRing, parity = (seq / kRing) & 1, kept incrementally
   for (PassIter it; it.begin(h, fixed_rounds); it.next(npasses)) {
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
-      uint32_t* out = bitmap + g * kGroupThreads + row;       // word w of this ray at out[w * kShadeThreads]
+      uint32_t o = bitmap0 + g * (kGroupThreads * 4u);        // word w of this ray at o + w * kShadeThreads * 4
       uint32_t sum = 0;                                       // bit (31 - w): word w is non-zero
-      for (int j = 0; j < nchunks; ++j, ++seq) {
+      for (int j = 0; j < nchunks; ++j, ++seq, o += (kNC / 32) * kShadeThreads * 4u, slot = slot == kRing - 1 ? 0u : slot + 1u, parity ^= (slot == 0u ? 1u : 0u)) {
         if (kScanGroups > 1 && (uint32_t)(j % kScanGroups) != sg) continue;      // another warpgroup's chunk
-        const uint32_t slot = seq % kRing, use = seq / kRing;
+        const uint32_t use = parity;
 #ifdef UECRT_TC_PROFILE
         if (mbar_test(full0 + 8u * slot, use & 1u)) { ++p_ready_now; } else { const long long b0_ = clock64(); mbar_wait(full0 + 8u * slot, use & 1u); ++p_blocked; if (prof_counters && lane == 0 && j < 4) { atomicAdd(prof_counters + 26 + j, 1ull); if (j == 0) { atomicAdd(prof_counters + 42 + g, 1ull); atomicAdd(prof_counters + 46 + g, (unsigned long long)(clock64() - b0_)); } } }
 #else
@@ -136,7 +137,6 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 2] = clock64();
 #endif
         const uint32_t t0 = lane_taddr + slot * kNC;
-        uint32_t* o = out + (size_t)j * (kNC / 32) * kShadeThreads;
         int va[32], vb[32];
         tmem_ld32(t0, va);
         tmem_ld32(t0 + 32, vb);
@@ -145,8 +145,8 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         tmem_ld32(t0 + 64, va);
         const uint32_t w1 = SWEEP ? sign_word_sparse(vb) : sign_word(vb);
         tmem_ld32(t0 + 96, vb);
-        o[0] = w0;
-        o[kShadeThreads] = w1;
+        sts32(o, w0);
+        sts32(o + kShadeThreads * 4u, w1);
         tmem_ld_wait();
         fence_before_sync();                              // the whole slot is in registers: hand it back
         if (lane == 0) mbar_arrive(empty0 + 8u * slot);
@@ -155,8 +155,8 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         if (prof_counters && blockIdx.x == 0 && (st == 0u || st == 96u) && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + (st == 0u ? 6 : 7)] = clock64();
 #endif
         const uint32_t w2 = SWEEP ? sign_word_sparse(va) : sign_word(va), w3 = SWEEP ? sign_word_sparse(vb) : sign_word(vb);
-        o[2 * kShadeThreads] = w2;
-        o[3 * kShadeThreads] = w3;
+        sts32(o + 2u * kShadeThreads * 4u, w2);
+        sts32(o + 3u * kShadeThreads * 4u, w3);
         const uint32_t nz = (w0 ? 8u : 0u) | (w1 ? 4u : 0u) | (w2 ? 2u : 0u) | (w3 ? 1u : 0u);
         sum |= nz << (28 - 4 * j);
 #ifdef UECRT_TC_TRACE
@@ -164,7 +164,7 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
 #endif
         UECRT_TCS(pl)
       }
-      summary[g * kGroupThreads + row] = sum;
+      sts32(summary0 + g * (kGroupThreads * 4u), sum);
       mbar_arrive(done0 + 8u * g);
 #ifdef UECRT_TC_PROFILE
       ++ptiles;

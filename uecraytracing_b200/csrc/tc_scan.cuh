@@ -175,6 +175,11 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      
       : "memory");
   return ok != 0;
 }
+// Keep a loop-invariant value in its register: without this ptxas re-derives shared addresses inside the
+// pipeline loops from S2R (SR_CgaCtaId, SR_TID) -- two ~25-cycle special-register reads and a dependent
+// integer chain in front of every chunk's barrier wait and first TMEM load (timeline trace: ~130 cycles per chunk).
+__device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 // named barrier of `nthreads` threads (tools/microbench/tc_probe.cu only)
 __device__ __forceinline__ void group_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -398,8 +403,9 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC, SWEEP ? 2u : 1u);
   const uint32_t b_smem0 = smem_addr(smem_raw + lay.b), pass_bytes = (uint32_t)nchunks * (kNC * 128u);
-  const uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), ready0 = smem_addr(&h->a_ready[0]);
+  uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), ready0 = smem_addr(&h->a_ready[0]);
   const uint32_t bfull0 = smem_addr(&h->b_full[0]), bfree0 = smem_addr(&h->b_free[0]);
+  pin(full0); pin(empty0); pin(ready0);
   uint32_t load_pass = 0;                                   // the operand slice the next load fetches
   auto load_slice = [&](uint32_t m) {                       // into buffer m & 1, completing on b_full[m & 1]
     bulk_load(b_smem0 + (m & 1u) * pass_bytes, b_global + (size_t)load_pass * pass_bytes, pass_bytes, bfull0 + 8u * (m & 1u));
@@ -407,7 +413,7 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
   };
   if (!SWEEP) mbar_wait(smem_addr(&h->b_loaded), 0);
   else { load_slice(0); load_slice(1); }
-  uint32_t seq = 0;
+  uint32_t seq = 0, slot = 0, parity = 1;                   // slot = seq % kRing; parity = that of the slot's PREVIOUS use, ((seq / kRing) - 1) & 1
   PassIter it;
   for (; it.begin(h, fixed_rounds); it.next(npasses)) {
     const uint32_t m = it.m;
@@ -428,12 +434,11 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
       if (trt_) prof_counters[768 + 4 * (seq / 4u - 750u) + 1] = clock64();
 #endif
       UECRT_TCI(p_ready)
-      for (int j = 0; j < nchunks; ++j, ++seq) {
-        const uint32_t slot = seq % kRing, use = seq / kRing;
+      for (int j = 0; j < nchunks; ++j, ++seq, slot = slot == kRing - 1 ? 0u : slot + 1u, parity ^= (slot == 0u ? 1u : 0u)) {
 #ifdef UECRT_TC_TRACE
         if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + 5] = clock64();
 #endif
-        if (use >= 1u) mbar_wait(empty0 + 8u * slot, (use - 1u) & 1u);  // the scanners have read the previous contents
+        if (seq >= (uint32_t)kRing) mbar_wait(empty0 + 8u * slot, parity);  // the scanners have read the previous contents
         UECRT_TCI(p_empty)
 #ifdef UECRT_TC_TRACE
         if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u)] = clock64();
