@@ -80,11 +80,11 @@ __device__ __forceinline__ uint32_t sign_word(const int (&v)[32]) {
   return ~__byte_perm(lo, hi, 0x5410);                   // a set sign bit = NOT a candidate
 }
 
-// Same word when the scene is large and candidates are sparse (swept operand): most 32-sphere words are empty for
-// ALL 32 rays of a warp (dense 10 k scene: ~80 %), so first reduce the 32 accumulators with integer max (full
-// issue rate; an accumulator read as a signed integer is >= 0 iff its sign bit is clear) and pack only if some
-// lane of the warp has a candidate in this word.  Same bits as sign_word in every case.  WARP-CONVERGENT.
-__device__ __forceinline__ uint32_t sign_word_sparse(const int (&v)[32]) {
+// When the scene is large and candidates are sparse (swept operand), most 32-sphere words are empty for ALL 32
+// rays of a warp (dense 10 k scene: ~80 %): first reduce the 32 accumulators with integer max (full issue
+// rate; an accumulator read as a signed integer is >= 0 iff its sign bit is clear) and pack only if some lane
+// of the warp has a candidate in this word.  Same bits as sign_word in every case.
+__device__ __forceinline__ int max_of(const int (&v)[32]) {
   int m[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -92,10 +92,10 @@ __device__ __forceinline__ uint32_t sign_word_sparse(const int (&v)[32]) {
 #pragma unroll
     for (int i = 1; i < 8; ++i) m[k] = max(m[k], v[8 * k + i]);
   }
-  const int mx = max(max(m[0], m[1]), max(m[2], m[3]));
-  if (!__any_sync(0xffffffffu, mx >= 0)) return 0u;
-  return sign_word(v);
+  return max(max(m[0], m[1]), max(m[2], m[3]));
 }
+// word of v if `any` (warp-uniform: some lane of the warp has a candidate in it), else 0
+__device__ __forceinline__ uint32_t sign_word_if(bool any, const int (&v)[32]) { return any ? sign_word(v) : 0u; }
 
 // SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
 template <bool SWEEP>
@@ -141,10 +141,21 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         tmem_ld32(t0, va);
         tmem_ld32(t0 + 32, vb);
         tmem_ld_wait();
-        const uint32_t w0 = SWEEP ? sign_word_sparse(va) : sign_word(va);
-        tmem_ld32(t0 + 64, va);
-        const uint32_t w1 = SWEEP ? sign_word_sparse(vb) : sign_word(vb);
-        tmem_ld32(t0 + 96, vb);
+        uint32_t w0, w1, w2, w3;
+        if (SWEEP) {
+          // the two max reductions first (8 independent chains), then the warp votes, then the packing where needed
+          const int ma = max_of(va), mb = max_of(vb);
+          const bool any_a = __any_sync(0xffffffffu, ma >= 0), any_b = __any_sync(0xffffffffu, mb >= 0);
+          w0 = sign_word_if(any_a, va);
+          tmem_ld32(t0 + 64, va);
+          w1 = sign_word_if(any_b, vb);
+          tmem_ld32(t0 + 96, vb);
+        } else {
+          w0 = sign_word(va);
+          tmem_ld32(t0 + 64, va);
+          w1 = sign_word(vb);
+          tmem_ld32(t0 + 96, vb);
+        }
         sts32(o, w0);
         sts32(o + kShadeThreads * 4u, w1);
         tmem_ld_wait();
@@ -154,7 +165,15 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 3] = clock64();
         if (prof_counters && blockIdx.x == 0 && (st == 0u || st == 96u) && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + (st == 0u ? 6 : 7)] = clock64();
 #endif
-        const uint32_t w2 = SWEEP ? sign_word_sparse(va) : sign_word(va), w3 = SWEEP ? sign_word_sparse(vb) : sign_word(vb);
+        if (SWEEP) {
+          const int ma = max_of(va), mb = max_of(vb);
+          const bool any_a = __any_sync(0xffffffffu, ma >= 0), any_b = __any_sync(0xffffffffu, mb >= 0);
+          w2 = sign_word_if(any_a, va);
+          w3 = sign_word_if(any_b, vb);
+        } else {
+          w2 = sign_word(va);
+          w3 = sign_word(vb);
+        }
         sts32(o + 2u * kShadeThreads * 4u, w2);
         sts32(o + 3u * kShadeThreads * 4u, w3);
         const uint32_t nz = (w0 ? 8u : 0u) | (w1 ? 4u : 0u) | (w2 ? 2u : 0u) | (w3 ? 1u : 0u);
