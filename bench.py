@@ -330,7 +330,8 @@ def main():
             out["roofline"]["rays_per_second"] = rays_per_launch * max(world, 1) / (k1_avg * 1e-3) if k1_avg > 0 else None
         if tensor_scan:
             # executed tensor work: every 128-ray tile x 128-sphere chunk is four M=128, N=128, K=8 TF32 MMAs
-            rows = (scene.n + 511) // 512 * 512 if swept else (scene.n + 127) // 128 * 128
+            chunks = (scene.n + 127) // 128
+            rows = 128 * (min((chunks + 3) // 4 * 4, (chunks + 2) // 3 * 3) if swept else chunks)      # kernels.cu tc_sweep_rows: slices of 4 or 3 chunks
             tiles = rays_per_launch / 128.0                     # lower bound: tiles also carry dead rows
             tf32 = 2.0 * 128 * rows * 32 * tiles / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
             bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 2250.0

@@ -1122,7 +1122,17 @@ int tc_resident_max_spheres() {
 #ifndef UECRT_TC_SWEEP_ROWS
 #define UECRT_TC_SWEEP_ROWS 512      // two operand buffers of 64 KB + 32 KB of bitmaps
 #endif
-int tc_sweep_rows() { return UECRT_TC_SWEEP_ROWS; }
+// slice size for a swept scene of n spheres: at most UECRT_TC_SWEEP_ROWS rows, and one 128-row chunk less per
+// slice when that leaves fewer never-hit pad rows in total (1025 spheres: 3 slices of 384 rows, not 3 of 512)
+int tc_sweep_rows(int n) {
+  const int chunks = (n + tc::kNC - 1) / tc::kNC, max_per = UECRT_TC_SWEEP_ROWS / tc::kNC;
+  int best_per = max_per, best_total = (chunks + max_per - 1) / max_per * max_per;
+  if (max_per > 1) {
+    const int per = max_per - 1, total = (chunks + per - 1) / per * per;
+    if (total < best_total) { best_per = per; best_total = total; }
+  }
+  return best_per * tc::kNC;
+}
 int tc_threads() { return tc::kThreads; }
 int tc_chunk() { return tc::kNC; }
 size_t tc_smem_bytes(int tc_nrows, int tc_npasses) {

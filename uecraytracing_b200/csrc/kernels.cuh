@@ -78,9 +78,9 @@ void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, 
 cudaError_t configure_kernels_grid(int* regs_render, int* max_blocks_per_sm);
 
 // ---- tensor-core scan variants (tc_scan.cuh): the sphere operand is resident in shared memory up to
-// tc_resident_max_spheres() spheres and swept through it in slices of tc_sweep_rows() rows above that
+// tc_resident_max_spheres() spheres and swept through it in slices of tc_sweep_rows(n) rows above that
 int tc_resident_max_spheres();
-int tc_sweep_rows();
+int tc_sweep_rows(int n_spheres);
 int tc_threads();
 int tc_chunk();
 size_t tc_smem_bytes(int tc_nrows, int tc_npasses);

@@ -193,11 +193,12 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     CUDA_TRY(cudaMemcpy(c->d_mat_param, scene->mat_param, (size_t)scene->n * sizeof(uecrt_float4), cudaMemcpyHostToDevice));
   }
   // tensor-core scan operand (128 B per sphere): resident in shared memory when the scene fits, else padded to
-  // whole slices of tc_sweep_rows() rows that the kernel sweeps through two shared-memory buffers
+  // whole slices of tc_sweep_rows(n) rows that the kernel sweeps through two shared-memory buffers
   c->sc.tc_rows = nullptr; c->sc.tc_nrows = 0; c->sc.tc_npasses = 1; c->smem_tc = 0;
   {
     const bool resident = (int)scene->n <= uecrt::tc_resident_max_spheres();
-    const uecrt::PackedSceneTc pt = uecrt::pack_scene_tc(*scene, (uint32_t)(resident ? uecrt::tc_chunk() : uecrt::tc_sweep_rows()));
+    const int slice_rows = resident ? uecrt::tc_chunk() : uecrt::tc_sweep_rows((int)scene->n);
+    const uecrt::PackedSceneTc pt = uecrt::pack_scene_tc(*scene, (uint32_t)slice_rows);
     if (pt.bytes.size() > c->cap_tc) {
       cudaFree(c->d_tc); c->d_tc = nullptr; c->cap_tc = 0;
       CUDA_TRY(cudaMalloc(&c->d_tc, pt.bytes.size()));
@@ -206,7 +207,7 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     CUDA_TRY(cudaMemcpy(c->d_tc, pt.bytes.data(), pt.bytes.size(), cudaMemcpyHostToDevice));
     c->sc.tc_rows = static_cast<const unsigned char*>(c->d_tc);
     c->sc.tc_nrows = (int)pt.rows;
-    c->sc.tc_npasses = resident ? 1 : (int)pt.rows / uecrt::tc_sweep_rows();
+    c->sc.tc_npasses = resident ? 1 : (int)pt.rows / slice_rows;
     c->smem_tc = uecrt::tc_smem_bytes((int)pt.rows, c->sc.tc_npasses);
   }
   c->h_geom.assign(scene->geom, scene->geom + scene->n);
