@@ -206,6 +206,25 @@ def test_swept_operand_hits_identical_to_fp32_scan(u, n, exact):
         assert np.array_equal(x, y)
 
 
+def test_swept_operand_at_the_scene_size_limit(u):
+    """65 534 spheres (the scene size limit): 128 slices of 512 rows, an 8 MB operand streamed from L2."""
+    n = u.tensor_scan_max_spheres()
+    sc = _random_scene(u, n, 77, span=40.0)
+    rng = np.random.default_rng(78)
+    o = rng.uniform(-45, 45, (3000, 3)).astype(np.float32)
+    d = rng.normal(size=(3000, 3)).astype(np.float32)
+    out = {}
+    for mode in ("fp32", "tensor"):
+        u.set_scan_mode(mode)
+        try:
+            out[mode] = u.primary_hits(sc, o, d, exact=True)
+        finally:
+            u.set_scan_mode("auto")
+    assert (out["fp32"][2] >= 0).sum() > 500 and out["fp32"][2].max() > n - n // 8
+    for x, y in zip(out["fp32"], out["tensor"]):
+        assert np.array_equal(x, y)
+
+
 def test_swept_operand_render_takes_the_same_paths(u, oracle):
     n = 3000
     sc, cam = u.Scene.named("dense", seed=1, n=n), u.Camera.named("dense")
