@@ -294,9 +294,10 @@ def main():
         peaks = measured_peaks()
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"]          # one ncu --set full capture, per launch
+                traffic_db = json.load(f)                                # one ncu --set full capture per kernel, per launch
         except Exception:
-            traffic = None
+            traffic_db = {}
+        traffic = None
         sm_max = peaks.get("sm_max_mhz", 1965.0)
         peak = 2 * 128 * st["sm_count"] * sm_max * 1e6 / 1e12
         rays_per_launch = rays / max(args.steps, 1) / max(world, 1)
@@ -308,6 +309,11 @@ def main():
                           "uniform grid (opt-in spatial index; NOT the brute-force 18 x N x rays figure)" if grid_scan else
                           "FP32 pipe (packed FFMA2 from shared memory)")
         kernel_name = "k_render_paths_tc" if tensor_scan else "k_render_paths_grid" if grid_scan else "k_render_paths"
+        # DRAM bytes per launch exist only for the (kernel, workload) pairs that were captured; null otherwise
+        if args.workload == "final":
+            traffic = (traffic_db if tensor_scan else traffic_db.get("fp32_scan", {}) if not grid_scan else {}).get("dram_bytes_per_launch")
+        elif args.workload == "dense" and swept:
+            traffic = traffic_db.get("swept_scan", {}).get("dram_bytes_per_launch")
         if grid_scan:       # executed tests, not N per ray
             achieved = FLOP_PER_TEST * (tests / max(args.steps, 1) / max(world, 1)) / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
         out = {"metric": "path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
