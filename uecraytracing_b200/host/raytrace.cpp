@@ -36,7 +36,7 @@ int main(int argc, char* argv[]) {
       .add(0, "scene-seed", "seed of the random scene generator (default 1)", true)
       .add(0, "dense-n", "sphere count of --scene dense (default 10000)", true)
       .add(0, "exact-hits", "resolve every closest hit in FP64", false)
-      .add(0, "scan", "closest-hit search: auto | fp32 | tensor | grid (default auto: brute force on the tensor cores when the scene fits; grid = opt-in spatial index)", true)
+      .add(0, "scan", "closest-hit search: auto | fp32 | tensor | grid (default auto: brute force on the tensor cores from 96 spheres up; grid = opt-in spatial index)", true)
       .add(0, "dump-accum", "also write the linear float image (.pfm) or the raw W*H*4 f32 accumulation buffer", true);
   options.positional("output");
   options.parse(argc, argv);

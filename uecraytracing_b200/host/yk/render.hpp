@@ -43,7 +43,7 @@ struct render_config {
   std::uint64_t seed = 0;
   int gpus = 1;
   bool exact_hits = false;
-  int scan = UECRT_SCAN_AUTO;           // candidate scan of K1: tensor cores when the scene fits, else the FP32 pipe
+  int scan = UECRT_SCAN_AUTO;           // candidate scan of K1: tensor cores from 96 spheres up, else the FP32 pipe
 };
 
 struct image_t {
