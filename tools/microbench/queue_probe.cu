@@ -3,6 +3,7 @@
 // issues one 128x128x32 TF32 tile (4 MMAs) every `period` cycles, paced by the clock (no barrier waits), with
 //   mode 0: nothing     1: the MMAs only     2: MMAs + tcgen05.commit after every tile     3: commit only (no MMAs)
 //   4: MMAs + commit, issued from warp 5 (sub-partition 1)
+// Periods below the 296 cycles the four MMAs take saturate the tensor pipe: the issuer then stalls in dispatch.
 // Output: cycles per 128-column slot for each scan warp.
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -74,7 +75,7 @@ int main() {
   cudaMalloc(&d_out, 4 * sizeof(long long)); cudaMalloc(&d_sink, 128 * 4); cudaMalloc(&d_flag, 4);
   const int iters = 4000;
   const char* names[5] = {"nothing", "MMAs only", "MMAs + commit per tile", "commit only", "MMAs + commit from sub-partition 1"};
-  for (int period : {700, 450})
+  for (int period : {700, 450, 320, 250, 100})
     for (int mode = 0; mode < 5; ++mode) {
       cudaMemset(d_out, 0, 4 * sizeof(long long)); cudaMemset(d_flag, 0, 4);
       k_probe<<<1, 256, 128 * 128>>>(iters, mode, period, d_out, d_sink, d_flag);      // one CTA: the flag is per CTA

@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
     tc::reg_dealloc<tc::kIssuerRegs>();
     const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - (tc::kShadeThreads + tc::kScanThreads) / 32;   // warp-uniform
     if (iw == UECRT_TC_ISSUER_WARP) {
-      if (tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, a.sc.tc_rows, -1, a.counters);
+      if (UECRT_TC_ISSUER_LANES != 1 || tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, a.sc.tc_rows, -1, a.counters);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
     tc::reg_dealloc<tc::kIssuerRegs>();
     const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - (tc::kShadeThreads + tc::kScanThreads) / 32;   // warp-uniform
     if (iw == UECRT_TC_ISSUER_WARP) {
-      if (tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, sc.tc_rows, batches);
+      if (UECRT_TC_ISSUER_LANES != 1 || tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, sc.tc_rows, batches);
     }
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();

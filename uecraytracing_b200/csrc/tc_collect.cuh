@@ -138,9 +138,17 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
 #endif
         const uint32_t t0 = lane_taddr + slot * kNC;
         int va[32], vb[32];
+#ifdef UECRT_TC_TRACE
+        const bool ph_ = prof_counters && blockIdx.x == 0 && lane == 0 && seq >= 3000u && seq < 3256u;
+        long long ph0_ = 0, ph1_ = 0, ph2_ = 0, ph3_ = 0, ph4_ = 0;
+        if (ph_) ph0_ = clock64();
+#endif
         tmem_ld32(t0, va);
         tmem_ld32(t0 + 32, vb);
         tmem_ld_wait();
+#ifdef UECRT_TC_TRACE
+        if (ph_) ph1_ = clock64();
+#endif
         uint32_t w0, w1, w2, w3;
         if (SWEEP) {
           // the two max reductions first (8 independent chains), then the warp votes, then the packing where needed
@@ -158,7 +166,13 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         }
         sts32(o, w0);
         sts32(o + kShadeThreads * 4u, w1);
+#ifdef UECRT_TC_TRACE
+        if (ph_) ph2_ = clock64();
+#endif
         tmem_ld_wait();
+#ifdef UECRT_TC_TRACE
+        if (ph_) ph3_ = clock64();
+#endif
         fence_before_sync();                              // the whole slot is in registers: hand it back
         if (lane == 0) mbar_arrive(empty0 + 8u * slot);
 #ifdef UECRT_TC_TRACE
@@ -176,6 +190,14 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         }
         sts32(o + 2u * kShadeThreads * 4u, w2);
         sts32(o + 3u * kShadeThreads * 4u, w3);
+#ifdef UECRT_TC_TRACE
+        if (ph_) {   // per scan warp: sums of the phase lengths over 256 chunks
+          ph4_ = clock64();
+          unsigned long long* p_ = prof_counters + 900 + 8 * (st >> 5);
+          atomicAdd(p_ + 0, (unsigned long long)(ph1_ - ph0_)); atomicAdd(p_ + 1, (unsigned long long)(ph2_ - ph1_));
+          atomicAdd(p_ + 2, (unsigned long long)(ph3_ - ph2_)); atomicAdd(p_ + 3, (unsigned long long)(ph4_ - ph3_)); atomicAdd(p_ + 4, 1ull);
+        }
+#endif
         const uint32_t nz = (w0 ? 8u : 0u) | (w1 ? 4u : 0u) | (w2 ? 2u : 0u) | (w3 ? 1u : 0u);
         sum |= nz << (28 - 4 * j);
 #ifdef UECRT_TC_TRACE

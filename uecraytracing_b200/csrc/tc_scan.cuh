@@ -386,6 +386,9 @@ struct PassIter {
   __device__ __forceinline__ void next(uint32_t npasses) { ++m; if (++pass == npasses) { pass = 0; ++round; } }
 };
 
+#ifndef UECRT_TC_ISSUER_LANES
+#define UECRT_TC_ISSUER_LANES 32    // 32: the whole warp runs the loop convergently and one elected lane issues (2.5 - 5 % faster than 1: one elected lane running the whole role in a diverged warp)
+#endif
 // ISSUER: one thread.  SWEEP: it also streams the operand: the slice of pass m+1 is requested during pass m
 // (behind its first tile) into buffer (m+1) & 1, once the MMAs of pass m-1 (the buffer's previous readers) have
 // completed (b_free, a tcgen05.commit behind that pass's last MMA); pass m starts when its slice has landed (b_full).
@@ -408,7 +411,8 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
   pin(full0); pin(empty0); pin(ready0);
   uint32_t load_pass = 0;                                   // the operand slice the next load fetches
   auto load_slice = [&](uint32_t m) {                       // into buffer m & 1, completing on b_full[m & 1]
-    bulk_load(b_smem0 + (m & 1u) * pass_bytes, b_global + (size_t)load_pass * pass_bytes, pass_bytes, bfull0 + 8u * (m & 1u));
+    if (UECRT_TC_ISSUER_LANES == 1 || elect_one())
+      bulk_load(b_smem0 + (m & 1u) * pass_bytes, b_global + (size_t)load_pass * pass_bytes, pass_bytes, bfull0 + 8u * (m & 1u));
     if (++load_pass == npasses) load_pass = 0;
   };
   if (!SWEEP) mbar_wait(smem_addr(&h->b_loaded), 0);
@@ -444,8 +448,11 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
         if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u)] = clock64();
 #endif
         fence_after_sync();
-        issue_tile_ts(tmem_base + slot * kNC, tmem_base + kATmemCol + g * (uint32_t)kSlots, b_smem + (uint32_t)j * (kNC * 128u), kNC);
-        mma_commit(full0 + 8u * slot);
+        if (UECRT_TC_ISSUER_LANES == 1 || elect_one()) {
+          issue_tile_ts(tmem_base + slot * kNC, tmem_base + kATmemCol + g * (uint32_t)kSlots, b_smem + (uint32_t)j * (kNC * 128u), kNC);
+          mma_commit(full0 + 8u * slot);
+        }
+        if (UECRT_TC_ISSUER_LANES != 1) __syncwarp();
 #ifdef UECRT_TC_TRACE
         if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + 1] = clock64();
 #endif
@@ -464,7 +471,7 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
         UECRT_TCI(p_bfull)
       }
     }
-    if (SWEEP) mma_commit(bfree0 + 8u * (m & 1u));
+    if (SWEEP && (UECRT_TC_ISSUER_LANES == 1 || elect_one())) mma_commit(bfree0 + 8u * (m & 1u));
   }
   if (SWEEP) {
     // loads were requested for passes 0 .. max(1, m_end); those never run: let them land before the CTA goes away

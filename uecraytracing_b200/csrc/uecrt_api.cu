@@ -459,6 +459,11 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
         const unsigned long long* e = q + 768 + 4 * i, t0 = q[128];
         fprintf(stderr, "[tc trace] %4d | %7lld %7lld | %7lld %7lld\n", 750 + i, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0), (long long)(e[3] - t0));
       }
+      for (int w = 0; w < 4; ++w) {
+        const unsigned long long* e = q + 900 + 8 * w;
+        if (e[4]) fprintf(stderr, "[tc trace] scan warp %d, mean cycles per chunk over %llu chunks: first two loads + wait %.0f | words 0, 1 (+ two more loads issued) %.0f | second wait %.0f | release + words 2, 3 %.0f\n",
+                          w, e[4], (double)e[0] / e[4], (double)e[1] / e[4], (double)e[2] / e[4], (double)e[3] / e[4]);
+      }
       fprintf(stderr, "[tc trace] CTA 0, chunk sequence numbers from 3000; cycles relative to the first event\n[tc trace]  seq | issuer: reaches the slot wait, slot free, MMAs+commit issued | scan warp 1: slot full, all loaded (slot released), packed | release by scan warp 0, 3\n");
       for (int i = 0; i < 40; ++i) {
         const unsigned long long* e = q + 128 + 8 * i, t0 = q[128];
