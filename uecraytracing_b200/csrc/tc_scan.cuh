@@ -222,10 +222,22 @@ __device__ __forceinline__ void store_row(unsigned char* base, uint32_t row, con
 }
 
 // issue D[128 x n] (+)= A[128 x 32] . B[n x 32]^T as four K=8 steps; A in TMEM columns [a_tmem, a_tmem + 32).  One thread.
+// The four descriptors differ only in the start-address field (+256 B = +16 units per step), so the low word is
+// built once and incremented: the issuer's instructions come out of the issue slots of the scan warp that
+// shares its SM sub-partition.
+__device__ __forceinline__ void mma_tf32_ts_desc(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem, uint32_t n) {
   const uint32_t idesc = make_idesc_tf32(128, n);
+  const uint64_t d0 = make_smem_desc(b_smem);
+  const uint32_t lo = (uint32_t)d0, hi = (uint32_t)(d0 >> 32);
 #pragma unroll
-  for (uint32_t s = 0; s < 4; ++s) mma_tf32_ts(d_tmem, a_tmem + s * 8u, make_smem_desc(b_smem + s * 256u), idesc, s);
+  for (uint32_t s = 0; s < 4; ++s) mma_tf32_ts_desc(d_tmem, a_tmem + s * 8u, lo + s * 16u, hi, idesc, s);
 }
 // ---------------------------------------------------------------------------------------
 // Warp-specialised pipeline of one CTA (kThreads = 768 threads = 6 warpgroups, 1 CTA per SM; launched
