@@ -241,26 +241,31 @@ __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, 
 }
 // ---------------------------------------------------------------------------------------
 // Warp-specialised pipeline of one CTA (kThreads = 768 threads = 6 warpgroups, 1 CTA per SM; launched
-// at 80 registers per thread, then setmaxnreg moves registers from the issuer warpgroup (-> 32) to
-// the scan warpgroup (-> 128), whose two 32-register TMEM loads in flight do not fit in 80):
+// at 80 registers per thread, then setmaxnreg redistributes the pool: shade 72, issuer warpgroup 24,
+// scan warpgroup 168 -- its two 32-register TMEM loads in flight plus the packing do not fit in 80):
 //   SHADE   4 groups x 128 threads (warps 0-15): each thread owns one path; per round it publishes
 //           its lifted ray as row t of the group's A tile (+ its threshold P), waits for the group's
-//           candidate lists, resolves the closest hit and shades.
-//   ISSUER  one elected lane of warp 20 (warps 21-23 only donate their registers): for round r = 0, 1, ... and group g = 0..3 IN THAT FIXED ORDER it waits
-//           for the group's A tile and issues the MMAs of every sphere chunk into a ring of kRing
+//           candidate bitmap, resolves the closest hit and shades.
+//   ISSUER  warp 20 (warps 21-23 only donate their registers).  The whole warp runs the loop and waits
+//           convergently, one elect.sync lane issues: for pass m = 0, 1, ... and group g = 0..3 IN THAT FIXED
+//           ORDER it waits for the group's A tile and issues the MMAs of every sphere chunk into a ring of kRing
 //           TMEM slots of kNC columns (3 x 128 columns; the other 128 columns hold the four A tiles).
+//           Swept operand: it also streams the next slice of the sphere operand (issuer_role).
 //   SCAN    warps 16-19 (warp 16+q owns TMEM lanes 32q..32q+31): consume the ring in the same fixed
 //           order; thread t reads the f values of ray row t of the current group with
-//           tcgen05.ld.32x32b.x32 (the four loads of a slot in flight) and packs the 32 sign bits of every load into
+//           tcgen05.ld.32x32b.x32 (two loads in flight) and packs the 32 sign bits of every load into
 //           one word of that ray's candidate BITMAP in shared memory (funnel shifts: no compare,
 //           no branch, no divergence; bit 31 of word w = sphere 32w).
-// Barriers (all mbarriers with deterministic phase parity):
-//   a_ready[g]   128 arrivals (shade threads of group g): the A tile of round r is stored
+// Barriers (all mbarriers with deterministic phase parity; a parity wait only tells adjacent phases apart,
+// so every barrier is waited on by a party that visits each of its phases in turn):
+//   a_ready[g]   128 arrivals (shade threads of group g): the A tile of the round is stored / the bitmap
+//                of the previous pass has been consumed
 //   tmem_full[s] 1 arrival (tcgen05.commit): the MMAs of the chunk in ring slot s are complete
 //   tmem_empty[s] 4 arrivals (scan warps): slot s has been read into registers
-//   scan_done[g] 128 arrivals (scan threads): the bitmaps of group g, round r are complete
-// Ring slots are numbered by a sequence number running across groups and rounds (slot = seq % kRing,
-// use = seq / kRing, parity = use & 1).
+//   scan_done[g] 128 arrivals (scan threads): the bitmaps of group g for this pass are complete
+//   b_full[i], b_free[i] (swept operand only): slice buffer i has landed / all MMAs reading it are complete
+// Ring slots are numbered by a sequence number running across groups and passes (slot = seq % kRing,
+// use = seq / kRing, parity = use & 1; both are kept incrementally in the loops).
 // Termination: every shade warp stores "all my paths are done" for round r into done_flags[r & 7]
 // before its a_ready arrive; EVERY role leaves at the first round r >= 2 for which all 16 flags of
 // round r-2 are set.  All roles are within two rounds of each other and the flags of round r-2
