@@ -73,8 +73,8 @@ enum {
   UECRT_FLAG_EXACT_HITS = 1u, /* resolve every closest hit in FP64 (reference-exact index) inside K1 */
   UECRT_FLAG_NO_COUNTERS = 2u, /* do not count rays/sphere tests (saves two atomics per CTA)         */
   UECRT_FLAG_SCAN_FP32 = 4u,   /* force the FP32-pipe candidate scan (packed FFMA2 from shared memory) */
-  UECRT_FLAG_SCAN_TENSOR = 8u, /* force the tensor-core candidate scan (tcgen05 TF32 x3, TMEM); fails
-                                  with UECRT_ERR_INVALID when the scene is too large for it           */
+  UECRT_FLAG_SCAN_TENSOR = 8u, /* force the tensor-core candidate scan (tcgen05 TF32 x3, TMEM), any
+                                  scene size: resident or swept sphere operand, see below             */
   UECRT_FLAG_SCAN_GRID = 16u   /* walk a uniform grid instead of scanning every sphere (opt-in spatial
                                   index: same closest hit, different algorithmic work)                */
 };
