@@ -97,6 +97,49 @@ __device__ __forceinline__ int max_of(const int (&v)[32]) {
 // word of v if `any` (warp-uniform: some lane of the warp has a candidate in it), else 0
 __device__ __forceinline__ uint32_t sign_word_if(bool any, const int (&v)[32]) { return any ? sign_word(v) : 0u; }
 
+// Hierarchical form of the same word.  Candidates are sparse AND the 32 rays of a warp are neighbours, so most
+// 8-sphere octets are empty for the whole warp (final scene: ~90 %): reduce every octet with full-rate
+// integer max (VIMNMX3; an accumulator read as a signed integer is >= 0 iff its sign bit is clear), let the warp
+// vote per word and then per octet, and run the half-rate funnel-shift packing only for octets in which some
+// lane has a candidate.  Same bits as sign_word in every case; WARP-CONVERGENT.
+__device__ __forceinline__ int max_of8(const int* v) {
+  return max(max(max(v[0], v[1]), v[2]), max(max(max(v[3], v[4]), v[5]), max(v[6], v[7])));
+}
+__device__ __forceinline__ uint32_t sign_word_oct(const int (&v)[32]) {
+  int o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = max_of8(&v[8 * k]);
+  if (!__any_sync(0xffffffffu, max(max(o[0], o[1]), max(o[2], o[3])) >= 0)) return 0u;
+  uint32_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t m = 0xffu;                                   // all sign bits set = no candidate
+    if (__any_sync(0xffffffffu, o[k] >= 0)) {
+      m = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m = __funnelshift_l((uint32_t)v[8 * k + i], m, 1);
+    }
+    c[k] = m;
+  }
+  const uint32_t hi = __byte_perm(c[1], c[0], 0x0040);
+  const uint32_t lo = __byte_perm(c[3], c[2], 0x0040);
+  return ~__byte_perm(lo, hi, 0x5410);
+}
+// how the scan warps turn 32 accumulators into a bitmap word: 0 = always pack (sign_word), 1 = skip words that are
+// empty for the whole warp, 2 = skip empty words and, inside the others, empty octets
+#ifndef UECRT_TC_PACK
+#define UECRT_TC_PACK 2
+#endif
+__device__ __forceinline__ uint32_t pack_word(const int (&v)[32]) {
+#if UECRT_TC_PACK == 0
+  return sign_word(v);
+#elif UECRT_TC_PACK == 1
+  return sign_word_if(__any_sync(0xffffffffu, max_of(v) >= 0), v);
+#else
+  return sign_word_oct(v);
+#endif
+}
+
 // SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
 template <bool SWEEP>
 __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses, int fixed_rounds,
@@ -150,20 +193,10 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         if (ph_) ph1_ = clock64();
 #endif
         uint32_t w0, w1, w2, w3;
-        if (SWEEP) {
-          // the two max reductions first (8 independent chains), then the warp votes, then the packing where needed
-          const int ma = max_of(va), mb = max_of(vb);
-          const bool any_a = __any_sync(0xffffffffu, ma >= 0), any_b = __any_sync(0xffffffffu, mb >= 0);
-          w0 = sign_word_if(any_a, va);
-          tmem_ld32(t0 + 64, va);
-          w1 = sign_word_if(any_b, vb);
-          tmem_ld32(t0 + 96, vb);
-        } else {
-          w0 = sign_word(va);
-          tmem_ld32(t0 + 64, va);
-          w1 = sign_word(vb);
-          tmem_ld32(t0 + 96, vb);
-        }
+        w0 = pack_word(va);
+        tmem_ld32(t0 + 64, va);
+        w1 = pack_word(vb);
+        tmem_ld32(t0 + 96, vb);
         sts32(o, w0);
         sts32(o + kShadeThreads * 4u, w1);
 #ifdef UECRT_TC_TRACE
@@ -179,15 +212,8 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 3] = clock64();
         if (prof_counters && blockIdx.x == 0 && (st == 0u || st == 96u) && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + (st == 0u ? 6 : 7)] = clock64();
 #endif
-        if (SWEEP) {
-          const int ma = max_of(va), mb = max_of(vb);
-          const bool any_a = __any_sync(0xffffffffu, ma >= 0), any_b = __any_sync(0xffffffffu, mb >= 0);
-          w2 = sign_word_if(any_a, va);
-          w3 = sign_word_if(any_b, vb);
-        } else {
-          w2 = sign_word(va);
-          w3 = sign_word(vb);
-        }
+        w2 = pack_word(va);
+        w3 = pack_word(vb);
         sts32(o + 2u * kShadeThreads * 4u, w2);
         sts32(o + 3u * kShadeThreads * 4u, w3);
 #ifdef UECRT_TC_TRACE
