@@ -600,6 +600,18 @@ struct TcProf {};
 // `m` is the pipeline's pass counter (tc_scan.cuh PassIter): one pass per round when the sphere operand is
 // resident; SWEEP: npasses passes of pass_rows spheres each, folded into one running closest hit in
 // ascending sphere index, so the later-index-wins tie rule holds across passes as it does inside one.
+// candidates of one flagged quad (tc_collect.cuh): the FP32 scan's packed discriminant test on its four spheres, then
+// the resolve test on the survivors in ascending index
+template <class Test>
+__device__ __forceinline__ void tc_quad(const DeviceScene& sc, int quad, const tc::QuadRay& qr, Test&& test) {
+  uint32_t cm = tc::quad_candidates(sc.tc_quads, quad, qr);
+  while (cm) {
+    const int j = __ffs((int)cm) - 1;
+    cm &= cm - 1u;
+    test(4 * quad + j);
+  }
+}
+
 template <bool EXACT, bool SWEEP, class InWindow>
 __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint32_t npasses, int pass_rows, const DeviceScene& sc,
                                                const RayQuery& q, Hit& h, TcProf& prof, InWindow&& in_window) {
@@ -609,22 +621,18 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
   UECRT_TCP(prof, 2)
   in_window();                                    // work that does not depend on this round's hit
   UECRT_TCP(prof, 1)
+  const tc::QuadRay qr = tc::make_quad_ray(sr);
+  const int pass_quads = pass_rows / tc::kQuad;
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+    for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
       tc::shade_wait(sh, m++);
-#ifdef UECRT_TC_TRACE
-      const uint32_t tile_ = 4u * (m - 1u) + threadIdx.x / 128u;
-      const bool trs_ = sh.trace && blockIdx.x == 0 && (threadIdx.x & 127u) == 0 && tile_ >= 750u && tile_ < 782u;
-      if (trs_) sh.trace[768 + 4 * (tile_ - 750u) + 2] = clock64();
-#endif
       UECRT_TCP(prof, 3)
-      tc::for_each_candidate(sh, q.live, [&](int j) { test_fast(sc.geom, (int)base + j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+      tc::for_each_quad(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
+        tc_quad(sc, (int)base + k, qr, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+      });
       if (!SWEEP || ++p == npasses) break;
       tc::shade_next_pass(sh);
-#ifdef UECRT_TC_TRACE
-      if (trs_) sh.trace[768 + 4 * (tile_ - 750u) + 3] = clock64();
-#endif
     }
     if (best.id >= 0) {
       h.id = best.id;
@@ -635,10 +643,12 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+    for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
       tc::shade_wait(sh, m++);
       UECRT_TCP(prof, 3)
-      tc::for_each_candidate(sh, q.live, [&](int j) { test_exact(sc.geom, (int)base + j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+      tc::for_each_quad(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
+        tc_quad(sc, (int)base + k, qr, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+      });
       if (!SWEEP || ++p == npasses) break;
       tc::shade_next_pass(sh);
     }
@@ -652,6 +662,127 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
       h.id = best.id; h.t = (float)best.t; h.front = front;
       h.px = (float)px; h.py = (float)py; h.pz = (float)pz;
       h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
+    }
+  }
+}
+
+// The collect half alone (resident operand): the ray was submitted one tile earlier, its quad flags are in bitmap buffer `buf`.
+template <bool EXACT>
+__device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, const DeviceScene& sc, const RayQuery& q, Hit& h) {
+  h.id = -1;
+  const tc::QuadRay qr = tc::make_quad_ray(make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz));
+  if (!EXACT) {
+    FastBest best{CUDART_INF_F, -1};
+    tc::for_each_quad(sh, buf, q.live, [&](int k) {
+      tc_quad(sc, k, qr, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+    });
+    if (best.id >= 0) {
+      h.id = best.id;
+      h.t = best.t;
+      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+    }
+  } else {
+    ExactBest best{(double)CUDART_INF, -1};
+    const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
+    const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
+    tc::for_each_quad(sh, buf, q.live, [&](int k) {
+      tc_quad(sc, k, qr, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+    });
+    if (best.id >= 0) {
+      const float4 g = __ldg(&sc.geom[best.id]);
+      const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
+      const double rad = g.w;
+      double nx = (px - (double)g.x) / rad, ny = (py - (double)g.y) / rad, nz = (pz - (double)g.z) / rad;   // sphere.hpp:44
+      const bool front = (Dx * nx + Dy * ny + Dz * nz) < 0;                                     // hittable.hpp:25
+      if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+      h.id = best.id; h.t = (float)best.t; h.front = front;
+      h.px = (float)px; h.py = (float)py; h.pz = (float)pz;
+      h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
+    }
+  }
+}
+
+// SHADE role of K1, resident operand: TWO independent paths per thread.  While the tile that carries path Q goes
+// through the MMA + scan pipeline, the thread resolves and shades path P from the bitmap of ITS last tile, so the
+// closed loop of four groups around one scanner always has a tile to scan (round 1: one path per thread, each
+// group waited 7.3 k of a 13.5 k-cycle round for its own tile).  Tile m of a group carries the group's P paths
+// for even m and its Q paths for odd m; its quad flags go to bitmap buffer m & 1.  Per tile m the thread
+//   waits for tile m's flags (so the tile's MMAs have completed and the group's A rows in TMEM are free),
+//   submits the OTHER path's ray as tile m + 1,
+//   then resolves and shades tile m's path, which leaves that path's next ray (or the next path's camera ray).
+template <bool EXACT>
+__device__ __forceinline__ void shade_role_resident(const RenderArgs& a, unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
+  tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
+  tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, 1u);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long n_pixels = a.n_slots;
+  const double inv_np = 1.0 / (double)n_pixels;
+  const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
+  unsigned n_rays = 0, n_paths = 0;
+  TcProf prof{};
+#ifdef UECRT_TC_PROFILE
+  unsigned long long pc_rounds = 0;
+  prof.last = clock64();
+#endif
+  WorkPool pool;
+  pool_init(pool, a, lane);
+  PathState P{}, Q{};                           // Q: in the pipeline; P: its next ray is ready
+  P.dz = 1.f; P.dlen = 1.f; P.self_id = -1;
+  Q = P;
+  slot_refill_pooled(Q, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+  slot_refill_pooled(P, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+  auto vote = [&](uint32_t tile) {              // termination vote (tc_scan.cuh): stored before this warp's a_ready arrive of `tile`
+    const bool warp_done = __all_sync(0xffffffffu, P.done && Q.done);
+    if (lane == 0) hdr->done_flags[tile & 7u][threadIdx.x >> 5] = warp_done ? 1 : 0;
+  };
+  auto submit = [&](const PathState& s) {
+    tc::shade_submit(sh, make_scan_ray(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz), s.active);
+  };
+  vote(0u);
+  submit(Q);                                    // tile 0
+  for (uint32_t m = 0; tc::round_continues(hdr, m, -1); ++m) {
+#ifdef UECRT_TC_PROFILE
+    const long long pc_start = prof.last;
+#endif
+    tc::shade_wait(sh, m);                      // tile m (path Q) is scanned
+    UECRT_TCP(prof, 3)
+    if (tc::round_continues(hdr, m + 1u, -1)) { // the flags of tile m - 1 are final: every role decides alike
+      vote(m + 1u);
+      submit(P);                                // tile m + 1
+    }
+    UECRT_TCP(prof, 2)
+    { const PathState t = P; P = Q; Q = t; }    // P: tile m's path, results pending; Q: in the pipeline
+    const RayQuery q{P.ox, P.oy, P.oz, P.dx, P.dy, P.dz, 0.001f * P.dlen, P.self_id, P.active};
+    Hit h;
+    tc_collect_hit<EXACT>(sh, m & 1u, a.sc, q, h);
+    UECRT_TCP(prof, 4)
+    if (P.active) {
+      ++n_rays;
+      slot_shade(P, h, a, n_paths);
+    }
+    UECRT_TCP(prof, 5)
+    slot_refill_pooled(P, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);   // a path that ended: the next one's camera ray
+    UECRT_TCP(prof, 1)
+#ifdef UECRT_TC_PROFILE
+    prof.t[6] += prof.last - pc_start;
+    ++pc_rounds;
+#endif
+  }
+#ifdef UECRT_TC_PROFILE
+  if (lane == 0) {
+    atomicAdd(a.counters + 4, pc_rounds);
+    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + 5 + i, (unsigned long long)prof.t[i]);
+    atomicAdd(a.counters + 16, sh.prof_trips);
+  }
+  atomicAdd(a.counters + 18, sh.prof_cands);
+#endif
+  if (a.count_stats) {
+    unsigned r = n_rays, p = n_paths;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+    if (lane == 0) {
+      atomicAdd(a.counters + 1, (unsigned long long)r);
+      atomicAdd(a.counters + 2, (unsigned long long)p);
     }
   }
 }
@@ -673,8 +804,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   } else if (threadIdx.x >= tc::kShadeThreads) {
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, -1, a.counters);
-  } else {
+  } else if (!SWEEP) {
     if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
+    else if (tc::kShadeRegs > tc::kLaunchRegs) tc::reg_alloc<tc::kShadeRegs>();
+    shade_role_resident<EXACT>(a, smem_raw, tmem_base, nchunks);
+  } else {
+    // swept operand: one path per thread; the thread serves every pass of its tile (tc_closest_hit)
+    if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
+    else if (tc::kShadeRegs > tc::kLaunchRegs) tc::reg_alloc<tc::kShadeRegs>();
     tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, SWEEP ? 2u : 1u);
 #ifdef UECRT_TC_TRACE
@@ -777,6 +914,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
     tc::scanner_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, batches);
   } else {
     if (tc::kShadeRegs < tc::kLaunchRegs) tc::reg_dealloc<tc::kShadeRegs>();
+    else if (tc::kShadeRegs > tc::kLaunchRegs) tc::reg_alloc<tc::kShadeRegs>();
     tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, SWEEP ? 2u : 1u);
     uint32_t pass_m = 0;
     for (int b = 0; b < batches; ++b) {
@@ -790,15 +928,19 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
       const float dx = rx * inv, dy = ry * inv, dz = rz * inv;
       const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
       tc::shade_submit(sh, sr, has_ray);
+      const tc::QuadRay qr = tc::make_quad_ray(sr);
+      const int pass_quads = pass_rows / tc::kQuad;
       double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
       int id = -1;
       bool front = false;
       if (!EXACT) {
         const float tmin_w = (float)tmin * dlen;
         FastBest best{(float)tmax * dlen, -1};
-        for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+        for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
           tc::shade_wait(sh, pass_m++);
-          tc::for_each_candidate(sh, has_ray, [&](int j) { test_fast(sc.geom, (int)base + j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+          tc::for_each_quad(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
+            tc_quad(sc, (int)base + k, qr, [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+          });
           if (!SWEEP || ++p == npasses) break;
           tc::shade_next_pass(sh);
         }
@@ -811,9 +953,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
         const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));  // sphere.hpp:28
         ExactBest best{tmax, -1};
-        for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_rows) {
+        for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
           tc::shade_wait(sh, pass_m++);
-          tc::for_each_candidate(sh, has_ray, [&](int j) { test_exact(sc.geom, (int)base + j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+          tc::for_each_quad(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
+            tc_quad(sc, (int)base + k, qr, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+          });
           if (!SWEEP || ++p == npasses) break;
           tc::shade_next_pass(sh);
         }
@@ -1116,7 +1260,7 @@ void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, 
 // ---- tensor-core scan variants
 int tc_resident_max_spheres() {
   const size_t fixed = tc::make_layout(0).total;
-  const int fit = (int)((232448 - fixed) / (128 + 64) / tc::kNC * tc::kNC);   // 128 B operand + 64 B bitmap per sphere row
+  const int fit = (int)((232448 - fixed) / (128 + 32) / tc::kNC * tc::kNC);   // 128 B operand + 2 x 16 B bitmap (one bit per quad and ray, two buffers) per sphere row
   return fit < tc::kMaxRows ? fit : tc::kMaxRows;
 }
 #ifndef UECRT_TC_SWEEP_ROWS

@@ -27,6 +27,7 @@ struct DeviceScene {
   const unsigned char* tc_rows;   // tensor-core scan operand (scene_pack.hpp pack_scene_tc), or null
   int tc_nrows;                   // rows (spheres padded to a multiple of tc::kNC, or of the pass size when swept)
   int tc_npasses;                 // 1: the operand is resident in shared memory; > 1: swept in that many equal slices
+  const float4* tc_quads;         // per 4 spheres {-cx[4]}, {-cy[4]}, {-cz[4]}, {nk[4]} (scene_pack.hpp pack_scene_quads), tc_nrows / 4 quads
   DeviceGrid grid;
 };
 

@@ -126,4 +126,23 @@ inline PackedSceneTc pack_scene_tc(const uecrt_scene& sc, uint32_t chunk) {
   return p;
 }
 
+// Quad table of the tensor scan's shade side (tc_collect.cuh quad_candidates): for spheres 4q .. 4q+3 four float4
+// {-cx[4]}, {-cy[4]}, {-cz[4]}, {nk[4]} with the FP32 scan's nk (same value, same bound as pack_scene above), so a flagged
+// quad is re-tested with exactly the FP32 scan's arithmetic.  Rows beyond n are never-hit (nk = -1e30).
+inline std::vector<float> pack_scene_quads(const uecrt_scene& sc, uint32_t rows) {
+  std::vector<float> q((size_t)rows * 4, 0.0f);
+  const double u = 5.9604644775390625e-8;   // 2^-24
+  for (uint32_t i = 0; i < rows; ++i) {
+    float* base = &q[(size_t)(i / 4) * 16 + (i & 3)];
+    base[12] = -1e30f;
+    if (i >= sc.n) continue;
+    const double cx = sc.geom[i].x, cy = sc.geom[i].y, cz = sc.geom[i].z, r = sc.geom[i].w;
+    const double c2 = cx * cx + cy * cy + cz * cz;
+    const double bound = 88.0 * u * c2 + 10.0 * u * r * r;
+    base[0] = -sc.geom[i].x; base[4] = -sc.geom[i].y; base[8] = -sc.geom[i].z;
+    base[12] = round_up_to_float(-(c2 - r * r) + bound);
+  }
+  return q;
+}
+
 }  // namespace uecrt

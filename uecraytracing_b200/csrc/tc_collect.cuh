@@ -1,8 +1,21 @@
-// tc_collect.cuh -- the SCAN role and the shade-side hand-off of the tensor-core scan.  The scan
-// leaves one candidate BITMAP per ray (bit set = the sphere's discriminant may be >= 0); the shade
-// thread walks the set bits in ascending sphere index and applies the same per-candidate test as
-// the FP32 scan's resolve phase (closest_hit.cuh test_fast / test_exact: reference root selection,
-// closed interval, later index wins -- hittable_list.hpp:32-58, sphere.hpp:32-39).
+// tc_collect.cuh -- the SCAN role and the shade-side hand-off of the tensor-core scan.
+//
+// The MMAs leave G = f - P for every (ray, sphere) pair in TMEM (tc_scan.cuh); a sphere may be hit iff the
+// sign bit of its word is clear.  Turning 128 x 512 accumulators per tile into something a shade thread can
+// walk is what paces the whole kernel: it is integer work on the ALU pipe, where shifts and logic ops issue
+// at HALF rate and only integer min/max at full rate (profiles/iops_r1.log).  Round 1 packed one bit per
+// sphere (one funnel shift per accumulator: 2.3 k cycles per tile on the one scan warp of a sub-partition,
+// twice what the tile's MMAs take).  Now the scan warps reduce every QUAD of spheres with 3-input integer max
+// (an accumulator read as a signed integer is >= 0 iff its sign bit is clear, so the max of four is >= 0 iff
+// one of them may be hit: 2 full-rate instructions per quad) and pack one bit per quad (one half-rate
+// shift): half the pipe cycles and 3/4 of the issue slots per accumulator, still branch-free straight-line code.
+// (Skipping words or octets that are empty for all 32 rays of a warp costs a vote + branch each and made the
+// single-warp scan stream latency-bound: 19.9 / 26.1 ms against 18.7, profiles/README.md.)
+// The shade thread walks the set bits in ascending order; for a flagged quad it re-evaluates the four
+// discriminants with the FP32 scan's packed form and bound (closest_hit.cuh: 7 packed FP32 instructions per two
+// spheres on the otherwise idle FMA pipe; {f >= P} is again a superset of the reference's "discriminant >= 0")
+// and applies the per-candidate test of the resolve phase (test_fast / test_exact: reference root selection,
+// closed interval, later index wins -- hittable_list.hpp:32-58, sphere.hpp:32-39) to the survivors, in index order.
 #pragma once
 #include "closest_hit.cuh"
 #include "tc_scan.cuh"
@@ -32,25 +45,18 @@ __device__ __forceinline__ void shade_wait(const Shade& s, uint32_t m) { mbar_wa
 // write it again behind MMAs the issuer launches after this barrier's phase completes)
 __device__ __forceinline__ void shade_next_pass(const Shade& s) { mbar_arrive(s.a_ready); }
 
-// SHADE: f(sphere index) for every candidate of this thread's ray, ascending index.  WARP-CONVERGENT:
-// all 32 lanes must call it (a lane without a live ray passes live = false).  Every trip of the
-// loop hands one candidate to every lane that still has one (a lane whose current bitmap word is
-// exhausted jumps to its next non-empty word through the summary word), so the warp makes
-// max-over-lanes(candidates) trips and f runs once per trip with the lanes converged.
+// SHADE: f(quad index within the pass) for every flagged quad of this thread's ray, ascending.  WARP-CONVERGENT:
+// all 32 lanes must call it (a lane without a live ray passes live = false).  Every trip of the loop hands
+// one quad to every lane that still has one (a lane whose current word is exhausted moves on to its next
+// non-empty chunk word), so the warp makes max-over-lanes(flagged quads) trips and f runs once per trip with
+// the lanes converged.
 template <class F>
-__device__ __forceinline__ void for_each_candidate(Shade& s, bool live, F&& f) {
-  uint32_t sum = 0u, m = 0u;
-  if (live) {
-#pragma unroll
-    for (int sg = 0; sg < kScanGroups; ++sg) sum |= s.summary[sg * kShadeThreads];
-  }
-  int w = 0;
+__device__ __forceinline__ void for_each_quad(Shade& s, uint32_t buf, bool live, F&& f) {
+  uint32_t m = 0u;
+  int c = live ? -1 : s.nchunks;
+  const uint32_t* bm = s.bitmap + buf * (uint32_t)(s.nchunks * kShadeThreads);
   for (;;) {
-    if (m == 0u && sum != 0u) {
-      w = __clz((int)sum);
-      sum &= ~(0x80000000u >> w);
-      m = s.bitmap[w * kShadeThreads];
-    }
+    while (m == 0u && c + 1 < s.nchunks) { ++c; m = bm[c * kShadeThreads]; }
     if (!__any_sync(0xffffffffu, m != 0u)) return;
 #ifdef UECRT_TC_PROFILE
     ++s.prof_trips;
@@ -59,85 +65,51 @@ __device__ __forceinline__ void for_each_candidate(Shade& s, bool live, F&& f) {
     if (m != 0u) {
       const int b = __clz((int)m);
       m &= ~(0x80000000u >> b);
-      f(w * 32 + b);
+      f(c * (kNC / kQuad) + b);
     }
   }
 }
 
-// 32 accumulators -> one bitmap word: bit (31 - i) = (v[i] >= 0).  Four independent funnel-shift
-// chains (mask = (mask << 1) | sign(v)), merged with byte permutes.
-__device__ __forceinline__ uint32_t sign_word(const int (&v)[32]) {
-  uint32_t c[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m = __funnelshift_l((uint32_t)v[8 * k + i], m, 1);
-    c[k] = m;
-  }
-  const uint32_t hi = __byte_perm(c[1], c[0], 0x0040);   // low 16 bits = (c0 << 8) | c1
-  const uint32_t lo = __byte_perm(c[3], c[2], 0x0040);   // low 16 bits = (c2 << 8) | c3
-  return ~__byte_perm(lo, hi, 0x5410);                   // a set sign bit = NOT a candidate
+// Per-ray constants of the quad re-test (the FP32 scan's packed operands, closest_hit.cuh scan_pairs)
+struct QuadRay {
+  unsigned long long dx2, dy2, dz2, qx2, qy2, qz2;
+  int thr;
+};
+__device__ __forceinline__ QuadRay make_quad_ray(const ScanRay& r) {
+  QuadRay q;
+  q.dx2 = pk2(r.dx, r.dx); q.dy2 = pk2(r.dy, r.dy); q.dz2 = pk2(r.dz, r.dz);
+  q.qx2 = pk2(r.nqx, r.nqx); q.qy2 = pk2(r.nqy, r.nqy); q.qz2 = pk2(r.nqz, r.nqz);
+  q.thr = r.thr;
+  return q;
+}
+// quads: per quad four float4 {-cx[4]}, {-cy[4]}, {-cz[4]}, {nk[4]} (scene_pack.hpp pack_scene_quads; nk carries the
+// FP32 scan's bound).  Returns a 4-bit mask: bit j = sphere 4*quad + j passes f >= P.
+__device__ __forceinline__ uint32_t quad_candidates(const float4* __restrict__ quads, int quad, const QuadRay& r) {
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(quads) + 4 * (size_t)quad;
+  const ulonglong2 X = __ldg(q), Y = __ldg(q + 1), Z = __ldg(q + 2), K = __ldg(q + 3);
+  unsigned long long cd0 = mul2(X.x, r.dx2), cd1 = mul2(X.y, r.dx2);
+  unsigned long long e0 = fma2(X.x, r.qx2, K.x), e1 = fma2(X.y, r.qx2, K.y);
+  cd0 = fma2(Y.x, r.dy2, cd0); cd1 = fma2(Y.y, r.dy2, cd1);
+  e0 = fma2(Y.x, r.qy2, e0); e1 = fma2(Y.y, r.qy2, e1);
+  cd0 = fma2(Z.x, r.dz2, cd0); cd1 = fma2(Z.y, r.dz2, cd1);
+  e0 = fma2(Z.x, r.qz2, e0); e1 = fma2(Z.y, r.qz2, e1);
+  const unsigned long long g0 = fma2(cd0, cd0, e0), g1 = fma2(cd1, cd1, e1);
+  int f0, f1, f2, f3;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(f0), "=r"(f1) : "l"(g0));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(f2), "=r"(f3) : "l"(g1));
+  return (f0 >= r.thr ? 1u : 0u) | (f1 >= r.thr ? 2u : 0u) | (f2 >= r.thr ? 4u : 0u) | (f3 >= r.thr ? 8u : 0u);
 }
 
-// When the scene is large and candidates are sparse (swept operand), most 32-sphere words are empty for ALL 32
-// rays of a warp (dense 10 k scene: ~80 %): first reduce the 32 accumulators with integer max (full issue
-// rate; an accumulator read as a signed integer is >= 0 iff its sign bit is clear) and pack only if some lane
-// of the warp has a candidate in this word.  Same bits as sign_word in every case.
-__device__ __forceinline__ int max_of(const int (&v)[32]) {
-  int m[4];
+// 32 accumulators -> 8 quad flags in the low byte: bit (7 - k) SET = every accumulator of quad k is negative
+// (no candidate).  One funnel-shift chain (mask = (mask << 1) | sign(max of the quad)).
+__device__ __forceinline__ uint32_t quad_signs(const int (&v)[32]) {
+  uint32_t m = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    m[k] = v[8 * k];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m[k] = max(m[k], v[8 * k + i]);
+  for (int k = 0; k < 8; ++k) {
+    const int q = max(max(max(v[4 * k], v[4 * k + 1]), v[4 * k + 2]), v[4 * k + 3]);
+    m = __funnelshift_l((uint32_t)q, m, 1);
   }
-  return max(max(m[0], m[1]), max(m[2], m[3]));
-}
-// word of v if `any` (warp-uniform: some lane of the warp has a candidate in it), else 0
-__device__ __forceinline__ uint32_t sign_word_if(bool any, const int (&v)[32]) { return any ? sign_word(v) : 0u; }
-
-// Hierarchical form of the same word.  Candidates are sparse AND the 32 rays of a warp are neighbours, so most
-// 8-sphere octets are empty for the whole warp (final scene: ~90 %): reduce every octet with full-rate
-// integer max (VIMNMX3; an accumulator read as a signed integer is >= 0 iff its sign bit is clear), let the warp
-// vote per word and then per octet, and run the half-rate funnel-shift packing only for octets in which some
-// lane has a candidate.  Same bits as sign_word in every case; WARP-CONVERGENT.
-__device__ __forceinline__ int max_of8(const int* v) {
-  return max(max(max(v[0], v[1]), v[2]), max(max(max(v[3], v[4]), v[5]), max(v[6], v[7])));
-}
-__device__ __forceinline__ uint32_t sign_word_oct(const int (&v)[32]) {
-  int o[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) o[k] = max_of8(&v[8 * k]);
-  if (!__any_sync(0xffffffffu, max(max(o[0], o[1]), max(o[2], o[3])) >= 0)) return 0u;
-  uint32_t c[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t m = 0xffu;                                   // all sign bits set = no candidate
-    if (__any_sync(0xffffffffu, o[k] >= 0)) {
-      m = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m = __funnelshift_l((uint32_t)v[8 * k + i], m, 1);
-    }
-    c[k] = m;
-  }
-  const uint32_t hi = __byte_perm(c[1], c[0], 0x0040);
-  const uint32_t lo = __byte_perm(c[3], c[2], 0x0040);
-  return ~__byte_perm(lo, hi, 0x5410);
-}
-// how the scan warps turn 32 accumulators into a bitmap word: 0 = always pack (sign_word), 1 = skip words that are
-// empty for the whole warp, 2 = skip empty words and, inside the others, empty octets
-#ifndef UECRT_TC_PACK
-#define UECRT_TC_PACK 2
-#endif
-__device__ __forceinline__ uint32_t pack_word(const int (&v)[32]) {
-#if UECRT_TC_PACK == 0
-  return sign_word(v);
-#elif UECRT_TC_PACK == 1
-  return sign_word_if(__any_sync(0xffffffffu, max_of(v) >= 0), v);
-#else
-  return sign_word_oct(v);
-#endif
+  return m;
 }
 
 // SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
@@ -156,16 +128,15 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
   const uint32_t st = threadIdx.x - kShadeThreads, sg = st >> 7, row = st & 127u, lane = row & 31u;
   uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
   uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), done0 = smem_addr(&h->scan_done[0]);
-  // this ray's bitmap word 0 of group 0 / its summary word, as shared addresses (word w of group g: + (w * kShadeThreads + g * 128) * 4)
+  // this ray's bitmap word of chunk 0, group 0, as a shared address (chunk c of group g: + (c * kShadeThreads + g * 128) * 4)
   uint32_t bitmap0 = smem_addr(smem_raw + lay.bitmap) + row * 4u;
-  uint32_t summary0 = smem_addr(smem_raw + lay.summary) + (sg * kShadeThreads + row) * 4u;
-  pin(lane_taddr); pin(full0); pin(empty0); pin(done0); pin(bitmap0); pin(summary0);
+  pin(lane_taddr); pin(full0); pin(empty0); pin(done0); pin(bitmap0);
   uint32_t seq = 0, slot = 0, parity = 0;                     // slot = seq % kRing, parity = (seq / kRing) & 1, kept incrementally
   for (PassIter it; it.begin(h, fixed_rounds); it.next(npasses)) {
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
-      uint32_t o = bitmap0 + g * (kGroupThreads * 4u);        // word w of this ray at o + w * kShadeThreads * 4
-      uint32_t sum = 0;                                       // bit (31 - w): word w is non-zero
-      for (int j = 0; j < nchunks; ++j, ++seq, o += (kNC / 32) * kShadeThreads * 4u, slot = slot == kRing - 1 ? 0u : slot + 1u, parity ^= (slot == 0u ? 1u : 0u)) {
+      // word of chunk c of this ray at o + c * kShadeThreads * 4; resident operand: tile m of a group goes to bitmap buffer m & 1
+      uint32_t o = bitmap0 + g * (kGroupThreads * 4u) + (SWEEP ? 0u : (it.m & 1u) * lay.bitmap_buf_bytes);
+      for (int j = 0; j < nchunks; ++j, ++seq, o += kShadeThreads * 4u, slot = slot == kRing - 1 ? 0u : slot + 1u, parity ^= (slot == 0u ? 1u : 0u)) {
         if (kScanGroups > 1 && (uint32_t)(j % kScanGroups) != sg) continue;      // another warpgroup's chunk
         const uint32_t use = parity;
 #ifdef UECRT_TC_PROFILE
@@ -176,62 +147,35 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
         fence_after_sync();
         UECRT_TCS(pw)
 #ifdef UECRT_TC_TRACE
-        const bool tr_ = prof_counters && blockIdx.x == 0 && st == 32u && seq >= 3000u && seq < 3064u;
-        if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 2] = clock64();
+        const bool trs_ = prof_counters && blockIdx.x == 0 && lane == 0 && seq >= 3000u && seq < 3048u;
+        unsigned long long* tre_ = prof_counters + 128 + 20 * (seq - 3000u) + 4 + 4 * (st >> 5);
+        if (trs_) tre_[0] = clock64();
 #endif
         const uint32_t t0 = lane_taddr + slot * kNC;
         int va[32], vb[32];
-#ifdef UECRT_TC_TRACE
-        const bool ph_ = prof_counters && blockIdx.x == 0 && lane == 0 && seq >= 3000u && seq < 3256u;
-        long long ph0_ = 0, ph1_ = 0, ph2_ = 0, ph3_ = 0, ph4_ = 0;
-        if (ph_) ph0_ = clock64();
-#endif
         tmem_ld32(t0, va);
         tmem_ld32(t0 + 32, vb);
         tmem_ld_wait();
-#ifdef UECRT_TC_TRACE
-        if (ph_) ph1_ = clock64();
-#endif
-        uint32_t w0, w1, w2, w3;
-        w0 = pack_word(va);
+        const uint32_t c0 = quad_signs(va);
         tmem_ld32(t0 + 64, va);
-        w1 = pack_word(vb);
+        const uint32_t c1 = quad_signs(vb);
         tmem_ld32(t0 + 96, vb);
-        sts32(o, w0);
-        sts32(o + kShadeThreads * 4u, w1);
-#ifdef UECRT_TC_TRACE
-        if (ph_) ph2_ = clock64();
-#endif
         tmem_ld_wait();
-#ifdef UECRT_TC_TRACE
-        if (ph_) ph3_ = clock64();
-#endif
         fence_before_sync();                              // the whole slot is in registers: hand it back
         if (lane == 0) mbar_arrive(empty0 + 8u * slot);
 #ifdef UECRT_TC_TRACE
-        if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 3] = clock64();
-        if (prof_counters && blockIdx.x == 0 && (st == 0u || st == 96u) && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + (st == 0u ? 6 : 7)] = clock64();
+        if (trs_) tre_[1] = clock64();
 #endif
-        w2 = pack_word(va);
-        w3 = pack_word(vb);
-        sts32(o + 2u * kShadeThreads * 4u, w2);
-        sts32(o + 3u * kShadeThreads * 4u, w3);
+        const uint32_t c2 = quad_signs(va);
+        const uint32_t c3 = quad_signs(vb);
+        const uint32_t hi = __byte_perm(c1, c0, 0x0040);   // low 16 bits = (c0 << 8) | c1
+        const uint32_t lo = __byte_perm(c3, c2, 0x0040);   // low 16 bits = (c2 << 8) | c3
+        sts32(o, ~__byte_perm(lo, hi, 0x5410));            // a set sign bit = NOT a candidate; bit 31 = quad 0 of the chunk
 #ifdef UECRT_TC_TRACE
-        if (ph_) {   // per scan warp: sums of the phase lengths over 256 chunks
-          ph4_ = clock64();
-          unsigned long long* p_ = prof_counters + 900 + 8 * (st >> 5);
-          atomicAdd(p_ + 0, (unsigned long long)(ph1_ - ph0_)); atomicAdd(p_ + 1, (unsigned long long)(ph2_ - ph1_));
-          atomicAdd(p_ + 2, (unsigned long long)(ph3_ - ph2_)); atomicAdd(p_ + 3, (unsigned long long)(ph4_ - ph3_)); atomicAdd(p_ + 4, 1ull);
-        }
-#endif
-        const uint32_t nz = (w0 ? 8u : 0u) | (w1 ? 4u : 0u) | (w2 ? 2u : 0u) | (w3 ? 1u : 0u);
-        sum |= nz << (28 - 4 * j);
-#ifdef UECRT_TC_TRACE
-        if (tr_) prof_counters[128 + 8 * (seq - 3000u) + 4] = clock64();
+        if (trs_) tre_[2] = clock64();
 #endif
         UECRT_TCS(pl)
       }
-      sts32(summary0 + g * (kGroupThreads * 4u), sum);
       mbar_arrive(done0 + 8u * g);
 #ifdef UECRT_TC_PROFILE
       ++ptiles;

@@ -278,7 +278,7 @@ __device__ __forceinline__ void issue_tile_ts(uint32_t d_tmem, uint32_t a_tmem, 
 #define UECRT_TC_SCAN_WGS 1        // scan warpgroups; 2: they split the chunks of every tile by parity
 #endif
 #ifndef UECRT_TC_SHADE_REGS
-#define UECRT_TC_SHADE_REGS 72
+#define UECRT_TC_SHADE_REGS 88
 #endif
 constexpr int kGroups = UECRT_TC_GROUPS;
 constexpr int kGroupThreads = 128;
@@ -295,7 +295,8 @@ constexpr int kNC = 128;                                     // spheres (TMEM co
 constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kATmemCol = kRing * kNC;                  // A tile of group g: TMEM columns [384 + 32g, 384 + 32g + 32)
-constexpr int kMaxRows = 1024;                               // one 32-bit summary word per ray: at most 32 bitmap words of 32 spheres
+constexpr int kQuad = 4;                                     // spheres per candidate-bitmap bit (tc_collect.cuh)
+constexpr int kMaxRows = 1536;                               // resident operand: 128 B + 16 B of bitmap per sphere row must fit in shared memory
 constexpr uint32_t kHeaderBytes = 1024;
 
 struct Header {               // first kHeaderBytes of dynamic shared memory
@@ -311,20 +312,22 @@ struct Header {               // first kHeaderBytes of dynamic shared memory
   uint8_t done_flags[8][16];  // [round & 7][shade warp] (kShadeThreads / 32 of the 16 are used)
 };
 
-// smem layout: [Header][B: nbuf x rows * 128 B][summary: 512 words][bitmap: rows/32 words x 512 rays]
+// smem layout: [Header][B: nbuf x rows * 128 B][bitmap: rows/128 words x 512 rays]
 // (nbuf = 1: the whole sphere operand is resident; nbuf = 2: it is swept through two buffers of `rows` rows, see issuer_role)
-// bitmap word w of ray i lives at bitmap[w * 512 + i] (the 32 lanes of a warp touch consecutive words);
-// summary[sg * kShadeThreads + i] has bit (31 - w) set iff bitmap word w of ray i is non-zero (sg = the scan
-// warpgroup that packed word w; the shade thread ORs the warpgroups' words).
+// One bitmap word per ray and 128-sphere chunk: bit (31 - k) = some sphere of QUAD k of the chunk (spheres 4k .. 4k+3)
+// may be hit.  Word c of ray i lives at bitmap[c * 512 + i]: the 32 lanes of a warp touch 32 different banks
+// whatever chunk each of them is at.
+// Resident operand: TWO bitmap buffers (tile m of a group goes to buffer m & 1): a shade thread walks the bitmap of
+// one of its two paths while the scan warps write the other's (kernels.cu, k_render_paths_tc).  Swept operand: one.
 struct Layout {
-  uint32_t b, summary, bitmap, total;
+  uint32_t b, bitmap, bitmap_buf_bytes, total;
 };
 __host__ __device__ inline Layout make_layout(uint32_t b_rows, uint32_t nbuf = 1u) {
   Layout l;
   l.b = kHeaderBytes;
-  l.summary = l.b + nbuf * b_rows * 128u;
-  l.bitmap = l.summary + (uint32_t)kScanGroups * kShadeThreads * 4u;
-  l.total = l.bitmap + (b_rows / 32u) * (uint32_t)kShadeThreads * 4u;
+  l.bitmap = l.b + nbuf * b_rows * 128u;
+  l.bitmap_buf_bytes = (b_rows / (uint32_t)kNC) * (uint32_t)kShadeThreads * 4u;
+  l.total = l.bitmap + (nbuf == 1u ? 2u : 1u) * l.bitmap_buf_bytes;
   return l;
 }
 
@@ -446,23 +449,17 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
     const uint32_t b_smem = b_smem0 + (SWEEP ? (m & 1u) * pass_bytes : 0u);
     for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
       UECRT_TCI(p_issue)
-#ifdef UECRT_TC_TRACE
-      const bool trt_ = prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u;
-      if (trt_) prof_counters[768 + 4 * (seq / 4u - 750u)] = clock64();
-#endif
       mbar_wait(ready0 + 8u * g, m & 1u);
-#ifdef UECRT_TC_TRACE
-      if (trt_) prof_counters[768 + 4 * (seq / 4u - 750u) + 1] = clock64();
-#endif
       UECRT_TCI(p_ready)
       for (int j = 0; j < nchunks; ++j, ++seq, slot = slot == kRing - 1 ? 0u : slot + 1u, parity ^= (slot == 0u ? 1u : 0u)) {
 #ifdef UECRT_TC_TRACE
-        if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + 5] = clock64();
+        const bool tri_ = prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3048u;
+        if (tri_) prof_counters[128 + 20 * (seq - 3000u)] = clock64();
 #endif
         if (seq >= (uint32_t)kRing) mbar_wait(empty0 + 8u * slot, parity);  // the scanners have read the previous contents
         UECRT_TCI(p_empty)
 #ifdef UECRT_TC_TRACE
-        if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u)] = clock64();
+        if (tri_) prof_counters[128 + 20 * (seq - 3000u) + 1] = clock64();
 #endif
         fence_after_sync();
         if (UECRT_TC_ISSUER_LANES == 1 || elect_one()) {
@@ -471,7 +468,7 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
         }
         if (UECRT_TC_ISSUER_LANES != 1) __syncwarp();
 #ifdef UECRT_TC_TRACE
-        if (prof_counters && blockIdx.x == 0 && seq >= 3000u && seq < 3064u) prof_counters[128 + 8 * (seq - 3000u) + 1] = clock64();
+        if (tri_) prof_counters[128 + 20 * (seq - 3000u) + 2] = clock64();
 #endif
         UECRT_TCI(p_issue)
       }
@@ -511,8 +508,8 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
 struct Shade {
   uint32_t a_ready, scan_done;       // shared addresses of the group's barriers
   uint32_t a_taddr;                  // TMEM address of this thread's A row: its warp's lane quarter | the group's A columns
-  const uint32_t* summary;           // this ray's summary word
-  const uint32_t* bitmap;            // this ray's candidate bitmap: word w at bitmap[w * kShadeThreads]
+  const uint32_t* bitmap;            // this ray's candidate bitmap (buffer 0): the word of chunk c at bitmap[c * kShadeThreads]
+  int nchunks;                       // words per pass; bitmap buffer 1 starts nchunks * kShadeThreads words further
 #ifdef UECRT_TC_PROFILE
   unsigned long long prof_trips = 0, prof_steps = 0, prof_cands = 0;
 #endif
@@ -527,8 +524,8 @@ __device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tm
   Shade s;
   s.a_ready = smem_addr(&h->a_ready[g]); s.scan_done = smem_addr(&h->scan_done[g]);
   s.a_taddr = tmem_base + kATmemCol + g * (uint32_t)kSlots + (((threadIdx.x >> 5) & 3u) * 32u << 16);
-  s.summary = reinterpret_cast<const uint32_t*>(smem_raw + lay.summary) + threadIdx.x;
   s.bitmap = reinterpret_cast<const uint32_t*>(smem_raw + lay.bitmap) + threadIdx.x;
+  s.nchunks = nchunks;
   return s;
 }
 #endif  // __CUDACC__

@@ -128,6 +128,8 @@ struct uecrt_ctx {
   // tensor-core scan (tc_scan.cuh): available when the scene fits its residency limit
   void* d_tc = nullptr;
   size_t cap_tc = 0;
+  void* d_quads = nullptr;
+  size_t cap_quads = 0;
   size_t smem_tc = 0;
   int regs_tc = 0;
   // uniform grid (grid_build.hpp): built and uploaded on first use of UECRT_SCAN_GRID with the current scene
@@ -148,7 +150,7 @@ std::atomic<int> g_scan_mode{UECRT_SCAN_AUTO};
 #define UECRT_AUTO_SCAN UECRT_SCAN_TENSOR   // what UECRT_SCAN_AUTO resolves to when the scene fits the tensor scan
 #endif
 std::atomic<int> g_rays_per_thread{UECRT_DEFAULT_RAYS};   // paths per K1 thread sharing one scene scan (1 or 2)
-constexpr int kCounterWords = 1024;      // [0,64): statistics and profile sums; [128, 128 + 5*128): UECRT_TC_TRACE timeline
+constexpr int kCounterWords = 2048;      // [0,64): statistics and profile sums; [128, 128 + 5*128): UECRT_TC_TRACE timeline
 #ifndef UECRT_AUTO_SWEEP
 #define UECRT_AUTO_SWEEP 1
 #endif
@@ -194,7 +196,7 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
   }
   // tensor-core scan operand (128 B per sphere): resident in shared memory when the scene fits, else padded to
   // whole slices of tc_sweep_rows(n) rows that the kernel sweeps through two shared-memory buffers
-  c->sc.tc_rows = nullptr; c->sc.tc_nrows = 0; c->sc.tc_npasses = 1; c->smem_tc = 0;
+  c->sc.tc_rows = nullptr; c->sc.tc_quads = nullptr; c->sc.tc_nrows = 0; c->sc.tc_npasses = 1; c->smem_tc = 0;
   {
     const bool resident = (int)scene->n <= uecrt::tc_resident_max_spheres();
     const int slice_rows = resident ? uecrt::tc_chunk() : uecrt::tc_sweep_rows((int)scene->n);
@@ -205,6 +207,14 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
       c->cap_tc = pt.bytes.size();
     }
     CUDA_TRY(cudaMemcpy(c->d_tc, pt.bytes.data(), pt.bytes.size(), cudaMemcpyHostToDevice));
+    const std::vector<float> quads = uecrt::pack_scene_quads(*scene, pt.rows);
+    if (quads.size() * sizeof(float) > c->cap_quads) {
+      cudaFree(c->d_quads); c->d_quads = nullptr; c->cap_quads = 0;
+      CUDA_TRY(cudaMalloc(&c->d_quads, quads.size() * sizeof(float)));
+      c->cap_quads = quads.size() * sizeof(float);
+    }
+    CUDA_TRY(cudaMemcpy(c->d_quads, quads.data(), quads.size() * sizeof(float), cudaMemcpyHostToDevice));
+    c->sc.tc_quads = static_cast<const float4*>(c->d_quads);
     c->sc.tc_rows = static_cast<const unsigned char*>(c->d_tc);
     c->sc.tc_nrows = (int)pt.rows;
     c->sc.tc_npasses = resident ? 1 : (int)pt.rows / slice_rows;
@@ -230,7 +240,7 @@ void ctx_free(uecrt_ctx* c) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
-  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc);
+  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc); cudaFree(c->d_quads);
   cudaFree(c->d_cell_start); cudaFree(c->d_items); cudaFree(c->d_always);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -450,25 +460,18 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
   out->rays_traced = h[1]; out->paths = h[2];
   out->sphere_tests = ctx->last_scan_mode == UECRT_SCAN_GRID ? h[3] : h[1] * (unsigned long long)ctx->n;
 #ifdef UECRT_TC_TRACE
-  {   // timeline of one CTA's issuer and one scan warp (debugging builds only)
+  {   // timeline of one CTA's issuer and its four scan warps over 48 consecutive chunks (debugging builds only)
     static unsigned long long q[kCounterWords];
     CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
     if (q[128]) {
-      fprintf(stderr, "[tc trace] tiles from 750 (tile = 4 x pass + group): issuer waits a_ready from, until | shade warp 0 of the group: scan_done seen, bitmap consumed + re-armed (that is the a_ready of tile + 4)\n");
-      for (int i = 0; i < 24; ++i) {
-        const unsigned long long* e = q + 768 + 4 * i, t0 = q[128];
-        fprintf(stderr, "[tc trace] %4d | %7lld %7lld | %7lld %7lld\n", 750 + i, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0), (long long)(e[3] - t0));
-      }
-      for (int w = 0; w < 4; ++w) {
-        const unsigned long long* e = q + 900 + 8 * w;
-        if (e[4]) fprintf(stderr, "[tc trace] scan warp %d, mean cycles per chunk over %llu chunks: first two loads + wait %.0f | words 0, 1 (+ two more loads issued) %.0f | second wait %.0f | release + words 2, 3 %.0f\n",
-                          w, e[4], (double)e[0] / e[4], (double)e[1] / e[4], (double)e[2] / e[4], (double)e[3] / e[4]);
-      }
-      fprintf(stderr, "[tc trace] CTA 0, chunk sequence numbers from 3000; cycles relative to the first event\n[tc trace]  seq | issuer: reaches the slot wait, slot free, MMAs+commit issued | scan warp 1: slot full, all loaded (slot released), packed | release by scan warp 0, 3\n");
-      for (int i = 0; i < 40; ++i) {
-        const unsigned long long* e = q + 128 + 8 * i, t0 = q[128];
-        fprintf(stderr, "[tc trace] %4d | %7lld %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld\n", 3000 + i, (long long)(e[5] - t0), (long long)(e[0] - t0), (long long)(e[1] - t0),
-                (long long)(e[2] - t0), (long long)(e[3] - t0), (long long)(e[4] - t0), (long long)(e[6] - t0), (long long)(e[7] - t0));
+      const unsigned long long t0 = q[128];
+      fprintf(stderr, "[tc trace] CTA 0, chunk sequence numbers from 3000; cycles relative to the first event\n"
+                      "[tc trace]  seq | issuer: reaches the slot wait, slot free, MMAs+commit issued | scan warp 0..3: slot full seen, slot released, packed\n");
+      for (int i = 0; i < 48; ++i) {
+        const unsigned long long* e = q + 128 + 20 * i;
+        fprintf(stderr, "[tc trace] %4d | %6lld %6lld %6lld |", 3000 + i, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0));
+        for (int w = 0; w < 4; ++w) fprintf(stderr, " %6lld %6lld %6lld |", (long long)(e[4 + 4 * w] - t0), (long long)(e[5 + 4 * w] - t0), (long long)(e[6 + 4 * w] - t0));
+        fprintf(stderr, "\n");
       }
     }
   }
