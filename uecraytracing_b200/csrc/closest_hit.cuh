@@ -111,9 +111,8 @@ struct FastBest { float t; int id; };
 // "later index wins"; ORDERED = false (grid walk: arbitrary order, a sphere may come twice): the same rule
 // spelled out, t < best or (t == best and j > best.id).
 template <bool ORDERED = true>
-__device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j, float ox, float oy, float oz, float dx,
-                                          float dy, float dz, float tmin, int self_id, FastBest& best) {
-  const float4 g = __ldg(&geom[j]);
+__device__ __forceinline__ void test_fast_g(const float4 g, int j, float ox, float oy, float oz, float dx,
+                                            float dy, float dz, float tmin, int self_id, FastBest& best) {
   const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
   const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
   float t;
@@ -135,6 +134,11 @@ __device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j
   }
   if (ORDERED ? (t <= best.t) : (t < best.t || (t == best.t && j > best.id))) { best.t = t; best.id = j; }   // closed interval: later index wins ties
 }
+template <bool ORDERED = true>
+__device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j, float ox, float oy, float oz, float dx,
+                                          float dy, float dz, float tmin, int self_id, FastBest& best) {
+  test_fast_g<ORDERED>(__ldg(&geom[j]), j, ox, oy, oz, dx, dy, dz, tmin, self_id, best);
+}
 
 template <int STRIDE>
 __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, const CandList<STRIDE>& L, int cnt,
@@ -149,9 +153,8 @@ __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, co
 struct ExactBest { double t; int id; };
 
 template <bool ORDERED = true>
-__device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int j, double ox, double oy, double oz, double dx,
-                                           double dy, double dz, double a, double tmin, ExactBest& best) {
-  const float4 g = __ldg(&geom[j]);
+__device__ __forceinline__ void test_exact_g(const float4 g, int j, double ox, double oy, double oz, double dx,
+                                             double dy, double dz, double a, double tmin, ExactBest& best) {
   const double cx = g.x, cy = g.y, cz = g.z, r = g.w;
   const double ocx = __dsub_rn(ox, cx), ocy = __dsub_rn(oy, cy), ocz = __dsub_rn(oz, cz);     // sphere.hpp:27
   const double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));  // :29
@@ -168,6 +171,11 @@ __device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int 
   if (!ORDERED && root == best.t && j <= best.id) return;   // unordered candidates: an equal root only wins with a LATER index
   best.t = root;                                                                                // hittable_list.hpp:40-41
   best.id = j;
+}
+template <bool ORDERED = true>
+__device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int j, double ox, double oy, double oz, double dx,
+                                           double dy, double dz, double a, double tmin, ExactBest& best) {
+  test_exact_g<ORDERED>(__ldg(&geom[j]), j, ox, oy, oz, dx, dy, dz, a, tmin, best);
 }
 
 template <int STRIDE>
@@ -289,9 +297,8 @@ struct Hit {
 
 // sphere.hpp:41-45 + hittable.hpp:23-27 for the winning sphere, normal taken from the
 // centre-relative vector (never from the rounded world-space hit point).
-__device__ __forceinline__ void finish_hit_fast(const float4* __restrict__ geom, float ox, float oy, float oz,
-                                                float dx, float dy, float dz, Hit& h) {
-  const float4 g = __ldg(&geom[h.id]);
+__device__ __forceinline__ void finish_hit_fast_g(const float4 g, float ox, float oy, float oz,
+                                                  float dx, float dy, float dz, Hit& h) {
   const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
   const float inv_r = __fdividef(1.0f, g.w);
   h.px = fmaf(h.t, dx, ox); h.py = fmaf(h.t, dy, oy); h.pz = fmaf(h.t, dz, oz);
@@ -301,6 +308,10 @@ __device__ __forceinline__ void finish_hit_fast(const float4* __restrict__ geom,
   nx *= s; ny *= s; nz *= s;
   h.front = fmaf(dz, nz, fmaf(dy, ny, dx * nx)) < 0.0f;
   h.nx = h.front ? nx : -nx; h.ny = h.front ? ny : -ny; h.nz = h.front ? nz : -nz;
+}
+__device__ __forceinline__ void finish_hit_fast(const float4* __restrict__ geom, float ox, float oy, float oz,
+                                                float dx, float dy, float dz, Hit& h) {
+  finish_hit_fast_g(__ldg(&geom[h.id]), ox, oy, oz, dx, dy, dz, h);
 }
 
 }  // namespace uecrt

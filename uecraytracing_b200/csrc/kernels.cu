@@ -667,29 +667,39 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
 }
 
 // The collect half alone (resident operand): the ray was submitted one tile earlier, its quad flags are in bitmap buffer `buf`.
+// s_quads / s_geom: shared addresses of the CTA's copies of the quad table and the sphere array (tc_scan.cuh Layout).
+template <class Test>
+__device__ __forceinline__ void tc_quad_s(uint32_t s_quads, int quad, const tc::QuadRay& qr, Test&& test) {
+  uint32_t cm = tc::quad_candidates_s(s_quads, quad, qr);
+  while (cm) {
+    const int j = __ffs((int)cm) - 1;
+    cm &= cm - 1u;
+    test(4 * quad + j);
+  }
+}
 template <bool EXACT>
-__device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, const DeviceScene& sc, const RayQuery& q, Hit& h) {
+__device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint32_t s_quads, uint32_t s_geom, const RayQuery& q, Hit& h) {
   h.id = -1;
   const tc::QuadRay qr = tc::make_quad_ray(make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz));
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
     tc::for_each_quad(sh, buf, q.live, [&](int k) {
-      tc_quad(sc, k, qr, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+      tc_quad_s(s_quads, k, qr, [&](int j) { test_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
     });
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
-      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+      finish_hit_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)best.id), q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
     }
   } else {
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
     tc::for_each_quad(sh, buf, q.live, [&](int k) {
-      tc_quad(sc, k, qr, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+      tc_quad_s(s_quads, k, qr, [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
     });
     if (best.id >= 0) {
-      const float4 g = __ldg(&sc.geom[best.id]);
+      const float4 g = tc::lds_f4(s_geom + 16u * (uint32_t)best.id);
       const double px = Ox + Dx * best.t, py = Oy + Dy * best.t, pz = Oz + Dz * best.t;   // ray.hpp:16-19
       const double rad = g.w;
       double nx = (px - (double)g.x) / rad, ny = (py - (double)g.y) / rad, nz = (pz - (double)g.z) / rad;   // sphere.hpp:44
@@ -714,6 +724,8 @@ template <bool EXACT>
 __device__ __forceinline__ void shade_role_resident(const RenderArgs& a, unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
   tc::Header* hdr = reinterpret_cast<tc::Header*>(smem_raw);
   tc::Shade sh = tc::make_shade(smem_raw, tmem_base, nchunks, 1u);
+  const tc::Layout lay = tc::make_layout((uint32_t)nchunks * tc::kNC, 1u);
+  const uint32_t s_quads = tc::smem_addr(smem_raw + lay.quads), s_geom = tc::smem_addr(smem_raw + lay.geom);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long n_pixels = a.n_slots;
   const double inv_np = 1.0 / (double)n_pixels;
@@ -754,7 +766,7 @@ __device__ __forceinline__ void shade_role_resident(const RenderArgs& a, unsigne
     { const PathState t = P; P = Q; Q = t; }    // P: tile m's path, results pending; Q: in the pipeline
     const RayQuery q{P.ox, P.oy, P.oz, P.dx, P.dy, P.dz, 0.001f * P.dlen, P.self_id, P.active};
     Hit h;
-    tc_collect_hit<EXACT>(sh, m & 1u, a.sc, q, h);
+    tc_collect_hit<EXACT>(sh, m & 1u, s_quads, s_geom, q, h);
     UECRT_TCP(prof, 4)
     if (P.active) {
       ++n_rays;
@@ -793,15 +805,25 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   const uint32_t npasses = SWEEP ? (uint32_t)a.sc.tc_npasses : 1u;
   const int pass_rows = a.sc.tc_nrows / (int)npasses;
   const int nchunks = pass_rows / tc::kNC;
-  const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, SWEEP ? 0u : (uint32_t)a.sc.tc_nrows * 128u);
+  const uint32_t tmem_base = tc::cta_setup(smem_raw, a.sc.tc_rows, SWEEP ? 0u : (uint32_t)a.sc.tc_nrows * 128u, (uint32_t)nchunks);
+  if (!SWEEP) {   // the shade side's tables: quad table and spheres (rows beyond n: never-hit quads, zero spheres)
+    const tc::Layout lay = tc::make_layout((uint32_t)a.sc.tc_nrows, 1u);
+    float4* sq = reinterpret_cast<float4*>(smem_raw + lay.quads);
+    float4* sg = reinterpret_cast<float4*>(smem_raw + lay.geom);
+    for (int i = threadIdx.x; i < a.sc.tc_nrows; i += tc::kThreads) {
+      sq[i] = __ldg(&a.sc.tc_quads[i]);
+      sg[i] = i < a.sc.n ? __ldg(&a.sc.geom[i]) : make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+    __syncthreads();
+  }
   const unsigned lane = threadIdx.x & 31u;
-  if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
+  if (tc::is_issuer_thread()) {
     tc::reg_dealloc<tc::kIssuerRegs>();
-    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - (tc::kShadeThreads + tc::kScanThreads) / 32;   // warp-uniform
+    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - tc::kIssuerFirstThread / 32;   // warp-uniform
     if (iw == UECRT_TC_ISSUER_WARP) {
       if (UECRT_TC_ISSUER_LANES != 1 || tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, a.sc.tc_rows, -1, a.counters);
     }
-  } else if (threadIdx.x >= tc::kShadeThreads) {
+  } else if (tc::is_scan_thread()) {
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, -1, a.counters);
   } else if (!SWEEP) {
@@ -900,16 +922,16 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
   const uint32_t npasses = SWEEP ? (uint32_t)sc.tc_npasses : 1u;
   const int pass_rows = sc.tc_nrows / (int)npasses;
   const int nchunks = pass_rows / tc::kNC;
-  const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, SWEEP ? 0u : (uint32_t)sc.tc_nrows * 128u);
+  const uint32_t tmem_base = tc::cta_setup(smem_raw, sc.tc_rows, SWEEP ? 0u : (uint32_t)sc.tc_nrows * 128u, (uint32_t)nchunks);
   const unsigned long long stride = (unsigned long long)gridDim.x * tc::kShadeThreads;
   const int batches = (int)((n_rays + stride - 1) / stride);
-  if (threadIdx.x >= tc::kShadeThreads + tc::kScanThreads) {
+  if (tc::is_issuer_thread()) {
     tc::reg_dealloc<tc::kIssuerRegs>();
-    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - (tc::kShadeThreads + tc::kScanThreads) / 32;   // warp-uniform
+    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - tc::kIssuerFirstThread / 32;   // warp-uniform
     if (iw == UECRT_TC_ISSUER_WARP) {
       if (UECRT_TC_ISSUER_LANES != 1 || tc::elect_one()) tc::issuer_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, sc.tc_rows, batches);
     }
-  } else if (threadIdx.x >= tc::kShadeThreads) {
+  } else if (tc::is_scan_thread()) {
     tc::reg_alloc<tc::kScanRegs>();
     tc::scanner_role<SWEEP>(smem_raw, tmem_base, nchunks, npasses, batches);
   } else {
@@ -1260,7 +1282,7 @@ void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, 
 // ---- tensor-core scan variants
 int tc_resident_max_spheres() {
   const size_t fixed = tc::make_layout(0).total;
-  const int fit = (int)((232448 - fixed) / (128 + 32) / tc::kNC * tc::kNC);   // 128 B operand + 2 x 16 B bitmap (one bit per quad and ray, two buffers) per sphere row
+  const int fit = (int)((232448 - fixed) / (128 + 32 + 32) / tc::kNC * tc::kNC);   // per sphere row: 128 B operand, 2 x 16 B bitmap (one bit per quad and ray, two buffers), 16 B quad table, 16 B sphere
   return fit < tc::kMaxRows ? fit : tc::kMaxRows;
 }
 #ifndef UECRT_TC_SWEEP_ROWS

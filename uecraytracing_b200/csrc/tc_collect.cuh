@@ -27,6 +27,7 @@ namespace tc {
 // A tile (warp-collective store).  A thread without a live ray passes live = false: its row is still
 // written (every row of the tile takes part in the MMA) with P = +1e30, so all its accumulators
 // come out negative and its bitmap is empty.
+__device__ __forceinline__ void shade_next_pass(const Shade& s);
 __device__ __forceinline__ void shade_submit(const Shade& s, const ScanRay& ray, bool live) {
   const float a[kTerms] = {ray.dx * ray.dx, ray.dy * ray.dy, ray.dz * ray.dz, 2.0f * ray.dx * ray.dy, 2.0f * ray.dx * ray.dz,
                            2.0f * ray.dy * ray.dz, ray.nqx, ray.nqy, ray.nqz, 1.0f};
@@ -36,14 +37,21 @@ __device__ __forceinline__ void shade_submit(const Shade& s, const ScanRay& ray,
   tmem_st32(s.a_taddr, row);
   tmem_st_wait();
   fence_before_sync();
-  mbar_arrive(s.a_ready);
+  shade_next_pass(s);
 }
 // SHADE: wait for the bitmaps of pass m (tc_scan.cuh PassIter: m = the round when the operand is resident)
-__device__ __forceinline__ void shade_wait(const Shade& s, uint32_t m) { mbar_wait(s.scan_done, m & 1u); }
+__device__ __forceinline__ void shade_wait(const Shade& s, uint32_t m) {
+  if (UECRT_TC_NAMED_BARRIERS) nbar_sync(s.scan_done, kBarScanDoneCount);
+  else mbar_wait(s.scan_done, m & 1u);
+}
 // SHADE, swept operand: this thread has consumed its bitmap of the current pass; the ray tile in TMEM stays
 // as it is and takes part in the next pass (the arrive releases the bitmap to the scan warps: they only
 // write it again behind MMAs the issuer launches after this barrier's phase completes)
-__device__ __forceinline__ void shade_next_pass(const Shade& s) { mbar_arrive(s.a_ready); }
+__device__ __forceinline__ void shade_next_pass(const Shade& s) {
+  if (UECRT_TC_NAMED_BARRIERS) { nbar_arrive(s.a_ready, kBarAReadyCount); return; }
+  __syncwarp();
+  if ((threadIdx.x & 31u) == 0u) mbar_arrive(s.a_ready);    // one arrival per warp (the barrier counts warps)
+}
 
 // SHADE: f(quad index within the pass) for every flagged quad of this thread's ray, ascending.  WARP-CONVERGENT:
 // all 32 lanes must call it (a lane without a live ray passes live = false).  Every trip of the loop hands
@@ -84,9 +92,7 @@ __device__ __forceinline__ QuadRay make_quad_ray(const ScanRay& r) {
 }
 // quads: per quad four float4 {-cx[4]}, {-cy[4]}, {-cz[4]}, {nk[4]} (scene_pack.hpp pack_scene_quads; nk carries the
 // FP32 scan's bound).  Returns a 4-bit mask: bit j = sphere 4*quad + j passes f >= P.
-__device__ __forceinline__ uint32_t quad_candidates(const float4* __restrict__ quads, int quad, const QuadRay& r) {
-  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(quads) + 4 * (size_t)quad;
-  const ulonglong2 X = __ldg(q), Y = __ldg(q + 1), Z = __ldg(q + 2), K = __ldg(q + 3);
+__device__ __forceinline__ uint32_t quad_candidates_v(const ulonglong2 X, const ulonglong2 Y, const ulonglong2 Z, const ulonglong2 K, const QuadRay& r) {
   unsigned long long cd0 = mul2(X.x, r.dx2), cd1 = mul2(X.y, r.dx2);
   unsigned long long e0 = fma2(X.x, r.qx2, K.x), e1 = fma2(X.y, r.qx2, K.y);
   cd0 = fma2(Y.x, r.dy2, cd0); cd1 = fma2(Y.y, r.dy2, cd1);
@@ -99,25 +105,76 @@ __device__ __forceinline__ uint32_t quad_candidates(const float4* __restrict__ q
   asm("mov.b64 {%0, %1}, %2;" : "=r"(f2), "=r"(f3) : "l"(g1));
   return (f0 >= r.thr ? 1u : 0u) | (f1 >= r.thr ? 2u : 0u) | (f2 >= r.thr ? 4u : 0u) | (f3 >= r.thr ? 8u : 0u);
 }
-
-// 32 accumulators -> 8 quad flags in the low byte: bit (7 - k) SET = every accumulator of quad k is negative
-// (no candidate).  One funnel-shift chain (mask = (mask << 1) | sign(max of the quad)).
-__device__ __forceinline__ uint32_t quad_signs(const int (&v)[32]) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int q = max(max(max(v[4 * k], v[4 * k + 1]), v[4 * k + 2]), v[4 * k + 3]);
-    m = __funnelshift_l((uint32_t)q, m, 1);
-  }
-  return m;
+__device__ __forceinline__ uint32_t quad_candidates(const float4* __restrict__ quads, int quad, const QuadRay& r) {
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(quads) + 4 * (size_t)quad;
+  return quad_candidates_v(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), r);
+}
+// the same tables in shared memory (resident operand): 16-byte loads from a shared address
+__device__ __forceinline__ ulonglong2 lds_u64x2(uint32_t saddr) {
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t quad_candidates_s(uint32_t s_quads, int quad, const QuadRay& r) {
+  const uint32_t q = s_quads + 64u * (uint32_t)quad;
+  return quad_candidates_v(lds_u64x2(q), lds_u64x2(q + 16u), lds_u64x2(q + 32u), lds_u64x2(q + 48u), r);
 }
 
-// SCAN: one thread of the scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + 128)).
+// the max of every quad of 32 accumulators (8 values, full-rate VIMNMX3 + VIMNMX each)
+__device__ __forceinline__ void quad_max(const int (&v)[32], int (&q)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) q[k] = max(max(max(v[4 * k], v[4 * k + 1]), v[4 * k + 2]), v[4 * k + 3]);
+}
+// 8 quad maxima -> 8 flags in the low byte: bit (7 - k) SET = every accumulator of quad k is negative (no candidate).
+// Two funnel-shift chains (mask = (mask << 1) | sign) of four, merged by one shift-add.
+__device__ __forceinline__ uint32_t quad_signs(const int (&q)[8]) {
+  uint32_t a = 0, b = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    a = __funnelshift_l((uint32_t)q[k], a, 1);
+    b = __funnelshift_l((uint32_t)q[4 + k], b, 1);
+  }
+  return a * 16u + b;
+}
+
+// Position in the issuer's chunk sequence: passes (PassIter), groups, chunks; slot = seq % kRing and the parity of the
+// slot's current use, kept incrementally.
+struct ChunkPos {
+  PassIter it;
+  uint32_t g = 0, slot = 0, parity = 0;
+  int j = 0;
+  // one chunk further; false when the sequence ends (the termination vote is read at a round's first tile)
+  __device__ __forceinline__ bool next(const Header* h, int fixed_rounds, uint32_t npasses, int nchunks) {
+    slot = slot == kRing - 1 ? 0u : slot + 1u;
+    parity ^= (slot == 0u ? 1u : 0u);
+    if (++j < nchunks) return true;
+    j = 0;
+    if (++g < (uint32_t)kGroups) return true;
+    g = 0;
+    it.next(npasses);
+    return it.begin(h, fixed_rounds);
+  }
+};
+
+// SCAN: one thread of a scan warpgroup (threadIdx.x in [kShadeThreads, kShadeThreads + kScanThreads)).
+// A tcgen05.ld round trip is ~150 cycles (tools/microbench/ldtm_probe.cu) and tcgen05.wait::ld waits for ALL of a
+// thread's loads, so the loop is software-pipelined over the chunk sequence: the quad maxima of a 32-column load
+// free its registers at once, the next load goes into them while the shifts of the previous one run, and the
+// first half of the warp's NEXT chunk is requested (after a non-blocking look at its tmem_full barrier) before this
+// chunk's second half is packed.  Chunks are consumed in the issuer's order; with kScanGroups warpgroups, warpgroup
+// sg takes the chunks whose sequence number is sg modulo kScanGroups, so every SM sub-partition has kScanGroups scan
+// warps whose load round trips, barrier checks and dependent chains overlap.
 template <bool SWEEP>
 __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses, int fixed_rounds,
                                              unsigned long long* prof_counters = nullptr) {
+  static_assert(kScanGroups == 1, "the named-barrier hand-off counts one scan warpgroup");
 #ifdef UECRT_TC_PROFILE
-  long long pw = 0, pl = 0, ps = 0, plast = clock64();
+  long long pw = 0, pl = 0, plast = clock64();
   unsigned long long ptiles = 0, p_ready_now = 0, p_blocked = 0;
 #define UECRT_TCS(acc) { const long long now_ = clock64(); acc += now_ - plast; plast = now_; }
 #else
@@ -125,70 +182,97 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
 #endif
   Header* h = reinterpret_cast<Header*>(smem_raw);
   const Layout lay = make_layout((uint32_t)nchunks * kNC, SWEEP ? 2u : 1u);
-  const uint32_t st = threadIdx.x - kShadeThreads, sg = st >> 7, row = st & 127u, lane = row & 31u;
+  const uint32_t st = threadIdx.x - (uint32_t)kScanFirstThread, sg = st >> 7, row = st & 127u;
+  uint32_t is_lane0 = (row & 31u) == 0u ? 1u : 0u;
   uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
   uint32_t full0 = smem_addr(&h->tmem_full[0]), empty0 = smem_addr(&h->tmem_empty[0]), done0 = smem_addr(&h->scan_done[0]);
-  // this ray's bitmap word of chunk 0, group 0, as a shared address (chunk c of group g: + (c * kShadeThreads + g * 128) * 4)
+  // this ray's bitmap word of chunk 0, group 0, buffer 0, as a shared address (chunk c of group g: + (c * kShadeThreads + g * 128) * 4)
   uint32_t bitmap0 = smem_addr(smem_raw + lay.bitmap) + row * 4u;
-  pin(lane_taddr); pin(full0); pin(empty0); pin(done0); pin(bitmap0);
-  uint32_t seq = 0, slot = 0, parity = 0;                     // slot = seq % kRing, parity = (seq / kRing) & 1, kept incrementally
-  for (PassIter it; it.begin(h, fixed_rounds); it.next(npasses)) {
-    for (uint32_t g = 0; g < (uint32_t)kGroups; ++g) {
-      // word of chunk c of this ray at o + c * kShadeThreads * 4; resident operand: tile m of a group goes to bitmap buffer m & 1
-      uint32_t o = bitmap0 + g * (kGroupThreads * 4u) + (SWEEP ? 0u : (it.m & 1u) * lay.bitmap_buf_bytes);
-      for (int j = 0; j < nchunks; ++j, ++seq, o += kShadeThreads * 4u, slot = slot == kRing - 1 ? 0u : slot + 1u, parity ^= (slot == 0u ? 1u : 0u)) {
-        if (kScanGroups > 1 && (uint32_t)(j % kScanGroups) != sg) continue;      // another warpgroup's chunk
-        const uint32_t use = parity;
-#ifdef UECRT_TC_PROFILE
-        if (mbar_test(full0 + 8u * slot, use & 1u)) { ++p_ready_now; } else { const long long b0_ = clock64(); mbar_wait(full0 + 8u * slot, use & 1u); ++p_blocked; if (prof_counters && lane == 0 && j < 4) { atomicAdd(prof_counters + 26 + j, 1ull); if (j == 0) { atomicAdd(prof_counters + 42 + g, 1ull); atomicAdd(prof_counters + 46 + g, (unsigned long long)(clock64() - b0_)); } } }
-#else
-        mbar_wait(full0 + 8u * slot, use & 1u);
-#endif
-        fence_after_sync();
-        UECRT_TCS(pw)
+  pin(lane_taddr); pin(full0); pin(empty0); pin(done0); pin(bitmap0); pin(is_lane0);
+  ChunkPos pos;
+  if (!pos.it.begin(h, fixed_rounds)) return;
+  for (uint32_t k = 0; k < sg; ++k)
+    if (!pos.next(h, fixed_rounds, npasses, nchunks)) return;
 #ifdef UECRT_TC_TRACE
-        const bool trs_ = prof_counters && blockIdx.x == 0 && lane == 0 && seq >= 3000u && seq < 3048u;
-        unsigned long long* tre_ = prof_counters + 128 + 20 * (seq - 3000u) + 4 + 4 * (st >> 5);
-        if (trs_) tre_[0] = clock64();
+  uint32_t seq = sg;
 #endif
-        const uint32_t t0 = lane_taddr + slot * kNC;
-        int va[32], vb[32];
-        tmem_ld32(t0, va);
-        tmem_ld32(t0 + 32, vb);
-        tmem_ld_wait();
-        const uint32_t c0 = quad_signs(va);
-        tmem_ld32(t0 + 64, va);
-        const uint32_t c1 = quad_signs(vb);
-        tmem_ld32(t0 + 96, vb);
-        tmem_ld_wait();
-        fence_before_sync();                              // the whole slot is in registers: hand it back
-        if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+  int va[32], vb[32];
+  mbar_wait(full0 + 8u * pos.slot, pos.parity);
+  fence_after_sync();
+  tmem_ld32(lane_taddr + pos.slot * kNC, va);
+  tmem_ld32(lane_taddr + pos.slot * kNC + 32, vb);
+  UECRT_TCS(pw)
+  for (;;) {
 #ifdef UECRT_TC_TRACE
-        if (trs_) tre_[1] = clock64();
+    const bool trs_ = prof_counters && blockIdx.x == 0 && is_lane0 && seq >= 3000u && seq < 3048u;
+    unsigned long long* tre_ = prof_counters + 128 + 20 * (seq - 3000u) + 4 + 4 * ((st >> 5) & 3u);
+    if (trs_) tre_[0] = clock64();
 #endif
-        const uint32_t c2 = quad_signs(va);
-        const uint32_t c3 = quad_signs(vb);
-        const uint32_t hi = __byte_perm(c1, c0, 0x0040);   // low 16 bits = (c0 << 8) | c1
-        const uint32_t lo = __byte_perm(c3, c2, 0x0040);   // low 16 bits = (c2 << 8) | c3
-        sts32(o, ~__byte_perm(lo, hi, 0x5410));            // a set sign bit = NOT a candidate; bit 31 = quad 0 of the chunk
+    const uint32_t t0 = lane_taddr + pos.slot * kNC;
+    int qa[8], qb[8];
+    tmem_ld_wait();
+    quad_max(va, qa);
+    tmem_ld32(t0 + 64, va);
+    quad_max(vb, qb);
+    tmem_ld32(t0 + 96, vb);
+    const uint32_t c0 = quad_signs(qa), c1 = quad_signs(qb);
+    // this warp's next chunk
+    ChunkPos np = pos;
+    bool more = true;
+#pragma unroll
+    for (int k = 0; k < kScanGroups; ++k) more = more && np.next(h, fixed_rounds, npasses, nchunks);
+    const bool ahead = more && __all_sync(0xffffffffu, mbar_test(full0 + 8u * np.slot, np.parity));   // its MMAs are complete already
+    tmem_ld_wait();
+    fence_before_sync();                                  // the whole slot is in registers: hand it back
+    if (UECRT_TC_NAMED_BARRIERS) nbar_arrive(kBarEmpty + pos.slot, kBarEmptyCount);
+    else if (is_lane0) mbar_arrive(empty0 + 8u * pos.slot);
 #ifdef UECRT_TC_TRACE
-        if (trs_) tre_[2] = clock64();
+    if (trs_) tre_[1] = clock64();
 #endif
-        UECRT_TCS(pl)
-      }
-      mbar_arrive(done0 + 8u * g);
-#ifdef UECRT_TC_PROFILE
-      ++ptiles;
-      UECRT_TCS(ps)
+    const uint32_t nt0 = lane_taddr + np.slot * kNC;
+    quad_max(va, qa);
+    if (ahead) { fence_after_sync(); tmem_ld32(nt0, va); }
+    quad_max(vb, qb);
+    if (ahead) tmem_ld32(nt0 + 32, vb);
+    const uint32_t c2 = quad_signs(qa), c3 = quad_signs(qb);
+    const uint32_t hi = __byte_perm(c1, c0, 0x0040);      // low 16 bits = (c0 << 8) | c1
+    const uint32_t lo = __byte_perm(c3, c2, 0x0040);      // low 16 bits = (c2 << 8) | c3
+    // word of chunk j of this ray; resident operand: tile m of a group goes to bitmap buffer m & 1
+    sts32(bitmap0 + ((uint32_t)pos.j * kShadeThreads + pos.g * kGroupThreads) * 4u + (SWEEP ? 0u : (pos.it.m & 1u) * lay.bitmap_buf_bytes),
+          ~__byte_perm(lo, hi, 0x5410));                  // a set sign bit = NOT a candidate; bit 31 = quad 0 of the chunk
+#ifdef UECRT_TC_TRACE
+    if (trs_) tre_[2] = clock64();
+    seq += kScanGroups;
 #endif
+    UECRT_TCS(pl)
+    if (pos.j + 1 == nchunks) {                           // the tile's last chunk: its bitmap is complete
+      if (UECRT_TC_NAMED_BARRIERS) { __threadfence_block(); nbar_arrive(kBarScanDone + pos.g, kBarScanDoneCount); }
+      else { __syncwarp(); if (is_lane0) mbar_arrive(done0 + 8u * pos.g); }   // the 32 lanes' words are ordered before the arrival
     }
+#ifdef UECRT_TC_PROFILE
+    if (pos.j + 1 == nchunks) ++ptiles;
+#endif
+    if (!more) break;
+    pos = np;
+    if (!ahead) {
+#ifdef UECRT_TC_PROFILE
+      ++p_blocked;
+#endif
+      mbar_wait(full0 + 8u * pos.slot, pos.parity);
+      fence_after_sync();
+      tmem_ld32(nt0, va);
+      tmem_ld32(nt0 + 32, vb);
+    }
+#ifdef UECRT_TC_PROFILE
+    else ++p_ready_now;
+#endif
+    UECRT_TCS(pw)
   }
 #ifdef UECRT_TC_PROFILE
-  if (prof_counters && lane == 0) {
+  if (prof_counters && is_lane0) {
     atomicAdd(prof_counters + 12, ptiles);
     atomicAdd(prof_counters + 13, (unsigned long long)pw);
     atomicAdd(prof_counters + 14, (unsigned long long)pl);
-    atomicAdd(prof_counters + 15, (unsigned long long)ps);
     atomicAdd(prof_counters + 32 + ((threadIdx.x >> 5) & 3), (unsigned long long)pw);
     atomicAdd(prof_counters + 36 + ((threadIdx.x >> 5) & 3), (unsigned long long)pl);
     atomicAdd(prof_counters + 24, p_ready_now);
