@@ -622,14 +622,15 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
   in_window();                                    // work that does not depend on this round's hit
   UECRT_TCP(prof, 1)
   const tc::QuadRay qr = tc::make_quad_ray(sr);
-  const int pass_quads = pass_rows / tc::kQuad;
+  const int pass_quads = pass_rows / tc::kQuad;   // bitmap bits per pass
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
     for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
       tc::shade_wait(sh, m++);
       UECRT_TCP(prof, 3)
-      tc::for_each_quad(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
-        tc_quad(sc, (int)base + k, qr, [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+      tc::for_each_flag(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
+        auto test = [&](int j) { test_fast(sc.geom, j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); };
+        if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
       });
       if (!SWEEP || ++p == npasses) break;
       tc::shade_next_pass(sh);
@@ -646,8 +647,9 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
     for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
       tc::shade_wait(sh, m++);
       UECRT_TCP(prof, 3)
-      tc::for_each_quad(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
-        tc_quad(sc, (int)base + k, qr, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+      tc::for_each_flag(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
+        auto test = [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); };
+        if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
       });
       if (!SWEEP || ++p == npasses) break;
       tc::shade_next_pass(sh);
@@ -683,8 +685,9 @@ __device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint
   const tc::QuadRay qr = tc::make_quad_ray(make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz));
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    tc::for_each_quad(sh, buf, q.live, [&](int k) {
-      tc_quad_s(s_quads, k, qr, [&](int j) { test_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); });
+    tc::for_each_flag(sh, buf, q.live, [&](int k) {
+      auto test = [&](int j) { test_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); };
+      if (tc::kQuad == 4) tc_quad_s(s_quads, k, qr, test); else test(k);
     });
     if (best.id >= 0) {
       h.id = best.id;
@@ -695,8 +698,9 @@ __device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    tc::for_each_quad(sh, buf, q.live, [&](int k) {
-      tc_quad_s(s_quads, k, qr, [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); });
+    tc::for_each_flag(sh, buf, q.live, [&](int k) {
+      auto test = [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); };
+      if (tc::kQuad == 4) tc_quad_s(s_quads, k, qr, test); else test(k);
     });
     if (best.id >= 0) {
       const float4 g = tc::lds_f4(s_geom + 16u * (uint32_t)best.id);
@@ -951,7 +955,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
       const ScanRay sr = make_scan_ray(ox, oy, oz, dx, dy, dz);
       tc::shade_submit(sh, sr, has_ray);
       const tc::QuadRay qr = tc::make_quad_ray(sr);
-      const int pass_quads = pass_rows / tc::kQuad;
+      const int pass_quads = pass_rows / tc::kQuad;   // bitmap bits per pass
       double t = -1.0, nx = 0.0, ny = 0.0, nz = 0.0;
       int id = -1;
       bool front = false;
@@ -960,8 +964,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         FastBest best{(float)tmax * dlen, -1};
         for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
           tc::shade_wait(sh, pass_m++);
-          tc::for_each_quad(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
-            tc_quad(sc, (int)base + k, qr, [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); });
+          tc::for_each_flag(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
+            auto test = [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); };
+            if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
           });
           if (!SWEEP || ++p == npasses) break;
           tc::shade_next_pass(sh);
@@ -977,8 +982,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         ExactBest best{tmax, -1};
         for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
           tc::shade_wait(sh, pass_m++);
-          tc::for_each_quad(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
-            tc_quad(sc, (int)base + k, qr, [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); });
+          tc::for_each_flag(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
+            auto test = [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); };
+            if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
           });
           if (!SWEEP || ++p == npasses) break;
           tc::shade_next_pass(sh);
@@ -1282,7 +1288,8 @@ void launch_primary_hits_grid(const DeviceScene& sc, unsigned long long n_rays, 
 // ---- tensor-core scan variants
 int tc_resident_max_spheres() {
   const size_t fixed = tc::make_layout(0).total;
-  const int fit = (int)((232448 - fixed) / (128 + 32 + 32) / tc::kNC * tc::kNC);   // per sphere row: 128 B operand, 2 x 16 B bitmap (one bit per quad and ray, two buffers), 16 B quad table, 16 B sphere
+  // per sphere row: 128 B operand, two bitmap buffers of 512 rays x 1 bit per kQuad spheres, 16 B quad table, 16 B sphere
+  const int fit = (int)((232448 - fixed) / (128 + 2 * 64 / tc::kQuad + 32) / tc::kNC * tc::kNC);
   return fit < tc::kMaxRows ? fit : tc::kMaxRows;
 }
 #ifndef UECRT_TC_SWEEP_ROWS

@@ -53,27 +53,53 @@ __device__ __forceinline__ void shade_next_pass(const Shade& s) {
   if ((threadIdx.x & 31u) == 0u) mbar_arrive(s.a_ready);    // one arrival per warp (the barrier counts warps)
 }
 
-// SHADE: f(quad index within the pass) for every flagged quad of this thread's ray, ascending.  WARP-CONVERGENT:
-// all 32 lanes must call it (a lane without a live ray passes live = false).  Every trip of the loop hands
-// one quad to every lane that still has one (a lane whose current word is exhausted moves on to its next
-// non-empty chunk word), so the warp makes max-over-lanes(flagged quads) trips and f runs once per trip with
-// the lanes converged.
+// SHADE: f(bit index within the pass) for every set bit of this thread's ray, ascending (bit index = sphere index with one
+// bit per sphere, quad index with one bit per quad).  WARP-CONVERGENT: all 32 lanes must call it (a lane without a live ray
+// passes live = false).  Every trip of the loop hands one bit to every lane that still has one (a lane whose current word is
+// exhausted moves on to its next non-empty word: through the summary word with one bit per sphere, word by word otherwise),
+// so the warp makes max-over-lanes(set bits) trips and f runs once per trip with the lanes converged.
 template <class F>
-__device__ __forceinline__ void for_each_quad(Shade& s, uint32_t buf, bool live, F&& f) {
+__device__ __forceinline__ void for_each_flag(Shade& s, uint32_t buf, bool live, F&& f) {
+  const uint32_t* bm = s.bitmap + buf * (uint32_t)((kScanGroups + s.nwords) * kShadeThreads);
   uint32_t m = 0u;
-  int c = live ? -1 : s.nchunks;
-  const uint32_t* bm = s.bitmap + buf * (uint32_t)(s.nchunks * kShadeThreads);
-  for (;;) {
-    while (m == 0u && c + 1 < s.nchunks) { ++c; m = bm[c * kShadeThreads]; }
-    if (!__any_sync(0xffffffffu, m != 0u)) return;
+  int w = 0;
+  if (kQuad == 1) {
+    uint32_t sum = 0u;
+    if (live) {
+#pragma unroll
+      for (int sg = 0; sg < kScanGroups; ++sg) sum |= bm[sg * kShadeThreads];
+    }
+    for (;;) {
+      if (m == 0u && sum != 0u) {
+        w = __clz((int)sum);
+        sum &= ~(0x80000000u >> w);
+        m = bm[(kScanGroups + w) * kShadeThreads];
+      }
+      if (!__any_sync(0xffffffffu, m != 0u)) return;
 #ifdef UECRT_TC_PROFILE
-    ++s.prof_trips;
-    if (m != 0u) ++s.prof_cands;
+      ++s.prof_trips;
+      if (m != 0u) ++s.prof_cands;
 #endif
-    if (m != 0u) {
-      const int b = __clz((int)m);
-      m &= ~(0x80000000u >> b);
-      f(c * (kNC / kQuad) + b);
+      if (m != 0u) {
+        const int b = __clz((int)m);
+        m &= ~(0x80000000u >> b);
+        f(w * 32 + b);
+      }
+    }
+  } else {
+    w = live ? -1 : s.nwords;
+    for (;;) {
+      while (m == 0u && w + 1 < s.nwords) { ++w; m = bm[(kScanGroups + w) * kShadeThreads]; }
+      if (!__any_sync(0xffffffffu, m != 0u)) return;
+#ifdef UECRT_TC_PROFILE
+      ++s.prof_trips;
+      if (m != 0u) ++s.prof_cands;
+#endif
+      if (m != 0u) {
+        const int b = __clz((int)m);
+        m &= ~(0x80000000u >> b);
+        f(w * 32 + b);
+      }
     }
   }
 }
@@ -125,6 +151,21 @@ __device__ __forceinline__ uint32_t quad_candidates_s(uint32_t s_quads, int quad
   return quad_candidates_v(lds_u64x2(q), lds_u64x2(q + 16u), lds_u64x2(q + 32u), lds_u64x2(q + 48u), r);
 }
 
+// one bit per sphere: 32 accumulators -> one bitmap word, bit (31 - i) = (v[i] >= 0).  Four independent funnel-shift
+// chains (mask = (mask << 1) | sign(v)), merged with byte permutes.
+__device__ __forceinline__ uint32_t sign_word(const int (&v)[32]) {
+  uint32_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = __funnelshift_l((uint32_t)v[8 * k + i], m, 1);
+    c[k] = m;
+  }
+  const uint32_t hi = __byte_perm(c[1], c[0], 0x0040);   // low 16 bits = (c0 << 8) | c1
+  const uint32_t lo = __byte_perm(c[3], c[2], 0x0040);   // low 16 bits = (c2 << 8) | c3
+  return ~__byte_perm(lo, hi, 0x5410);                   // a set sign bit = NOT a candidate
+}
 // the max of every quad of 32 accumulators (8 values, full-rate VIMNMX3 + VIMNMX each)
 __device__ __forceinline__ void quad_max(const int (&v)[32], int (&q)[8]) {
 #pragma unroll
@@ -172,7 +213,7 @@ struct ChunkPos {
 template <bool SWEEP>
 __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t npasses, int fixed_rounds,
                                              unsigned long long* prof_counters = nullptr) {
-  static_assert(kScanGroups == 1, "the named-barrier hand-off counts one scan warpgroup");
+  static_assert(kScanGroups == 1 || !UECRT_TC_NAMED_BARRIERS, "the named-barrier hand-off counts one scan warpgroup");
 #ifdef UECRT_TC_PROFILE
   long long pw = 0, pl = 0, plast = clock64();
   unsigned long long ptiles = 0, p_ready_now = 0, p_blocked = 0;
@@ -197,6 +238,7 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
   uint32_t seq = sg;
 #endif
   int va[32], vb[32];
+  uint32_t sum = 0, tile_key = 0xffffffffu;                 // one bit per sphere: bit (31 - w) = word w of the tile is non-zero (this warpgroup's chunks)
   mbar_wait(full0 + 8u * pos.slot, pos.parity);
   fence_after_sync();
   tmem_ld32(lane_taddr + pos.slot * kNC, va);
@@ -209,13 +251,16 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
     if (trs_) tre_[0] = clock64();
 #endif
     const uint32_t t0 = lane_taddr + pos.slot * kNC;
+    const bool first_of_tile = tile_key != (pos.it.m * (uint32_t)kGroups + pos.g);   // this warpgroup's first chunk of the tile
+    tile_key = pos.it.m * (uint32_t)kGroups + pos.g;
     int qa[8], qb[8];
+    uint32_t c0, c1, c2, c3;                              // one bit per quad: 8 flags each; one bit per sphere: a bitmap word each
     tmem_ld_wait();
-    quad_max(va, qa);
+    if (kQuad == 4) quad_max(va, qa); else c0 = sign_word(va);
     tmem_ld32(t0 + 64, va);
-    quad_max(vb, qb);
+    if (kQuad == 4) quad_max(vb, qb); else c1 = sign_word(vb);
     tmem_ld32(t0 + 96, vb);
-    const uint32_t c0 = quad_signs(qa), c1 = quad_signs(qb);
+    if (kQuad == 4) { c0 = quad_signs(qa); c1 = quad_signs(qb); }
     // this warp's next chunk
     ChunkPos np = pos;
     bool more = true;
@@ -230,24 +275,34 @@ __device__ __forceinline__ void scanner_role(unsigned char* smem_raw, uint32_t t
     if (trs_) tre_[1] = clock64();
 #endif
     const uint32_t nt0 = lane_taddr + np.slot * kNC;
-    quad_max(va, qa);
+    if (kQuad == 4) quad_max(va, qa); else c2 = sign_word(va);
     if (ahead) { fence_after_sync(); tmem_ld32(nt0, va); }
-    quad_max(vb, qb);
+    if (kQuad == 4) quad_max(vb, qb); else c3 = sign_word(vb);
     if (ahead) tmem_ld32(nt0 + 32, vb);
-    const uint32_t c2 = quad_signs(qa), c3 = quad_signs(qb);
-    const uint32_t hi = __byte_perm(c1, c0, 0x0040);      // low 16 bits = (c0 << 8) | c1
-    const uint32_t lo = __byte_perm(c3, c2, 0x0040);      // low 16 bits = (c2 << 8) | c3
-    // word of chunk j of this ray; resident operand: tile m of a group goes to bitmap buffer m & 1
-    sts32(bitmap0 + ((uint32_t)pos.j * kShadeThreads + pos.g * kGroupThreads) * 4u + (SWEEP ? 0u : (pos.it.m & 1u) * lay.bitmap_buf_bytes),
-          ~__byte_perm(lo, hi, 0x5410));                  // a set sign bit = NOT a candidate; bit 31 = quad 0 of the chunk
+    // this ray's summary word of the tile's bitmap buffer (resident operand: tile m of a group goes to buffer m & 1); word w follows at + (1 + w) * kShadeThreads * 4
+    const uint32_t ob = bitmap0 + pos.g * (kGroupThreads * 4u) + (SWEEP ? 0u : (pos.it.m & 1u) * lay.bitmap_buf_bytes);
+    if (kQuad == 4) {
+      c2 = quad_signs(qa); c3 = quad_signs(qb);
+      const uint32_t hi = __byte_perm(c1, c0, 0x0040);    // low 16 bits = (c0 << 8) | c1
+      const uint32_t lo = __byte_perm(c3, c2, 0x0040);    // low 16 bits = (c2 << 8) | c3
+      sts32(ob + ((uint32_t)kScanGroups + (uint32_t)pos.j) * (kShadeThreads * 4u), ~__byte_perm(lo, hi, 0x5410));   // a set sign bit = NOT a candidate; bit 31 = quad 0 of the chunk
+    } else {
+      const uint32_t o = ob + ((uint32_t)kScanGroups + 4u * (uint32_t)pos.j) * (kShadeThreads * 4u);
+      sts32(o, c0); sts32(o + kShadeThreads * 4u, c1); sts32(o + 2u * kShadeThreads * 4u, c2); sts32(o + 3u * kShadeThreads * 4u, c3);
+      const uint32_t nz = (c0 ? 8u : 0u) | (c1 ? 4u : 0u) | (c2 ? 2u : 0u) | (c3 ? 1u : 0u);
+      sum = (first_of_tile ? 0u : sum) | (nz << (28 - 4 * pos.j));
+      sts32(ob + sg * (kShadeThreads * 4u), sum);
+    }
 #ifdef UECRT_TC_TRACE
     if (trs_) tre_[2] = clock64();
     seq += kScanGroups;
 #endif
     UECRT_TCS(pl)
-    if (pos.j + 1 == nchunks) {                           // the tile's last chunk: its bitmap is complete
-      if (UECRT_TC_NAMED_BARRIERS) { __threadfence_block(); nbar_arrive(kBarScanDone + pos.g, kBarScanDoneCount); }
-      else { __syncwarp(); if (is_lane0) mbar_arrive(done0 + 8u * pos.g); }   // the 32 lanes' words are ordered before the arrival
+    if (UECRT_TC_NAMED_BARRIERS) {
+      if (pos.j + 1 == nchunks) { __threadfence_block(); nbar_arrive(kBarScanDone + pos.g, kBarScanDoneCount); }   // the tile's last chunk
+    } else {
+      __syncwarp();                                       // the 32 lanes' words are ordered before the arrival
+      if (is_lane0) mbar_arrive(done0 + 8u * pos.g);      // scan_done counts one arrival per scan warp and chunk of the tile
     }
 #ifdef UECRT_TC_PROFILE
     if (pos.j + 1 == nchunks) ++ptiles;

@@ -327,8 +327,13 @@ constexpr int kNC = 128;                                     // spheres (TMEM co
 constexpr int kRing = 3;                                     // ring slots: TMEM columns [0, 384)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kATmemCol = kRing * kNC;                  // A tile of group g: TMEM columns [384 + 32g, 384 + 32g + 32)
-constexpr int kQuad = 4;                                     // spheres per candidate-bitmap bit (tc_collect.cuh)
-constexpr int kMaxRows = 1536;                               // resident operand: 128 B + 16 B of bitmap per sphere row must fit in shared memory
+#ifndef UECRT_TC_QUAD
+#define UECRT_TC_QUAD 4            // spheres per candidate-bitmap bit: 1 (one bit per sphere) or 4 (one bit per quad, re-tested in FP32 by the shade thread)
+#endif
+constexpr int kQuad = UECRT_TC_QUAD;                         // spheres per candidate-bitmap bit (tc_collect.cuh)
+static_assert(kQuad == 1 || kQuad == 4, "bitmap granularity");
+constexpr int kWordsPerChunk = 128 / (32 * kQuad);           // bitmap words per ray and 128-sphere chunk (4 or 1)
+constexpr int kMaxRows = kQuad == 1 ? 1024 : 1536;           // one bit per sphere: a 32-bit summary word per ray covers 32 bitmap words
 constexpr uint32_t kHeaderBytes = 1024;
 
 struct Header {               // first kHeaderBytes of dynamic shared memory
@@ -353,6 +358,9 @@ struct Header {               // first kHeaderBytes of dynamic shared memory
 // one of its two paths while the scan warps write the other's (kernels.cu, k_render_paths_tc).  Swept operand: one.
 // Resident operand only: the shade side's tables follow the bitmaps, the quad table (64 B per quad, scene_pack.hpp
 // pack_scene_quads) and the spheres' float4 {cx,cy,cz,r}: a flagged quad costs shared-memory loads, not an L1 / L2 round trip.
+// One bit per sphere (kQuad == 1): bitmap word w of ray i covers spheres 32 w .. 32 w + 31 of the pass and the ray's SUMMARY
+// word (one per bitmap buffer, in front of it) has bit (31 - w) set iff word w is non-zero, so the shade thread jumps to its
+// next non-empty word.
 struct Layout {
   uint32_t b, bitmap, bitmap_buf_bytes, quads, geom, total;
 };
@@ -360,7 +368,8 @@ __host__ __device__ inline Layout make_layout(uint32_t b_rows, uint32_t nbuf = 1
   Layout l;
   l.b = kHeaderBytes;
   l.bitmap = l.b + nbuf * b_rows * 128u;
-  l.bitmap_buf_bytes = (b_rows / (uint32_t)kNC) * (uint32_t)kShadeThreads * 4u;
+  // per buffer: [summary: one word per ray and scan warpgroup][words: b_rows / (32 kQuad) per ray]
+  l.bitmap_buf_bytes = ((uint32_t)kScanGroups + (b_rows / (uint32_t)kNC) * (uint32_t)kWordsPerChunk) * (uint32_t)kShadeThreads * 4u;
   l.quads = l.bitmap + (nbuf == 1u ? 2u : 1u) * l.bitmap_buf_bytes;
   l.geom = l.quads + (nbuf == 1u ? b_rows * 16u : 0u);
   l.total = l.geom + (nbuf == 1u ? b_rows * 16u : 0u);
@@ -389,12 +398,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 // CTA-wide setup: barriers, TMEM, the bulk copy of the (resident) sphere operand; b_bytes = 0: the operand
 // is swept, the issuer loads it pass by pass.  Every thread calls it.
 __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const void* b_global, uint32_t b_bytes, uint32_t nchunks_per_tile) {
-  (void)nchunks_per_tile;
+
   Header* h = reinterpret_cast<Header*>(smem_raw);
   if (threadIdx.x == 0) {
     for (int g = 0; g < kGroups; ++g) {
       mbar_init(smem_addr(&h->a_ready[g]), kGroupThreads / 32);   // one arrival per shade warp
-      mbar_init(smem_addr(&h->scan_done[g]), 4);                  // one arrival per scan warp, at the tile's last chunk
+      mbar_init(smem_addr(&h->scan_done[g]), 4u * nchunks_per_tile);   // one arrival per scan warp and chunk of the tile
     }
     for (int s = 0; s < kRing; ++s) {
       mbar_init(smem_addr(&h->tmem_full[s]), 1);
@@ -549,8 +558,8 @@ __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tm
 struct Shade {
   uint32_t a_ready, scan_done;       // the group's barriers: shared addresses of the mbarriers (ids with UECRT_TC_NAMED_BARRIERS)
   uint32_t a_taddr;                  // TMEM address of this thread's A row: its warp's lane quarter | the group's A columns
-  const uint32_t* bitmap;            // this ray's candidate bitmap (buffer 0): the word of chunk c at bitmap[c * kShadeThreads]
-  int nchunks;                       // words per pass; bitmap buffer 1 starts nchunks * kShadeThreads words further
+  const uint32_t* bitmap;            // this ray's SUMMARY word(s) of bitmap buffer 0; bitmap word w at bitmap[(kScanGroups + w) * kShadeThreads]
+  int nwords;                        // bitmap words per pass; buffer 1 starts (kScanGroups + nwords) * kShadeThreads words further
 #ifdef UECRT_TC_PROFILE
   unsigned long long prof_trips = 0, prof_steps = 0, prof_cands = 0;
 #endif
@@ -567,7 +576,7 @@ __device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tm
   s.scan_done = UECRT_TC_NAMED_BARRIERS ? kBarScanDone + g : smem_addr(&h->scan_done[g]);
   s.a_taddr = tmem_base + kATmemCol + g * (uint32_t)kSlots + (((threadIdx.x >> 5) & 3u) * 32u << 16);
   s.bitmap = reinterpret_cast<const uint32_t*>(smem_raw + lay.bitmap) + threadIdx.x;
-  s.nchunks = nchunks;
+  s.nwords = nchunks * kWordsPerChunk;
   return s;
 }
 #endif  // __CUDACC__
