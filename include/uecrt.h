@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define UECRT_VERSION 1
+#define UECRT_VERSION 2
 
 enum {
   UECRT_OK = 0,
@@ -65,8 +65,16 @@ typedef struct {
   uint64_t seed;          /* Philox key                     */
   uint32_t sample_begin;  /* this call renders sample ids [sample_begin, sample_begin+sample_count) */
   uint32_t sample_count;  /*   of every pixel; 0 means "all spp" (sample_begin ignored)            */
-  int32_t num_gpus;       /* uecrt_render only: spp-shard over this many devices (>=1)             */
+  int32_t num_gpus;       /* uecrt_render only: shard the frame over this many devices (>=1)       */
   uint32_t flags;         /* UECRT_FLAG_*                   */
+  /* Work-item sharding (one process per GPU): a frame's work items are its (pixel, sample) paths, numbered
+   * sample-major, so a contiguous range of them is "a few whole samples of every pixel plus part of one more".
+   * shard_count > 0: this call renders the shard_index-th of shard_count equal ranges of the items selected by
+   * [sample_begin, +sample_count); every device of a G-way split gets items/G paths whatever spp is (spp-granular
+   * shards differ by a whole sample per pixel: 62 vs 63 spp at 500 spp over 8 GPUs).  The Philox streams are keyed
+   * by the global (pixel, sample), so the summed image does not depend on how the items were split.
+   * 0 = no sharding.  uecrt_render shards this way over num_gpus devices by itself. */
+  uint32_t shard_index, shard_count;
 } uecrt_params;
 
 enum {

@@ -129,6 +129,56 @@ class Oracle:
         return out
 
 
+# --- scenes / cameras without the product library -------------------------------------------------
+# bench.py's reference arm must not map libuecrt.so (the driver records which .so files each arm loads), so it
+# takes its scene and camera arrays from tests/golden/bench_scenes.npz (written by tools/make_bench_scenes.py
+# from the product's host scene builders) through these two stand-ins for uecraytracing_b200.Scene / Camera:
+# same .struct() layout as include/uecrt.h uecrt_scene / uecrt_camera.
+class _SceneStruct(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("geom", C.c_void_p), ("mat_type", C.c_void_p), ("mat_param", C.c_void_p)]
+
+
+class _CameraStruct(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("lower_left", C.c_float * 3), ("horizontal", C.c_float * 3),
+                ("vertical", C.c_float * 3), ("u", C.c_float * 3), ("v", C.c_float * 3), ("lens_radius", C.c_float)]
+
+
+class PlainScene:
+    def __init__(self, geom, mat_type, mat_param):
+        self.geom = np.ascontiguousarray(geom, np.float32).reshape(-1, 4)
+        self.mat_type = np.ascontiguousarray(mat_type, np.uint32).reshape(-1)
+        self.mat_param = np.ascontiguousarray(mat_param, np.float32).reshape(-1, 4)
+        self.n = len(self.geom)
+
+    def struct(self):
+        return _SceneStruct(self.n, _ptr(self.geom).value, _ptr(self.mat_type).value, _ptr(self.mat_param).value)
+
+
+class PlainCamera:
+    FIELDS = ("origin", "lower_left", "horizontal", "vertical", "u", "v")
+
+    def __init__(self, vec18, lens_radius):
+        self.s = _CameraStruct()
+        v = np.asarray(vec18, np.float32).reshape(6, 3)
+        for k, name in enumerate(self.FIELDS):
+            setattr(self.s, name, (C.c_float * 3)(*[float(x) for x in v[k]]))
+        self.s.lens_radius = float(lens_radius)
+
+    def struct(self):
+        return self.s
+
+
+BENCH_SCENES = os.path.join(os.path.dirname(HERE), "tests", "golden", "bench_scenes.npz")
+
+
+def bench_scene(name, camera):
+    """(PlainScene, PlainCamera) of a bench.py workload from the committed fixture (no product code involved)."""
+    z = np.load(BENCH_SCENES)
+    sc = PlainScene(z[f"{name}_geom"], z[f"{name}_mat_type"], z[f"{name}_mat_param"])
+    cam = PlainCamera(z[f"cam_{camera}_vec"], float(z[f"cam_{camera}_lens"]))
+    return sc, cam
+
+
 def load(which="best"):
     if which in ("ref", "best") and os.path.exists(REF):
         return Oracle(REF)

@@ -26,7 +26,7 @@ def test_abi_exports_every_declared_symbol(u):
         assert hasattr(L, name), f"{name} declared in include/ but not exported by libuecrt.so"
     from uecraytracing_b200._lib import EXPORTS
     assert declared == set(EXPORTS)
-    assert u.lib.uecrt_version() == 1
+    assert u.lib.uecrt_version() == 2
 
 
 def test_no_cpu_fallback(u):
@@ -47,6 +47,36 @@ def test_no_cpu_fallback(u):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 assert "oracle" not in open(os.path.join(root, f)).read().lower().replace("oracle_free", ""), f
+
+
+def test_bench_fixture_matches_the_scene_builders(u):
+    """tests/golden/bench_scenes.npz (what bench.py's CPU arm renders) == what the product's host builders produce."""
+    from oracle import pyoracle
+    for name, cam in (("final", "final"), ("ref4", "ref"), ("dense", "dense")):
+        fs, fc = pyoracle.bench_scene(name, cam)
+        s, c = u.Scene.named(name, seed=1, n=10000), u.Camera.named(cam)
+        assert np.array_equal(fs.geom, s.geom) and np.array_equal(fs.mat_type, s.mat_type) and np.array_equal(fs.mat_param, s.mat_param)
+        assert bytes(fc.struct()) == bytes(c.struct())
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """bench.py --impl reference renders through oracle/ only: libuecrt.so must not be mapped (the driver records it)."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--workload', 'ref4']\n"
+            "import bench\n"
+            "bench.cpu_reference_arm.__defaults__ = (0.2,)\n"
+            "orig = bench.cpu_reference_arm\n"
+            "bench.cpu_reference_arm = lambda *a, **k: orig(*a[:6], budget_s=0.2)\n"
+            "bench.main()\n"
+            "m = open('/proc/self/maps').read()\n"
+            "print('LOADED' if 'libuecrt' in m else 'CLEAN', 'ORACLE' if 'liboracle' in m else 'NOORACLE')\n")
+    r = subprocess.run([os.sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "CLEAN ORACLE" in r.stdout, r.stdout[-300:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][0]
+    import json
+    j = json.loads(line)
+    assert j["impl"] == "reference" and j["gpu_launches"] == 0 and j["cpu_baseline"]["value"] == j["value"]
 
 
 def test_image_height(u):

@@ -27,7 +27,7 @@ class CameraStruct(C.Structure):
 class ParamsStruct(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
                 ("seed", C.c_uint64), ("sample_begin", C.c_uint32), ("sample_count", C.c_uint32),
-                ("num_gpus", C.c_int32), ("flags", C.c_uint32)]
+                ("num_gpus", C.c_int32), ("flags", C.c_uint32), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32)]
 
 
 class StatsStruct(C.Structure):

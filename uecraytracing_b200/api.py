@@ -100,15 +100,15 @@ def stats_to_dict(s):
     return {k: getattr(s, k) for k, _ in StatsStruct._fields_}
 
 
-def _params(width, height, spp, max_depth, seed, sample_begin=0, sample_count=0, num_gpus=1, flags=0):
-    return ParamsStruct(width, height, spp, max_depth, seed, sample_begin, sample_count, num_gpus, flags)
+def _params(width, height, spp, max_depth, seed, sample_begin=0, sample_count=0, num_gpus=1, flags=0, shard=(0, 0)):
+    return ParamsStruct(width, height, spp, max_depth, seed, sample_begin, sample_count, num_gpus, flags, shard[0], shard[1])
 
 
 _SCAN_FLAGS = {None: 0, "auto": 0, "fp32": FLAG_SCAN_FP32, "tensor": FLAG_SCAN_TENSOR, "grid": FLAG_SCAN_GRID}
 
 
 def render(scene, camera, width=400, spp=100, max_depth=50, seed=0, gpus=1, exact=False, return_accum=False,
-           sample_begin=0, sample_count=0, scan=None):
+           sample_begin=0, sample_count=0, scan=None, shard=(0, 0)):
     """uecrt_render with HOST buffers: the call the re-hosted yk::render() makes."""
     height = image_height(width)
     rgb = np.zeros((height, width, 3), np.uint8)
@@ -116,7 +116,7 @@ def render(scene, camera, width=400, spp=100, max_depth=50, seed=0, gpus=1, exac
     st = StatsStruct()
     sc, cam = scene.struct(), camera.struct()
     p = _params(width, height, spp, max_depth, seed, sample_begin, sample_count, gpus,
-                (FLAG_EXACT_HITS if exact else 0) | _SCAN_FLAGS[scan])
+                (FLAG_EXACT_HITS if exact else 0) | _SCAN_FLAGS[scan], shard)
     check(lib.uecrt_render(C.byref(sc), C.byref(cam), C.byref(p), _ptr(rgb), _ptr(accum) if return_accum else None,
                            C.byref(st)), "uecrt_render")
     return rgb, accum, stats_to_dict(st)
@@ -168,8 +168,9 @@ class Context:
         check(lib.uecrt_ctx_set_scene(self._h, C.byref(sc), C.byref(cam)), "uecrt_ctx_set_scene")
 
     def accumulate(self, d_accum_ptr, width, height, spp, max_depth, seed, sample_begin=0, sample_count=0, stream=0,
-                   flags=0):
-        p = _params(width, height, spp, max_depth, seed, sample_begin, sample_count, 1, flags)
+                   flags=0, shard=(0, 0)):
+        """shard = (index, count): this call renders the index-th of count equal ranges of the frame's work items."""
+        p = _params(width, height, spp, max_depth, seed, sample_begin, sample_count, 1, flags, shard)
         check(lib.uecrt_accumulate_device(self._h, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(stream), None),
               "uecrt_accumulate_device")
 

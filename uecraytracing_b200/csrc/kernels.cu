@@ -267,6 +267,7 @@ struct PathState {
 __device__ __forceinline__ void slot_assign(PathState& p, const RenderArgs& a, unsigned long long w,
                                             unsigned long long n_pixels, double inv_np) {
   if (w < a.total_items) {
+    w += a.item_begin;
     unsigned long long q = __double2ull_rz(__ull2double_rz(w) * inv_np);
     long long rem = (long long)(w - q * n_pixels);
     if (rem < 0) { --q; rem += (long long)n_pixels; }

@@ -48,7 +48,8 @@ struct RenderArgs {
   uint32_t tiles_x;                             // 8x4-pixel tiles per row (ceil(width / 8))
   float inv_tiles_x;
   unsigned long long n_slots;                   // tiles * 32 (pixel slots incl. the ragged edge)
-  unsigned long long total_items;               // n_slots * sample_count: one work item per path slot
+  unsigned long long total_items;               // work items of this launch (one per path slot): [item_begin, item_begin + total_items)
+  unsigned long long item_begin;                //   of the n_slots * sample_count items of the sample range, sample-major
   float4* accum;
   unsigned long long* counters;
   int count_stats;

@@ -33,8 +33,10 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local unsigned long long g_err_seq = 0;
 std::mutex g_err_mutex;
 std::string g_last_err_any;   // last error from any thread (worker threads of uecrt_render)
+unsigned long long g_last_err_any_seq = 0, g_err_counter = 0;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -46,6 +48,7 @@ int fail(int code, const char* fmt, ...) {
   {
     std::lock_guard<std::mutex> lk(g_err_mutex);
     g_last_err_any = buf;
+    g_err_seq = g_last_err_any_seq = ++g_err_counter;
   }
   return code;
 }
@@ -160,6 +163,8 @@ constexpr uint32_t kAutoTileSpheres = 2048;   // 32 KB tiles: 2 buffers + lists 
 constexpr size_t kSmemOptin = 232448;
 
 int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
+  // A scene reload overwrites (or reallocates) buffers the context's last K1 may still be reading: wait for it.
+  if (c->timed && c->ev1) CUDA_TRY(cudaEventSynchronize(c->ev1));
   // resident while 3 CTAs of K1 still fit on an SM (scenes up to ~4000 spheres); beyond that the
   // scene is swept in 32 KB tiles, which keeps 3 CTAs/SM (measured on the 10k-sphere scene: 66% of
   // FP32 peak tiled vs 62% resident at 1 CTA/SM) and has no upper bound but the 16-bit list index
@@ -220,6 +225,10 @@ int ctx_upload_scene(uecrt_ctx* c, const uecrt_scene* scene) {
     c->sc.tc_npasses = resident ? 1 : (int)pt.rows / slice_rows;
     c->smem_tc = uecrt::tc_smem_bytes((int)pt.rows, c->sc.tc_npasses);
   }
+  // The copies above are cudaMemcpy from pageable memory on the legacy stream: they may return once the data is staged,
+  // before the DMA has landed, and the launch streams (cudaStreamNonBlocking, or the caller's) do not synchronise with the
+  // legacy stream.  Drain it so that every later launch, on whatever stream, sees the whole scene.
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
   c->h_geom.assign(scene->geom, scene->geom + scene->n);
   c->grid_ready = false;
   c->sc.grid = uecrt::DeviceGrid{};
@@ -366,6 +375,7 @@ int ctx_ensure_grid(uecrt_ctx* c) {
   if ((rc = up(c->d_cell_start, c->cap_cells, g.cell_start)) || (rc = up(c->d_items, c->cap_items, g.items)) ||
       (rc = up(c->d_always, c->cap_always, g.always)))
     return rc;
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));      // as in ctx_upload_scene: the grid is complete before any launch reads it
   uecrt::DeviceGrid& d = c->sc.grid;
   for (int a = 0; a < 3; ++a) { d.org[a] = g.org[a]; d.cell[a] = g.cell[a]; d.inv_cell[a] = g.inv_cell[a]; d.dim[a] = g.dim[a]; }
   d.cell_start = g.items.empty() ? nullptr : static_cast<const uint32_t*>(c->d_cell_start);
@@ -412,6 +422,13 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   a.inv_tiles_x = 1.0f / (float)a.tiles_x;
   a.n_slots = (unsigned long long)a.tiles_x * ((p->height + 3) / 4) * 32ull;
   a.total_items = a.n_slots * count;   // one work item per (pixel slot, sample) path
+  a.item_begin = 0;
+  if (p->shard_count) {                // the shard_index-th of shard_count equal ranges of those items
+    if (p->shard_index >= p->shard_count) return fail(UECRT_ERR_INVALID, "shard_index %u >= shard_count %u", p->shard_index, p->shard_count);
+    const unsigned long long t = a.total_items, lo = t / p->shard_count * p->shard_index + t % p->shard_count * p->shard_index / p->shard_count,
+                             hi = t / p->shard_count * (p->shard_index + 1) + t % p->shard_count * (p->shard_index + 1) / p->shard_count;
+    a.item_begin = lo; a.total_items = hi - lo;
+  }
   a.accum = reinterpret_cast<float4*>(d_accum);
   a.counters = ctx->d_counters;
   a.count_stats = (p->flags & UECRT_FLAG_NO_COUNTERS) ? 0 : 1;
@@ -571,10 +588,11 @@ int get_comms(int ndev, std::vector<void*>& out, NcclApi*& api) {
 // =========================================================================================
 extern "C" {
 
+// The most recent failure of the calling thread's last API call; if that call failed inside a worker thread
+// (uecrt_render with num_gpus > 1) the worker's message.  Every failing path goes through fail(), which stamps both.
 const char* uecrt_last_error(void) {
-  if (!g_err.empty()) return g_err.c_str();
   std::lock_guard<std::mutex> lk(g_err_mutex);
-  g_err = g_last_err_any;
+  if (g_err_seq < g_last_err_any_seq || g_err.empty()) { g_err = g_last_err_any; g_err_seq = g_last_err_any_seq; }
   return g_err.c_str();
 }
 int uecrt_version(void) { return UECRT_VERSION; }
@@ -629,7 +647,6 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
   if (ndev > avail) return fail(UECRT_ERR_INVALID, "num_gpus=%d but only %d sm_100 device(s) are visible", ndev, avail);
   uint32_t begin = params->sample_begin, count = params->sample_count;
   if (count == 0) { begin = 0; count = params->spp; }
-  ndev = (int)std::min<uint32_t>((uint32_t)ndev, count);
   const size_t npx = (size_t)params->width * params->height;
 
   int dev0 = 0;
@@ -650,11 +667,14 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
       if ((r = ctx_set_scene(w.ctx, scene, cam))) return r;
       CUDA_TRY(cudaMemsetAsync(w.accum, 0, npx * 4 * sizeof(float), w.st));
       uecrt_params p = *params;
-      // spp shard g of ndev: GLOBAL sample ids, so the image does not depend on ndev
-      const uint32_t lo = begin + (uint32_t)((uint64_t)count * g / ndev), hi = begin + (uint32_t)((uint64_t)count * (g + 1) / ndev);
-      p.sample_begin = lo; p.sample_count = hi - lo;
+      // shard g of ndev of the frame's work items (GLOBAL pixel / sample ids, so the image does not depend on ndev)
+      p.sample_begin = begin; p.sample_count = count;
+      p.shard_index = (uint32_t)g; p.shard_count = (uint32_t)ndev;
+      if (params->shard_count) {       // the caller's own shard, split once more over this process's devices
+        p.shard_index = params->shard_index * (uint32_t)ndev + (uint32_t)g; p.shard_count = params->shard_count * (uint32_t)ndev;
+      }
       w.ctx->timed = false;
-      if (p.sample_count && (r = accumulate(w.ctx, &p, w.accum, w.st))) return r;
+      if ((r = accumulate(w.ctx, &p, w.accum, w.st))) return r;
       return UECRT_OK;
     };
     wrc[g] = body();
@@ -665,9 +685,14 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
     for (int g = 0; g < ndev; ++g) th.emplace_back(worker, g);
     for (auto& t : th) t.join();
   }
+  // leave nothing in flight on any path out of this function: the workspaces (and their buffers) are reused by the next call
+  auto drain = [&]() {
+    for (int g = 0; g < ndev; ++g)
+      if (ws[g] && ws[g]->st) { cudaSetDevice(ws[g]->device); cudaStreamSynchronize(ws[g]->st); }
+  };
   auto restore = [&]() { cudaSetDevice(dev0); };
   for (int g = 0; g < ndev; ++g)
-    if (wrc[g]) { restore(); return wrc[g]; }
+    if (wrc[g]) { drain(); restore(); return wrc[g]; }
 
   // ---- one NCCL reduce of W*H*4 floats to device 0 (in place on the root) over NVLink
   double resolve_ms = 0, d2h_ms = 0, reduce_ms = 0;
@@ -682,7 +707,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
     int r = nccl->GroupEnd();
     if (r != 0 && !rc) rc = fail(UECRT_ERR_NCCL, "ncclGroupEnd failed: %s", nccl->GetErrorString ? nccl->GetErrorString(r) : "?");
     for (int g = 0; g < ndev; ++g) { cudaSetDevice(g); cudaEventRecord(ws[g]->r1, ws[g]->st); }
-    if (rc) { restore(); return rc; }
+    if (rc) { drain(); restore(); return rc; }
   }
 
   // ---- root: K3 resolve + copies back
@@ -704,6 +729,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
     return UECRT_OK;
   };
   rc = root();
+  if (rc) drain();
   for (int g = 1; g < ndev; ++g) { cudaSetDevice(g); cudaStreamSynchronize(ws[g]->st); }
   if (!rc && stats_or_null) {
     uecrt_stats total{};

@@ -17,6 +17,20 @@ def sample_shard(spp, rank, world):
     return lo, hi - lo
 
 
+def item_shard(rank, world):
+    """(shard_index, shard_count) for uecrt_params: rank's equal range of the frame's (pixel, sample) work items.
+    Unlike sample_shard every rank gets the same number of paths (to within one), whatever spp is."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return (rank, world) if world > 1 else (0, 0)
+
+
+def item_range(total_items, index, count):
+    """[lo, hi) of shard `index` of `count` over `total_items` work items -- the rule uecrt_api.cu applies."""
+    q, r = divmod(total_items, count)
+    return q * index + r * index // count, q * (index + 1) + r * (index + 1) // count
+
+
 def reduce_accum(accum, dst=0):
     """Sum the per-rank accumulation tensors onto `dst` (in place there). No-op for world size 1."""
     import torch.distributed as dist
