@@ -12,7 +12,7 @@ CSRC = $(PKG)/csrc
 HOST = $(PKG)/host
 BUILD = build
 
-all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface $(BUILD)/test_tc_pack $(BUILD)/test_grid_build
+all: $(PKG)/libuecrt.so $(PKG)/bin/raytrace $(BUILD)/test_yk_surface $(BUILD)/test_yk_raytracer $(BUILD)/test_tc_pack $(BUILD)/test_grid_build
 
 $(BUILD)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh $(CSRC)/closest_hit.cuh $(CSRC)/materials.cuh $(CSRC)/philox.cuh $(CSRC)/tc_scan.cuh $(CSRC)/tc_collect.cuh $(CSRC)/grid_walk.cuh include/uecrt.h
 	@mkdir -p $(BUILD)
@@ -33,6 +33,10 @@ $(PKG)/bin/raytrace: $(HOST)/raytrace.cpp $(HOST)/cli_options.hpp $(HOST)/png_wr
 
 # C++ test of the yk:: host surface (run by tests/test_cpp_surface.py)
 $(BUILD)/test_yk_surface: tests/cpp/test_yk_surface.cpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so
+	$(HOSTCXX) -std=c++20 -O1 -I$(HOST) $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
+# reference-named headers + raytracer::ray_color + hittable_list::scatter on the mirror (GPU; run by tests/test_cpp_surface.py)
+$(BUILD)/test_yk_raytracer: tests/cpp/test_yk_raytracer.cpp $(wildcard $(HOST)/yk/*.hpp) $(PKG)/libuecrt.so
 	$(HOSTCXX) -std=c++20 -O1 -I$(HOST) $< -o $@ -L$(PKG) -luecrt -lz -Wl,-rpath,'$$ORIGIN/../$(PKG)'
 
 # host-only check of the tensor-scan operand packing and its error bound (run by tests/test_cpp_surface.py)

@@ -188,6 +188,11 @@ int uecrt_accumulate_device(uecrt_ctx* ctx, const uecrt_params* params, float* d
 /* K3: to_color3b (source.cpp:73-83): d_accum (sum, any .w) / spp -> sqrt -> clamp -> *256 */
 int uecrt_resolve_device(const float* d_accum, uint32_t width, uint32_t height, uint32_t spp,
                          uint8_t* d_rgb, void* cuda_stream);
+/* uecrt_primary_hits against the context's resident scene: no scene upload, no allocation once the context's scratch
+ * has grown to the batch size.  What yk::hittable_list::hit (host/yk/hittable_list.hpp) calls, ray by ray or batched. */
+int uecrt_ctx_primary_hits(uecrt_ctx* ctx, uint64_t n_rays, const float* o_xyz, const float* d_xyz,
+                           double t_min, double t_max, int exact, double* t, double* n_xyz, int32_t* id,
+                           uint8_t* front_face);
 /* statistics of the last uecrt_accumulate_device on ctx (blocks on the stream's events) */
 int uecrt_ctx_stats(uecrt_ctx* ctx, uecrt_stats* out);
 

@@ -21,6 +21,18 @@ def test_yk_surface_gpu():
     assert r.returncode == 0 and r.stdout.split("\n")[:2] == ["cpu checks ok", "gpu checks ok"], r.stdout + r.stderr
 
 
+RT = os.path.join(ROOT, "build", "test_yk_raytracer")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RT), reason="build/test_yk_raytracer not built (make)")
+def test_yk_raytracer_and_reference_header_names_gpu():
+    """source.cpp:100-112 + world.hit / scatter<U> / raytracer::ray_color compiled against the mirror under the reference's
+    header names; SURVEY App. B known answers incl. ray_color(centre, mt19937(7)) (tests/cpp/test_yk_raytracer.cpp)."""
+    r = subprocess.run([RT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("yk raytracer ok"), r.stdout + r.stderr
+
+
 TC = os.path.join(ROOT, "build", "test_tc_pack")
 
 

@@ -100,6 +100,27 @@ def test_sample_shards_add_up(u):
     assert np.abs(other[..., :3] - full[..., :3]).mean() > 1e-3     # a different seed is a different image
 
 
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_item_shards_add_up(u, parts):
+    """Work-item sharding (uecrt_params.shard_index / shard_count, what every rank of an N-GPU run renders): the
+    shards' buffers sum to the unsharded frame, every pixel gets every sample exactly once, and the shards trace the
+    same number of paths to within one."""
+    sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
+    W, S = 100, 7                                   # ragged 8x4 tile grid, spp not divisible by the shard count
+    H = u.image_height(W)
+    _, full, st = u.render(sc, c, W, S, 50, seed=5, return_accum=True)
+    acc, paths, rays = np.zeros_like(full), [], 0
+    for i in range(parts):
+        _, a, s_ = u.render(sc, c, W, S, 50, seed=5, return_accum=True, shard=(i, parts))
+        acc += a; paths.append(s_["paths"]); rays += s_["rays_traced"]
+    assert np.all(acc[..., 3] == S) and sum(paths) == W * H * S and rays == st["rays_traced"]
+    slots = ((W + 7) // 8) * ((H + 3) // 4) * 32    # pixel slots of the tile grid, incl. the ragged edge
+    assert max(paths) - min(paths) <= slots * S // parts - (W * H * S) // parts + parts + 64   # equal up to the edge slots
+    np.testing.assert_allclose(acc[..., :3], full[..., :3], rtol=2e-5, atol=1e-5)
+    with pytest.raises(u.UecrtError):
+        u.render(sc, c, W, S, 50, seed=5, shard=(parts, parts))
+
+
 @pytest.mark.parametrize("W", [17, 36, 100])
 def test_ragged_tile_edges(u, oracle, W):
     """Work items are laid out on a grid of 8x4-pixel tiles; widths / heights that are not multiples of

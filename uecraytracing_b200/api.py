@@ -174,6 +174,17 @@ class Context:
         check(lib.uecrt_accumulate_device(self._h, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(stream), None),
               "uecrt_accumulate_device")
 
+    def primary_hits(self, o, d, t_min=0.001, t_max=float("inf"), exact=True):
+        """Closest hits of caller rays against this context's resident scene (uecrt_ctx_primary_hits)."""
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = len(o)
+        t = np.zeros(n, np.float64); nrm = np.zeros((n, 3), np.float64)
+        idx = np.zeros(n, np.int32); ff = np.zeros(n, np.uint8)
+        check(lib.uecrt_ctx_primary_hits(self._h, n, _ptr(o), _ptr(d), t_min, t_max, 1 if exact else 0, _ptr(t), _ptr(nrm),
+                                         _ptr(idx), _ptr(ff)), "uecrt_ctx_primary_hits")
+        return t, nrm, idx, ff
+
     def stats(self):
         st = StatsStruct()
         check(lib.uecrt_ctx_stats(self._h, C.byref(st)), "uecrt_ctx_stats")

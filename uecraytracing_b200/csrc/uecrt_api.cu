@@ -133,6 +133,9 @@ struct uecrt_ctx {
   size_t cap_tc = 0;
   void* d_quads = nullptr;
   size_t cap_quads = 0;
+  // grow-only scratch of uecrt_ctx_primary_hits (rays in, hit records out)
+  void* d_hits = nullptr;
+  size_t cap_hits = 0;
   size_t smem_tc = 0;
   int regs_tc = 0;
   // uniform grid (grid_build.hpp): built and uploaded on first use of UECRT_SCAN_GRID with the current scene
@@ -249,7 +252,7 @@ void ctx_free(uecrt_ctx* c) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
-  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc); cudaFree(c->d_quads);
+  cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc); cudaFree(c->d_quads); cudaFree(c->d_hits);
   cudaFree(c->d_cell_start); cudaFree(c->d_items); cudaFree(c->d_always);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -757,41 +760,60 @@ int uecrt_tensor_scan_max_spheres(void) { return 65534; }
 int uecrt_tensor_scan_resident_spheres(void) { return uecrt::tc_resident_max_spheres(); }
 void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store((rays == 2 && uecrt::max_rays_per_thread() == 2) ? 2 : 1); }
 
+// closest hits of caller rays against the context's scene; the device scratch lives in the context (grow-only)
+static int ctx_primary_hits(uecrt_ctx* c, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min, double t_max,
+                            int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
+  if (n_rays == 0) return UECRT_OK;
+  if (!o_xyz || !d_xyz || !t || !n_xyz || !id || !front_face) return fail(UECRT_ERR_INVALID, "null argument");
+  // one allocation: [o: 3 f32][d: 3 f32][t: f64][n: 3 f64][id: i32][ff: u8] per ray, each array 256-byte aligned
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t so = up(n_rays * 12), sd = so, st_ = up(n_rays * 8), sn = up(n_rays * 24), si = up(n_rays * 4), sf = up(n_rays);
+  const size_t need = so + sd + st_ + sn + si + sf;
+  if (need > c->cap_hits) {
+    cudaFree(c->d_hits); c->d_hits = nullptr; c->cap_hits = 0;
+    CUDA_TRY(cudaMalloc(&c->d_hits, need));
+    c->cap_hits = need;
+  }
+  char* base = static_cast<char*>(c->d_hits);
+  float* d_o = reinterpret_cast<float*>(base); float* d_d = reinterpret_cast<float*>(base + so);
+  double* d_t = reinterpret_cast<double*>(base + so + sd); double* d_n = reinterpret_cast<double*>(base + so + sd + st_);
+  int32_t* d_id = reinterpret_cast<int32_t*>(base + so + sd + st_ + sn); uint8_t* d_ff = reinterpret_cast<uint8_t*>(base + so + sd + st_ + sn + si);
+  CUDA_TRY(cudaMemcpy(d_o, o_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_d, d_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+  int mode = 0;
+  if (rc_mode(0, c, &mode)) return UECRT_ERR_INVALID;
+  if (mode == UECRT_SCAN_GRID) {
+    int r = ctx_ensure_grid(c);
+    if (r) return r;
+    uecrt::launch_primary_hits_grid(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
+  } else if (mode == UECRT_SCAN_TENSOR) uecrt::launch_primary_hits_tc(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, c->sm_count, 0);
+  else uecrt::launch_primary_hits(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(t, d_t, n_rays * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(n_xyz, d_n, n_rays * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(id, d_id, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(front_face, d_ff, n_rays, cudaMemcpyDeviceToHost));
+  return UECRT_OK;
+}
+
+int uecrt_ctx_primary_hits(uecrt_ctx* ctx, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
+                           double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
+  if (!ctx) return fail(UECRT_ERR_INVALID, "ctx is null");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != ctx->device) return fail(UECRT_ERR_INVALID, "context lives on device %d, current device is %d", ctx->device, dev);
+  return ctx_primary_hits(ctx, n_rays, o_xyz, d_xyz, t_min, t_max, exact, t, n_xyz, id, front_face);
+}
+
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
                        double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
   int rc = require_device();
   if (rc) return rc;
   if (n_rays == 0) return UECRT_OK;
-  if (!o_xyz || !d_xyz || !t || !n_xyz || !id || !front_face) return fail(UECRT_ERR_INVALID, "null argument");
   uecrt_ctx* c = nullptr;
   if ((rc = ctx_create_on_current_device(scene, nullptr, &c))) return rc;
-  float *d_o = nullptr, *d_d = nullptr;
-  double *d_t = nullptr, *d_n = nullptr;
-  int32_t* d_id = nullptr;
-  uint8_t* d_ff = nullptr;
-  auto body = [&]() -> int {
-    CUDA_TRY(cudaMalloc(&d_o, n_rays * 3 * sizeof(float))); CUDA_TRY(cudaMalloc(&d_d, n_rays * 3 * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&d_t, n_rays * sizeof(double))); CUDA_TRY(cudaMalloc(&d_n, n_rays * 3 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&d_id, n_rays * sizeof(int32_t))); CUDA_TRY(cudaMalloc(&d_ff, n_rays));
-    CUDA_TRY(cudaMemcpy(d_o, o_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_d, d_xyz, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    int mode = 0;
-    if (rc_mode(0, c, &mode)) return UECRT_ERR_INVALID;
-    if (mode == UECRT_SCAN_GRID) {
-      int r = ctx_ensure_grid(c);
-      if (r) return r;
-      uecrt::launch_primary_hits_grid(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
-    } else if (mode == UECRT_SCAN_TENSOR) uecrt::launch_primary_hits_tc(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, c->sm_count, 0);
-    else uecrt::launch_primary_hits(c->sc, n_rays, d_o, d_d, t_min, t_max, exact != 0, d_t, d_n, d_id, d_ff, 0);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(t, d_t, n_rays * sizeof(double), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(n_xyz, d_n, n_rays * 3 * sizeof(double), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(id, d_id, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(front_face, d_ff, n_rays, cudaMemcpyDeviceToHost));
-    return UECRT_OK;
-  };
-  rc = body();
-  cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_n); cudaFree(d_id); cudaFree(d_ff);
+  rc = ctx_primary_hits(c, n_rays, o_xyz, d_xyz, t_min, t_max, exact, t, n_xyz, id, front_face);
   ctx_free(c);
   return rc;
 }

@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include "../../../include/uecrt.h"
+#include "ray.hpp"
 #include "vec3.hpp"
 
 namespace yk {

@@ -55,11 +55,4 @@ template <class T, class A> constexpr vec3<T, A> reflect(const vec3<T, A>& v, co
 using vec3d = vec3<double>;
 template <class T, class Tag> using pos3 = vec3<T, Tag>;
 
-template <class T>
-struct ray {   // yk/ray.hpp:10-20
-  pos3<T, world_tag> origin;
-  vec3<T> direction;
-  constexpr pos3<T, world_tag> at(T t) const { return origin + direction * t; }
-};
-
 }  // namespace yk
