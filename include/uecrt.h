@@ -170,6 +170,13 @@ int uecrt_scatter(uint64_t n, const uint32_t* mat_type, const uecrt_float4* mat_
                   const uint8_t* front_face, const float* uniforms4, uint8_t* scattered,
                   float* attenuation_rgb, float* o_out_xyz, float* d_out_xyz);
 
+/* Test hook for the tensor-core candidate scan's SUPERSET guarantee: runs the scan alone on caller rays and reports its
+ * verdict before any resolve.  flags_out[i * n + j] != 0 iff the scan flagged sphere j for ray i; the scan flags whole
+ * groups of *spheres_per_flag_out consecutive spheres (1 or 4), so j's flag is its group's.  Every sphere whose reference
+ * discriminant (sphere.hpp:27-32, in double on the same float inputs) is >= 0 must be flagged. */
+int uecrt_debug_tensor_candidates(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz,
+                                  const float* d_xyz, uint8_t* flags_out, int32_t* spheres_per_flag_out);
+
 /* Philox4x32-10 block for (key = seed, counter = {c0,c1,c2,c3}), computed on the device. */
 int uecrt_philox(uint64_t n, uint64_t seed, const uint32_t* counters4, uint32_t* out4);
 

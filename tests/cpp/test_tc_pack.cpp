@@ -5,7 +5,7 @@
 //   2. the canonical-layout byte offsets place row r, chunk c where the UMMA descriptor expects them;
 //   3. the conservative-superset property: whenever the reference's double-precision discriminant
 //      (sphere.hpp:27-32) is >= 0, the emulated accumulator G = a.b is > 0 by at least the part of
-//      the bound reserved for the hardware's accumulation error (24 u S).
+//      the bound reserved for the hardware's accumulation error (80 u S).
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -73,7 +73,7 @@ int main() {
     const float od = std::fmaf(oz, dz, std::fmaf(oy, dy, ox * dx));
     const float nqx = 2.0f * std::fmaf(od, dx, -ox), nqy = 2.0f * std::fmaf(od, dy, -oy), nqz = 2.0f * std::fmaf(od, dz, -oz);
     const float oo = std::fmaf(oz, oz, std::fmaf(oy, oy, ox * ox));
-    const float P = std::fmaf(-od, od, oo) - oo * (80.0f * 5.9604644775390625e-8f);
+    const float P = std::fmaf(-od, od, oo) - oo * (208.0f * 5.9604644775390625e-8f);
     const float a[tc::kTerms] = {dx * dx, dy * dy, dz * dz, 2.0f * dx * dy, 2.0f * dx * dz, 2.0f * dy * dz, nqx, nqy, nqz, 1.0f};
     float arow[tc::kSlots];
     tc::fill_row_a(a, P, arow);
@@ -90,7 +90,7 @@ int main() {
       ++tested;
       if (disc >= 0) {
         ++hits;
-        const double margin = G - 24.0 * u * S;      // what is left after the hardware's share of the bound
+        const double margin = G - 80.0 * u * S;      // what is left after the hardware's share of the bound (truncating-adder model, scene_pack.hpp)
         if (margin < min_margin) min_margin = margin;
         if (!(margin > 0)) { std::printf("superset violated: ray %d sphere %u disc %.3e G %.3e S %.3e\n", it, n, disc, G, S); return 1; }
       }

@@ -65,8 +65,9 @@ int main() {
     CHECK(one.has_value() == batch[i].has_value() && one.has_value() == (ka[i].id >= 0));
     if (!one) continue;
     CHECK(one->id == (std::size_t)ka[i].id && batch[i]->id == one->id && one->front_face && one->t == batch[i]->t);
-    CHECK(std::fabs(one->t - ka[i].t) <= 1e-9 * ka[i].t);
-    CHECK(std::fabs(one->normal.x - ka[i].nx) < 1e-8 && std::fabs(one->normal.y - ka[i].ny) < 1e-8 && std::fabs(one->normal.z - ka[i].nz) < 1e-8);
+    // the ABI takes float rays: App. B's double directions (e.g. -0.8888888888888888) are rounded to float on the way in
+    CHECK(std::fabs(one->t - ka[i].t) <= 2e-7 * ka[i].t);
+    CHECK(std::fabs(one->normal.x - ka[i].nx) < 2e-7 && std::fabs(one->normal.y - ka[i].ny) < 2e-7 && std::fabs(one->normal.z - ka[i].nz) < 2e-7);
   }
   // a single sphere is hittable on its own (sphere.hpp:25-48): closed interval, far root (App. B, probe C.9)
   const auto s = sphere(pos3<T, world_tag>(0, 0, -1.5), 0.5, lambertian<double>({0.5, 0.5, 0.5}));

@@ -332,6 +332,64 @@ int main(int argc, char** argv) {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
   }
 
+  // ------------------------------------------------------------------ T5 accumulation error of the MMA itself, adversarial operands
+  // Operands that are already TF32-exact (no split error): what remains is how tcgen05.mma.kind::tf32 sums 32 exact
+  // products (four chained K = 8 steps into an FP32 accumulator in TMEM).  Families of rows / columns:
+  //   0 same sign, equal magnitude, full 11-bit mantissas     1 one dominant slot (2^12 x the rest)
+  //   2 alternating signs, equal magnitude (sum ~ 0, S large) 3 geometric spread 2^-k      4 random signs and exponents
+  // err / (u S), u = 2^-24, S = sum |a_k b_k|, maximum per (row family, column family).
+  if (which & 16) {
+    srand(777);
+    const int N = 640, GROUPS_TOTAL = 320, M = GROUPS_TOTAL * 128, F = 5;
+    auto tf = [](double mant01, int e, int sign) {   // TF32-exact: 1.xxxxxxxxxx (10 fraction bits) x 2^e
+      const double m = 1.0 + floor(mant01 * 1024.0) / 1024.0;
+      return (float)(sign * ldexp(m, e));
+    };
+    auto fill = [&](float* row, int fam) {
+      for (int k = 0; k < kSlots; ++k) {
+        switch (fam) {
+          case 0: row[k] = tf(urand(), 0, 1); break;
+          case 1: row[k] = tf(urand(), k == 5 ? 6 : 0, 1); break;
+          case 2: row[k] = tf(urand(), 0, (k & 1) ? -1 : 1); break;
+          case 3: row[k] = tf(urand(), -(k / 2), 1); break;
+          default: row[k] = tf(urand(), (int)(urand() * 12) - 6, urand() < 0.5 ? -1 : 1); break;
+        }
+      }
+    };
+    std::vector<float> arow((size_t)M * kSlots), brow((size_t)N * kSlots);
+    for (int i = 0; i < M; ++i) fill(&arow[(size_t)i * kSlots], i % F);
+    for (int n = 0; n < N; ++n) fill(&brow[(size_t)n * kSlots], n % F);
+    std::vector<unsigned char> Bp; pack_b(brow, N, Bp);
+    float* dA; unsigned char* dB; float* dD;
+    CK(cudaMalloc(&dA, arow.size() * 4)); CK(cudaMalloc(&dB, Bp.size())); CK(cudaMalloc(&dD, (size_t)M * N * 4));
+    CK(cudaMemcpy(dA, arow.data(), arow.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, Bp.data(), Bp.size(), cudaMemcpyHostToDevice));
+    ProbeArgs a{dA, dB, dD, nullptr, N, 1, 0, kLBO, kSBO};
+    run<4>(a, GROUPS_TOTAL / 4);
+    std::vector<float> D((size_t)M * N);
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    const double u = ldexp(1.0, -24);
+    double worst[F][F] = {}, worst_rel_sum[F][F] = {};
+    long above = 0, below = 0;   // sign of the error: truncation toward zero / -inf shows as a bias
+    for (int i = 0; i < M; ++i)
+      for (int n = 0; n < N; ++n) {
+        double e = 0, S = 0;
+        for (int k = 0; k < kSlots; ++k) { const double t = (double)arow[(size_t)i * kSlots + k] * brow[(size_t)n * kSlots + k]; e += t; S += fabs(t); }
+        const double d = (double)D[(size_t)i * N + n] - e;
+        const double kS = fabs(d) / (u * S);
+        if (kS > worst[i % F][n % F]) worst[i % F][n % F] = kS;
+        const double kR = fabs(d) / (u * fmax(fabs(e), 1e-300));
+        if (S < 1.0001 * fabs(e) && kR > worst_rel_sum[i % F][n % F]) worst_rel_sum[i % F][n % F] = kR;
+        if (d > 0) ++above; else if (d < 0) ++below;
+      }
+    printf("T5 accumulate error, TF32-exact operands, %d x %d pairs; max err / (u S) by (row family, column family):\n", M, N);
+    double all = 0;
+    for (int r = 0; r < F; ++r) { printf("   row family %d:", r); for (int c = 0; c < F; ++c) { printf(" %6.2f", worst[r][c]); if (worst[r][c] > all) all = worst[r][c]; } printf("\n"); }
+    printf("   overall max %.2f u*S; same-sign sums (S = |sum|): max err / (u |sum|) = %.2f; result above exact %ld, below %ld (a truncating adder is always below for positive sums)\n",
+           all, worst_rel_sum[0][0], above, below);
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  }
+
   // ------------------------------------------------------------------ T3 speed
   if (which & 4) {
     const int N = 512, rounds = 2000, blocks = prop.multiProcessorCount;

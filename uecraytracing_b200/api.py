@@ -134,6 +134,17 @@ def primary_hits(scene, o, d, t_min=0.001, t_max=float("inf"), exact=True):
     return t, nrm, idx, ff
 
 
+def tensor_candidates(scene, o, d):
+    """(flags (n_rays, n_spheres) uint8, spheres_per_flag): the tensor-core scan's verdict alone (uecrt_debug_tensor_candidates)."""
+    o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+    flags = np.zeros((len(o), scene.n), np.uint8)
+    q = C.c_int32(0)
+    sc = scene.struct()
+    check(lib.uecrt_debug_tensor_candidates(C.byref(sc), len(o), _ptr(o), _ptr(d), _ptr(flags), C.byref(q)), "uecrt_debug_tensor_candidates")
+    return flags, q.value
+
+
 def scatter(mat_type, mat_param, d_in, p, normal, front_face, uniforms4):
     mt = np.ascontiguousarray(mat_type, np.uint32); n = len(mt)
     mp = np.ascontiguousarray(mat_param, np.float32).reshape(n, 4)

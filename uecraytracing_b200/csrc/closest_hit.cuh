@@ -76,8 +76,9 @@ struct ScanRay {
   float p_low;             // the same lowered P before the clamp (tensor-core scan: subtracted inside the MMA)
 };
 
-// Fraction of |o|^2 by which the ray part of the discriminant bound lowers P (scene_pack.hpp).
-constexpr float kRayBound = 80.0f * 5.9604644775390625e-8f;   // 80 * 2^-24
+// Fraction of |o|^2 by which the ray part of the discriminant bound lowers P (scene_pack.hpp: the FP32 scan needs 62u,
+// the tensor scan 204u; both use this constant).
+constexpr float kRayBound = 208.0f * 5.9604644775390625e-8f;   // 208 * 2^-24
 
 __device__ __forceinline__ ScanRay make_scan_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
   ScanRay s;

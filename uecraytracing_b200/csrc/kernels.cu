@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
                                                                      const float* __restrict__ o, const float* __restrict__ d,
                                                                      double tmin, double tmax, double* __restrict__ t_out,
                                                                      double* __restrict__ n_out, int32_t* __restrict__ id_out,
-                                                                     uint8_t* __restrict__ ff_out) {
+                                                                     uint8_t* __restrict__ ff_out, uint32_t* __restrict__ dbg_words) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t npasses = SWEEP ? (uint32_t)sc.tc_npasses : 1u;
   const int pass_rows = sc.tc_nrows / (int)npasses;
@@ -965,6 +965,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         FastBest best{(float)tmax * dlen, -1};
         for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
           tc::shade_wait(sh, pass_m++);
+          if (dbg_words && has_ray) tc::dump_flags(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), dbg_words + (i * npasses + p) * (unsigned long long)sh.nwords);
           tc::for_each_flag(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
             auto test = [&](int j) { test_fast(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); };
             if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
@@ -983,6 +984,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         ExactBest best{tmax, -1};
         for (uint32_t p = 0, base = 0;; base += (uint32_t)pass_quads) {
           tc::shade_wait(sh, pass_m++);
+          if (dbg_words && has_ray) tc::dump_flags(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), dbg_words + (i * npasses + p) * (unsigned long long)sh.nwords);
           tc::for_each_flag(sh, SWEEP ? 0u : ((pass_m - 1u) & 1u), has_ray, [&](int k) {
             auto test = [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, tmin, best); };
             if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
@@ -1308,6 +1310,7 @@ int tc_sweep_rows(int n) {
   return best_per * tc::kNC;
 }
 int tc_threads() { return tc::kThreads; }
+int tc_quad() { return tc::kQuad; }
 int tc_chunk() { return tc::kNC; }
 size_t tc_smem_bytes(int tc_nrows, int tc_npasses) {
   return tc_npasses > 1 ? tc::make_layout((uint32_t)(tc_nrows / tc_npasses), 2u).total : tc::make_layout((uint32_t)tc_nrows).total;
@@ -1349,16 +1352,16 @@ void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t 
 
 void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d, double tmin,
                             double tmax, bool exact, double* t, double* nrm, int32_t* id, uint8_t* ff, int sm_count,
-                            cudaStream_t st) {
+                            cudaStream_t st, uint32_t* dbg_words) {
   const size_t smem = tc_smem_bytes(sc.tc_nrows, sc.tc_npasses);
   unsigned long long want = (n_rays + tc::kShadeThreads - 1) / tc::kShadeThreads;
   const int blocks = (int)(want < 1 ? 1 : (want > (unsigned long long)sm_count ? (unsigned long long)sm_count : want));
   if (sc.tc_npasses > 1) {
-    if (exact) k_primary_hits_tc<true, true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
-    else k_primary_hits_tc<false, true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+    if (exact) k_primary_hits_tc<true, true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff, dbg_words);
+    else k_primary_hits_tc<false, true><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff, dbg_words);
   } else {
-    if (exact) k_primary_hits_tc<true, false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
-    else k_primary_hits_tc<false, false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff);
+    if (exact) k_primary_hits_tc<true, false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff, dbg_words);
+    else k_primary_hits_tc<false, false><<<blocks, tc::kThreads, smem, st>>>(sc, n_rays, o, d, tmin, tmax, t, nrm, id, ff, dbg_words);
   }
 }
 

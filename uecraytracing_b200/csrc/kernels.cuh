@@ -90,6 +90,7 @@ cudaError_t configure_kernels_tc(int* regs_render, size_t smem);
 void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t smem, cudaStream_t st);
 void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, const float* o, const float* d,
                             double tmin, double tmax, bool exact, double* t, double* nrm, int32_t* id,
-                            uint8_t* ff, int sm_count, cudaStream_t st);
+                            uint8_t* ff, int sm_count, cudaStream_t st, uint32_t* dbg_words = nullptr);
+int tc_quad();               // spheres per candidate-bitmap bit of the tensor scan (1 or 4)
 
 }  // namespace uecrt

@@ -104,6 +104,12 @@ __device__ __forceinline__ void for_each_flag(Shade& s, uint32_t buf, bool live,
   }
 }
 
+// debugging / tests: this ray's bitmap words of the current pass, as the scan warps left them
+__device__ __forceinline__ void dump_flags(const Shade& s, uint32_t buf, uint32_t* out) {
+  const uint32_t* bm = s.bitmap + buf * (uint32_t)((kScanGroups + s.nwords) * kShadeThreads);
+  for (int w = 0; w < s.nwords; ++w) out[w] = bm[(kScanGroups + w) * kShadeThreads];
+}
+
 // Per-ray constants of the quad re-test (the FP32 scan's packed operands, closest_hit.cuh scan_pairs)
 struct QuadRay {
   unsigned long long dx2, dy2, dz2, qx2, qy2, qz2;

@@ -13,8 +13,8 @@
 // K slots of four K=8 MMA steps; the last two slots carry -P (hi, lo) against a sphere-side 1, so
 // the accumulator holds G = f - P and a sphere is a candidate iff G >= 0, i.e. iff the SIGN BIT of
 // the TMEM word is clear.  All products of TF32 values are exact in FP32; what is lost is
-// a_lo*b_lo (<= 2^-22 |a||b|), the truncation of the lo parts (<= 2^-21 each) and the accumulator's
-// own rounding.  The bound on the sum of those is applied exactly like the FP32 scan's bound
+// a_lo*b_lo (<= 2^-22 |a||b|), the rounding of the lo parts (<= 2^-22 each) and the accumulator's
+// own rounding / truncation (bounded in scene_pack.hpp).  The bound on the sum of those is applied exactly like the FP32 scan's bound
 // (scene_pack.hpp): the sphere part raises -k, the ray part lowers P, so {f >= P} stays a SUPERSET
 // of the reference's "discriminant >= 0" and the resolve phase (closest_hit.cuh) is unchanged.
 //
@@ -55,17 +55,18 @@ __host__ __device__ inline uint32_t row_chunk_offset(uint32_t row, uint32_t chun
   return (row >> 3) * kRowGroupBytes + chunk * 128u + (row & 7u) * 16u;
 }
 
-// hi = v rounded to nearest TF32 (11 significant bits), lo = (v - hi) truncated to TF32.
-// v - hi is exact in FP32 (Sterbenz-like: hi is v with the low bits rounded away).
+// hi = v rounded to nearest TF32 (11 significant bits), lo = (v - hi) rounded to nearest TF32 as well.
+// v - hi is exact in FP32 (hi is v with the low bits rounded away) and |v - hi| <= 2^-11 |v|; rounding it to 11 bits
+// leaves |v - hi - lo| <= 2^-11 * 2^-11 |v| = 4u |v| (u = 2^-24; truncating it, as round 1 did, leaves 8u |v|).
 __host__ __device__ inline void split_tf32(float v, float& hi, float& lo) {
 #ifdef __CUDA_ARCH__
   const uint32_t b = __float_as_uint(v);
   hi = __uint_as_float((b + 0x1000u) & 0xffffe000u);
-  lo = __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
 #else
   union { float f; uint32_t u; } x, y;
   x.f = v; x.u = (x.u + 0x1000u) & 0xffffe000u; hi = x.f;
-  y.f = v - hi; y.u &= 0xffffe000u; lo = y.f;
+  y.f = v - hi; y.u = (y.u + 0x1000u) & 0xffffe000u; lo = y.f;
 #endif
 }
 

@@ -806,6 +806,55 @@ int uecrt_ctx_primary_hits(uecrt_ctx* ctx, uint64_t n_rays, const float* o_xyz, 
   return ctx_primary_hits(ctx, n_rays, o_xyz, d_xyz, t_min, t_max, exact, t, n_xyz, id, front_face);
 }
 
+// Test hook: the tensor-core pre-filter's verdict on caller rays, before any resolve.  flags_out[i * n + j] = 1 iff the
+// scan flagged sphere j for ray i (with one bit per quad: iff it flagged j's quad).
+int uecrt_debug_tensor_candidates(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz,
+                                  uint8_t* flags_out, int32_t* spheres_per_flag_out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (spheres_per_flag_out) *spheres_per_flag_out = uecrt::tc_quad();
+  if (n_rays == 0) return UECRT_OK;
+  if (!scene || !o_xyz || !d_xyz || !flags_out) return fail(UECRT_ERR_INVALID, "null argument");
+  uecrt_ctx* c = nullptr;
+  if ((rc = ctx_create_on_current_device(scene, nullptr, &c))) return rc;
+  float *d_o = nullptr, *d_d = nullptr;
+  double *d_t = nullptr, *d_n = nullptr;
+  int32_t* d_id = nullptr;
+  uint8_t* d_ff = nullptr;
+  uint32_t* d_w = nullptr;
+  const int bits_per_pass = c->sc.tc_nrows / c->sc.tc_npasses / uecrt::tc_quad();
+  const size_t words_per_ray = (size_t)c->sc.tc_npasses * (bits_per_pass / 32);
+  std::vector<uint32_t> words(n_rays * words_per_ray);
+  auto body = [&]() -> int {
+    if (!c->sc.tc_rows) return fail(UECRT_ERR_INVALID, "no tensor-scan operand for this scene");
+    CUDA_TRY(cudaMalloc(&d_o, n_rays * 12)); CUDA_TRY(cudaMalloc(&d_d, n_rays * 12));
+    CUDA_TRY(cudaMalloc(&d_t, n_rays * 8)); CUDA_TRY(cudaMalloc(&d_n, n_rays * 24));
+    CUDA_TRY(cudaMalloc(&d_id, n_rays * 4)); CUDA_TRY(cudaMalloc(&d_ff, n_rays));
+    CUDA_TRY(cudaMalloc(&d_w, words.size() * 4));
+    CUDA_TRY(cudaMemset(d_w, 0, words.size() * 4));
+    CUDA_TRY(cudaMemcpy(d_o, o_xyz, n_rays * 12, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_d, d_xyz, n_rays * 12, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+    uecrt::launch_primary_hits_tc(c->sc, n_rays, d_o, d_d, 0.001, 1e300, false, d_t, d_n, d_id, d_ff, c->sm_count, 0, d_w);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(words.data(), d_w, words.size() * 4, cudaMemcpyDeviceToHost));
+    return UECRT_OK;
+  };
+  rc = body();
+  cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_n); cudaFree(d_id); cudaFree(d_ff); cudaFree(d_w);
+  if (!rc) {
+    const uint32_t n = scene->n, q = (uint32_t)uecrt::tc_quad();
+    for (uint64_t i = 0; i < n_rays; ++i)
+      for (uint32_t j = 0; j < n; ++j) {
+        const uint32_t bit = j / q, pass = bit / (uint32_t)bits_per_pass, b = bit % (uint32_t)bits_per_pass;
+        const uint32_t w = words[i * words_per_ray + pass * (bits_per_pass / 32) + b / 32];
+        flags_out[i * n + j] = (w >> (31u - (b & 31u))) & 1u;
+      }
+  }
+  ctx_free(c);
+  return rc;
+}
+
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz, double t_min,
                        double t_max, int exact, double* t, double* n_xyz, int32_t* id, uint8_t* front_face) {
   int rc = require_device();
