@@ -147,6 +147,15 @@ void uecrt_set_rays_per_thread(int rays);
  * operand (128 B per sphere) resident in shared memory; above that it sweeps it through shared memory in
  * 512-sphere slices, up to uecrt_tensor_scan_max_spheres() (the scene size limit). */
 void uecrt_set_scan_mode(int uecrt_scan_mode);
+/* Which pipeline K1 runs the tensor-core scan with when the sphere operand is resident in shared memory:
+ *   UECRT_TENSOR_PIPELINE_SELF      (default) every shade warp reads the TMEM accumulators of its own rays
+ *                                   (csrc/tc_self.cuh: 6 groups of 128 paths, 3 accumulator lanes, 3 issuer warps);
+ *   UECRT_TENSOR_PIPELINE_SCANWARPS dedicated scan warps hand candidate bitmaps to the shade warps through shared
+ *                                   memory (csrc/tc_scan.cuh; always used for swept operands and by uecrt_primary_hits).
+ * Both trace exactly the same rays.  The environment variable UECRT_TC_PIPELINE=self|scanwarps sets the process
+ * default; this call overrides it. */
+enum { UECRT_TENSOR_PIPELINE_SCANWARPS = 0, UECRT_TENSOR_PIPELINE_SELF = 1 };
+void uecrt_set_tensor_pipeline(int uecrt_tensor_pipeline);
 int uecrt_tensor_scan_max_spheres(void);
 int uecrt_tensor_scan_resident_spheres(void);
 

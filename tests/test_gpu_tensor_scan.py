@@ -279,7 +279,8 @@ def test_render_identical_to_fp32_scan(u, name, cam, W, spp, exact):
 def test_auto_mode_uses_tensor_scan_and_stats(u):
     sc, c = u.Scene.named("final", seed=1), u.Camera.named("final")
     _, _, st = u.render(sc, c, 200, 8, 50, seed=2)
-    assert st["scan_mode"] == 2 and st["k1_threads"] == 768 and st["k1_blocks"] == st["sm_count"]
+    # resident operand: the self-scan pipeline (csrc/tc_self.cuh), 6 groups of 128 paths + the issuer warpgroup
+    assert st["scan_mode"] == 2 and st["k1_threads"] == 896 and st["k1_blocks"] == st["sm_count"]
     assert st["rays_traced"] > st["paths"] == 200 * u.image_height(200) * 8
     _, _, st4 = u.render(u.Scene.named("ref4", seed=1), u.Camera.named("ref"), 200, 8, 50, seed=2)
     assert st4["scan_mode"] == 1           # below 96 spheres the FP32 scan is faster and the automatic mode uses it
@@ -312,3 +313,28 @@ def test_depth_and_sample_shards(u):
     _, whole, _ = u.render(sc, c, 160, 24, 50, seed=5, return_accum=True, scan="tensor")
     parts = [u.render(sc, c, 160, 24, 50, seed=5, return_accum=True, scan="tensor", sample_begin=b, sample_count=8)[1] for b in (0, 8, 16)]
     assert np.abs(sum(parts) - whole).max() <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("name,cam,n", [("final", "final", None), ("dense", "dense", 130), ("dense", "dense", 1100)])
+def test_both_tensor_pipelines_trace_the_same_paths(u, name, cam, n, exact):
+    """The self-scan pipeline (every shade warp reads its own accumulators, csrc/tc_self.cuh) and the scan-warp pipeline
+    (csrc/tc_scan.cuh) are two schedules of the same candidate scan: same flags, same resolve, same Philox streams, so
+    every path takes the same bounces; only the order of the atomic adds into the accumulation buffer differs."""
+    sc = u.Scene.named(name, seed=1) if n is None else u.Scene.named(name, seed=1, n=n)
+    c = u.Camera.named(cam)
+    out = {}
+    try:
+        for p in ("self", "scanwarps"):
+            u.set_tensor_pipeline(p)
+            out[p] = u.render(sc, c, 240, 12, 50, seed=5, exact=exact, return_accum=True, scan="tensor")
+    finally:
+        u.set_tensor_pipeline("self")
+    (ra, aa, sa), (rb, ab, sb) = out["self"], out["scanwarps"]
+    resident_self = sc.n <= 1152
+    assert sa["k1_threads"] == (896 if resident_self else 768) and sb["k1_threads"] == 768
+    assert sa["rays_traced"] == sb["rays_traced"] and sa["paths"] == sb["paths"] == 240 * u.image_height(240) * 12
+    assert np.array_equal(aa[..., 3], ab[..., 3]) and np.all(aa[..., 3] == 12)
+    assert np.abs(aa[..., :3] - ab[..., :3]).max() <= 1e-4 * 12
+    assert (ra != rb).mean() < 1e-4

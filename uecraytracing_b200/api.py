@@ -246,6 +246,11 @@ def set_scan_mode(mode):
     lib.uecrt_set_scan_mode({"auto": SCAN_AUTO, "fp32": SCAN_FP32, "tensor": SCAN_TENSOR, "grid": SCAN_GRID}[mode])
 
 
+def set_tensor_pipeline(name):
+    """'self' | 'scanwarps': K1 pipeline of the resident tensor-core scan (include/uecrt.h UECRT_TENSOR_PIPELINE_*)."""
+    lib.uecrt_set_tensor_pipeline({"scanwarps": 0, "self": 1}[name])
+
+
 def tensor_scan_max_spheres():
     return int(lib.uecrt_tensor_scan_max_spheres())
 

@@ -26,6 +26,9 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
 
 #include "closest_hit.cuh"
 #include "kernels.cuh"
@@ -33,6 +36,7 @@
 #include "philox.cuh"
 #include "grid_walk.cuh"
 #include "tc_collect.cuh"
+#include "tc_self.cuh"
 
 namespace uecrt {
 
@@ -680,13 +684,14 @@ __device__ __forceinline__ void tc_quad_s(uint32_t s_quads, int quad, const tc::
     test(4 * quad + j);
   }
 }
-template <bool EXACT>
-__device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint32_t s_quads, uint32_t s_geom, const RayQuery& q, Hit& h) {
+// fe(f): calls f(flag index) for every set flag of the ray, ascending, warp-convergently (tc::for_each_flag / ts::for_each_flag)
+template <bool EXACT, class ForEach>
+__device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_quads, uint32_t s_geom, const RayQuery& q, Hit& h) {
   h.id = -1;
   const tc::QuadRay qr = tc::make_quad_ray(make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz));
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
-    tc::for_each_flag(sh, buf, q.live, [&](int k) {
+    fe([&](int k) {
       auto test = [&](int j) { test_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); };
       if (tc::kQuad == 4) tc_quad_s(s_quads, k, qr, test); else test(k);
     });
@@ -699,7 +704,7 @@ __device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint
     ExactBest best{(double)CUDART_INF, -1};
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
-    tc::for_each_flag(sh, buf, q.live, [&](int k) {
+    fe([&](int k) {
       auto test = [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); };
       if (tc::kQuad == 4) tc_quad_s(s_quads, k, qr, test); else test(k);
     });
@@ -715,6 +720,10 @@ __device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint
       h.nx = (float)nx; h.ny = (float)ny; h.nz = (float)nz;
     }
   }
+}
+template <bool EXACT>
+__device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint32_t s_quads, uint32_t s_geom, const RayQuery& q, Hit& h) {
+  tc_collect_hit_with<EXACT>([&](auto&& f) { tc::for_each_flag(sh, buf, q.live, f); }, s_quads, s_geom, q, h);
 }
 
 // SHADE role of K1, resident operand: TWO independent paths per thread.  While the tile that carries path Q goes
@@ -913,6 +922,105 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
     }
   }
   tc::cta_teardown(tmem_base);
+}
+
+// K1, tensor-core scan, SELF-SCAN pipeline (tc_self.cuh): resident operand, one path per shade thread, every shade warp
+// reads the accumulators of its own rays.  Same path loop, same work queue, same tests as k_render_paths_tc.
+template <bool EXACT>
+__device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
+  ts::Header* hdr = reinterpret_cast<ts::Header*>(smem_raw);
+  ts::Shade sh = ts::make_shade(smem_raw, tmem_base, nchunks);
+  const ts::Layout lay = ts::make_layout((uint32_t)nchunks * ts::kNC);
+  const uint32_t s_quads = tc::smem_addr(smem_raw + lay.quads), s_geom = tc::smem_addr(smem_raw + lay.geom);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long n_pixels = a.n_slots;
+  const double inv_np = 1.0 / (double)n_pixels;
+  const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
+  unsigned n_rays = 0, n_paths = 0;
+  TcProf prof{};
+#ifdef UECRT_TC_PROFILE
+  unsigned long long pc_rounds = 0;
+  prof.last = clock64();
+#endif
+  WorkPool pool;
+  pool_init(pool, a, lane);
+  PathState st{};
+  st.dz = 1.f; st.dlen = 1.f; st.self_id = -1;
+  slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
+  uint32_t T = sh.g;                              // this group's tile of the round: T = round * kGroups + group
+  for (uint32_t r = 0; ts::round_continues(hdr, sh.g % (uint32_t)ts::kLanes, r); ++r, T += (uint32_t)ts::kGroups) {
+#ifdef UECRT_TC_PROFILE
+    const long long pc_start = prof.last;
+#endif
+    // termination vote (tc_self.cuh): this warp's flag of this round, stored before its a_ready arrive
+    const bool warp_done = __all_sync(0xffffffffu, st.done);
+    if (lane == 0) hdr->done_flags[r & 7u][threadIdx.x >> 5] = warp_done ? 1 : 0;
+    ts::submit(sh, T, make_scan_ray(st.ox, st.oy, st.oz, st.dx, st.dy, st.dz), st.active);
+    UECRT_TCP(prof, 2)
+#ifdef UECRT_TC_PROFILE
+    ts::scan_tile(sh, T, &prof.t[0]);
+#else
+    ts::scan_tile(sh, T);
+#endif
+    UECRT_TCP(prof, 3)
+    const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
+    Hit h;
+    tc_collect_hit_with<EXACT>([&](auto&& f) { ts::for_each_flag(sh, q.live, f); }, s_quads, s_geom, q, h);
+    UECRT_TCP(prof, 4)
+    if (st.active) {
+      ++n_rays;
+      slot_shade(st, h, a, n_paths);
+    }
+    UECRT_TCP(prof, 5)
+    slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);   // a path that ended: the next one's camera ray
+    UECRT_TCP(prof, 1)
+#ifdef UECRT_TC_PROFILE
+    prof.t[6] += prof.last - pc_start;
+    ++pc_rounds;
+#endif
+  }
+#ifdef UECRT_TC_PROFILE
+  if (lane == 0) {
+    atomicAdd(a.counters + 4, pc_rounds);
+    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + 5 + i, (unsigned long long)prof.t[i]);
+  }
+#endif
+  if (a.count_stats) {
+    unsigned r = n_rays, p = n_paths;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+    if (lane == 0) {
+      atomicAdd(a.counters + 1, (unsigned long long)r);
+      atomicAdd(a.counters + 2, (unsigned long long)p);
+    }
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(ts::kThreads, 1) k_render_paths_ts(const RenderArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nchunks = a.sc.tc_nrows / ts::kNC;
+  const uint32_t tmem_base = ts::cta_setup(smem_raw, a.sc.tc_rows, (uint32_t)a.sc.tc_nrows * 128u);
+  {   // the shade side's tables: quad table and spheres (rows beyond n: never-hit quads, zero spheres)
+    const ts::Layout lay = ts::make_layout((uint32_t)a.sc.tc_nrows);
+    float4* sq = reinterpret_cast<float4*>(smem_raw + lay.quads);
+    float4* sg = reinterpret_cast<float4*>(smem_raw + lay.geom);
+    for (int i = threadIdx.x; i < a.sc.tc_nrows; i += ts::kThreads) {
+      sq[i] = __ldg(&a.sc.tc_quads[i]);
+      sg[i] = i < a.sc.n ? __ldg(&a.sc.geom[i]) : make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+    __syncthreads();
+  }
+  if (ts::is_issuer_thread()) {
+    tc::reg_dealloc<ts::kIssuerRegs>();
+    const uint32_t iw = (uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) - ts::kShadeThreads / 32;   // warp-uniform
+    if (iw < (uint32_t)ts::kLanes) ts::issuer_role(smem_raw, tmem_base, nchunks, iw, a.counters);
+  } else {
+    if (ts::kShadeRegs < ts::kLaunchRegs) tc::reg_dealloc<ts::kShadeRegs>();
+    else if (ts::kShadeRegs > ts::kLaunchRegs) tc::reg_alloc<ts::kShadeRegs>();
+    shade_role_self<EXACT>(a, smem_raw, tmem_base, nchunks);
+  }
+  ts::cta_teardown(tmem_base);
 }
 
 // K2 on the tensor-core scan: every shade thread takes one caller ray per round; all CTAs run the
@@ -1316,6 +1424,32 @@ size_t tc_smem_bytes(int tc_nrows, int tc_npasses) {
   return tc_npasses > 1 ? tc::make_layout((uint32_t)(tc_nrows / tc_npasses), 2u).total : tc::make_layout((uint32_t)tc_nrows).total;
 }
 
+// Which pipeline K1 runs a tensor scan with: 1 = self-scan (tc_self.cuh: resident operand up to ts::kMaxRows rows),
+// 0 = scan warps (tc_scan.cuh / tc_collect.cuh: every scene; always for swept operands and for K2).
+// UECRT_TC_PIPELINE=scanwarps|self in the environment overrides the built-in choice (tuning and tests).
+#ifndef UECRT_TC_SELF_DEFAULT
+#define UECRT_TC_SELF_DEFAULT 1
+#endif
+static std::atomic<int> g_tc_pipeline{-1};      // -1: not set (environment, else the built-in default)
+void tc_set_pipeline(int p) { g_tc_pipeline.store(p == 0 ? 0 : 1); }
+static bool tc_self_enabled() {
+  static const int env = [] {
+    const char* e = getenv("UECRT_TC_PIPELINE");
+    if (e && !strcmp(e, "scanwarps")) return 0;
+    if (e && !strcmp(e, "self")) return 1;
+    return UECRT_TC_SELF_DEFAULT;
+  }();
+  const int v = g_tc_pipeline.load();
+  return (v < 0 ? env : v) != 0;
+}
+static bool tc_use_self(const DeviceScene& sc) { return tc_self_enabled() && sc.tc_npasses == 1 && sc.tc_nrows <= ts::kMaxRows; }
+void tc_render_config(const DeviceScene& sc, int* threads, size_t* smem, int* pipeline) {
+  const bool self = tc_use_self(sc);
+  if (threads) *threads = self ? ts::kThreads : tc::kThreads;
+  if (smem) *smem = self ? ts::make_layout((uint32_t)sc.tc_nrows).total : tc_smem_bytes(sc.tc_nrows, sc.tc_npasses);
+  if (pipeline) *pipeline = self ? 1 : 0;
+}
+
 cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
   cudaError_t e;
   static bool attrs_set[16] = {};
@@ -1328,6 +1462,7 @@ cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
     UECRT_SET((k_primary_hits_tc<false, false>)) UECRT_SET((k_primary_hits_tc<true, false>))
     UECRT_SET((k_render_paths_tc<false, true>)) UECRT_SET((k_render_paths_tc<true, true>))
     UECRT_SET((k_primary_hits_tc<false, true>)) UECRT_SET((k_primary_hits_tc<true, true>))
+    UECRT_SET((k_render_paths_ts<false>)) UECRT_SET((k_render_paths_ts<true>))
 #undef UECRT_SET
     attrs_set[dev] = true;
   }
@@ -1341,7 +1476,11 @@ cudaError_t configure_kernels_tc(int* regs_render, size_t smem) {
 
 void launch_render_paths_tc(const RenderArgs& a, bool exact, int blocks, size_t smem, cudaStream_t st) {
   const bool sweep = a.sc.tc_npasses > 1;
-  if (sweep) {
+  if (tc_use_self(a.sc)) {
+    const size_t smem_self = ts::make_layout((uint32_t)a.sc.tc_nrows).total;
+    if (exact) k_render_paths_ts<true><<<blocks, ts::kThreads, smem_self, st>>>(a);
+    else k_render_paths_ts<false><<<blocks, ts::kThreads, smem_self, st>>>(a);
+  } else if (sweep) {
     if (exact) k_render_paths_tc<true, true><<<blocks, tc::kThreads, smem, st>>>(a);
     else k_render_paths_tc<false, true><<<blocks, tc::kThreads, smem, st>>>(a);
   } else {

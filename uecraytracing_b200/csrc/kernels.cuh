@@ -92,5 +92,8 @@ void launch_primary_hits_tc(const DeviceScene& sc, unsigned long long n_rays, co
                             double tmin, double tmax, bool exact, double* t, double* nrm, int32_t* id,
                             uint8_t* ff, int sm_count, cudaStream_t st, uint32_t* dbg_words = nullptr);
 int tc_quad();               // spheres per candidate-bitmap bit of the tensor scan (1 or 4)
+// K1 launch shape for a tensor scan of this scene; pipeline: 1 = self-scan (tc_self.cuh), 0 = scan warps (tc_scan.cuh)
+void tc_render_config(const DeviceScene& sc, int* threads, size_t* smem, int* pipeline);
+void tc_set_pipeline(int pipeline);
 
 }  // namespace uecrt

@@ -448,8 +448,13 @@ int accumulate(uecrt_ctx* ctx, const uecrt_params* p, float* d_accum, cudaStream
   const int blocks = tensor ? ctx->sm_count : ctx->sm_count * (grid ? ctx->blocks_grid[exact ? 1 : 0] : ctx->blocks_per_sm[exact ? 1 : 0]);
   ctx->last_blocks = blocks;
   ctx->last_scan_mode = mode;
-  ctx->last_threads = tensor ? uecrt::tc_threads() : uecrt::kRenderThreads;
-  ctx->last_smem = tensor ? ctx->smem_tc : grid ? 0 : ctx->smem;
+  ctx->last_threads = uecrt::kRenderThreads;
+  ctx->last_smem = grid ? 0 : ctx->smem;
+  if (tensor) {
+    int thr = 0; size_t sm = 0;
+    uecrt::tc_render_config(a.sc, &thr, &sm, nullptr);
+    ctx->last_threads = thr; ctx->last_smem = sm;
+  }
   ctx->last_regs = tensor ? ctx->regs_tc : grid ? ctx->regs_grid : ctx->regs;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
   if (tensor) uecrt::launch_render_paths_tc(a, exact, blocks, ctx->smem_tc, st);
@@ -501,7 +506,7 @@ int ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) {
     static unsigned long long q[kCounterWords];
     CUDA_TRY(cudaMemcpy(q, ctx->d_counters, sizeof q, cudaMemcpyDeviceToHost));
     if (q[4]) {
-      const char* nm[7] = {"take_next", "prepare_next", "submit", "wait_scan", "resolve", "shade", "total"};
+      const char* nm[7] = {"full_wait", "prepare_next", "submit", "wait_scan", "resolve", "shade", "total"};
       fprintf(stderr, "[tc profile] warp-rounds %llu:", q[4]);
       for (int i = 0; i < 7; ++i) fprintf(stderr, " %s %.0f", nm[i], (double)q[5 + i] / (double)q[4]);
       fprintf(stderr, " cycles/round\n");
@@ -755,6 +760,7 @@ int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_
 
 void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
+void uecrt_set_tensor_pipeline(int p) { uecrt::tc_set_pipeline(p); }
 void uecrt_set_scan_mode(int m) { g_scan_mode.store((m == UECRT_SCAN_FP32 || m == UECRT_SCAN_TENSOR || m == UECRT_SCAN_GRID) ? m : UECRT_SCAN_AUTO); }
 int uecrt_tensor_scan_max_spheres(void) { return 65534; }
 int uecrt_tensor_scan_resident_spheres(void) { return uecrt::tc_resident_max_spheres(); }
