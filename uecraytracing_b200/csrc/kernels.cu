@@ -675,9 +675,10 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
 
 // The collect half alone (resident operand): the ray was submitted one tile earlier, its quad flags are in bitmap buffer `buf`.
 // s_quads / s_geom: shared addresses of the CTA's copies of the quad table and the sphere array (tc_scan.cuh Layout).
+// plane = 0: the table is the global one's copy (64 B per quad); plane > 0: planar copy (tc_collect.cuh quad_candidates_sp)
 template <class Test>
-__device__ __forceinline__ void tc_quad_s(uint32_t s_quads, int quad, const tc::QuadRay& qr, Test&& test) {
-  uint32_t cm = tc::quad_candidates_s(s_quads, quad, qr);
+__device__ __forceinline__ void tc_quad_s(uint32_t s_quads, uint32_t plane, int quad, const tc::QuadRay& qr, Test&& test) {
+  uint32_t cm = plane ? tc::quad_candidates_sp(s_quads, plane, quad, qr) : tc::quad_candidates_s(s_quads, quad, qr);
   while (cm) {
     const int j = __ffs((int)cm) - 1;
     cm &= cm - 1u;
@@ -686,14 +687,14 @@ __device__ __forceinline__ void tc_quad_s(uint32_t s_quads, int quad, const tc::
 }
 // fe(f): calls f(flag index) for every set flag of the ray, ascending, warp-convergently (tc::for_each_flag / ts::for_each_flag)
 template <bool EXACT, class ForEach>
-__device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_quads, uint32_t s_geom, const RayQuery& q, Hit& h) {
+__device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_quads, uint32_t plane, uint32_t s_geom, const RayQuery& q, Hit& h) {
   h.id = -1;
   const tc::QuadRay qr = tc::make_quad_ray(make_scan_ray(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz));
   if (!EXACT) {
     FastBest best{CUDART_INF_F, -1};
     fe([&](int k) {
       auto test = [&](int j) { test_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, q.tmin, q.self_id, best); };
-      if (tc::kQuad == 4) tc_quad_s(s_quads, k, qr, test); else test(k);
+      if (tc::kQuad == 4) tc_quad_s(s_quads, plane, k, qr, test); else test(k);
     });
     if (best.id >= 0) {
       h.id = best.id;
@@ -706,7 +707,7 @@ __device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_qua
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
     fe([&](int k) {
       auto test = [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); };
-      if (tc::kQuad == 4) tc_quad_s(s_quads, k, qr, test); else test(k);
+      if (tc::kQuad == 4) tc_quad_s(s_quads, plane, k, qr, test); else test(k);
     });
     if (best.id >= 0) {
       const float4 g = tc::lds_f4(s_geom + 16u * (uint32_t)best.id);
@@ -723,7 +724,7 @@ __device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_qua
 }
 template <bool EXACT>
 __device__ __forceinline__ void tc_collect_hit(tc::Shade& sh, uint32_t buf, uint32_t s_quads, uint32_t s_geom, const RayQuery& q, Hit& h) {
-  tc_collect_hit_with<EXACT>([&](auto&& f) { tc::for_each_flag(sh, buf, q.live, f); }, s_quads, s_geom, q, h);
+  tc_collect_hit_with<EXACT>([&](auto&& f) { tc::for_each_flag(sh, buf, q.live, f); }, s_quads, 0u, s_geom, q, h);
 }
 
 // SHADE role of K1, resident operand: TWO independent paths per thread.  While the tile that carries path Q goes
@@ -924,6 +925,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   tc::cta_teardown(tmem_base);
 }
 
+#ifndef UECRT_TS_PLANAR
+#define UECRT_TS_PLANAR 0      // 1: planar copy of the quad table in shared memory (fewer bank conflicts, measured SLOWER: 17.05 against 16.65 ms at 100 spp)
+#endif
 // K1, tensor-core scan, SELF-SCAN pipeline (tc_self.cuh): resident operand, one path per shade thread, every shade warp
 // reads the accumulators of its own rays.  Same path loop, same work queue, same tests as k_render_paths_tc.
 template <bool EXACT>
@@ -965,7 +969,7 @@ __device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned ch
     UECRT_TCP(prof, 3)
     const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
     Hit h;
-    tc_collect_hit_with<EXACT>([&](auto&& f) { ts::for_each_flag(sh, q.live, f); }, s_quads, s_geom, q, h);
+    tc_collect_hit_with<EXACT>([&](auto&& f) { ts::for_each_flag(sh, q.live, f); }, s_quads, UECRT_TS_PLANAR ? (uint32_t)nchunks * (ts::kNC * 4u) : 0u, s_geom, q, h);
     UECRT_TCP(prof, 4)
     if (st.active) {
       ++n_rays;
@@ -1005,8 +1009,10 @@ __global__ void __launch_bounds__(ts::kThreads, 1) k_render_paths_ts(const Rende
     const ts::Layout lay = ts::make_layout((uint32_t)a.sc.tc_nrows);
     float4* sq = reinterpret_cast<float4*>(smem_raw + lay.quads);
     float4* sg = reinterpret_cast<float4*>(smem_raw + lay.geom);
+    const int nquads = a.sc.tc_nrows / 4;
     for (int i = threadIdx.x; i < a.sc.tc_nrows; i += ts::kThreads) {
-      sq[i] = __ldg(&a.sc.tc_quads[i]);
+      // global table: float4 4q + k = plane k of quad q; planar copy: plane k at k * nquads (tc_collect.cuh quad_candidates_sp)
+      sq[UECRT_TS_PLANAR ? (i & 3) * nquads + (i >> 2) : i] = __ldg(&a.sc.tc_quads[i]);
       sg[i] = i < a.sc.n ? __ldg(&a.sc.geom[i]) : make_float4(0.f, 0.f, 0.f, 1.f);
     }
     __syncthreads();

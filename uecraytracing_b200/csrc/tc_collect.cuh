@@ -156,6 +156,13 @@ __device__ __forceinline__ uint32_t quad_candidates_s(uint32_t s_quads, int quad
   const uint32_t q = s_quads + 64u * (uint32_t)quad;
   return quad_candidates_v(lds_u64x2(q), lds_u64x2(q + 16u), lds_u64x2(q + 32u), lds_u64x2(q + 48u), r);
 }
+// PLANAR copy of the table: four arrays {-cx[4]}, {-cy[4]}, {-cz[4]}, {nk[4]} of 16 B per quad, `plane` bytes apart.  The
+// lanes of a warp look up different quads: with 64 B per quad every lane's 16 bytes fall on one of TWO bank groups
+// (ncu: 47 % of the kernel's shared-memory wavefronts were bank-conflict replays), with 16 B per quad on one of eight.
+__device__ __forceinline__ uint32_t quad_candidates_sp(uint32_t s_quads, uint32_t plane, int quad, const QuadRay& r) {
+  const uint32_t q = s_quads + 16u * (uint32_t)quad;
+  return quad_candidates_v(lds_u64x2(q), lds_u64x2(q + plane), lds_u64x2(q + 2u * plane), lds_u64x2(q + 3u * plane), r);
+}
 
 // one bit per sphere: 32 accumulators -> one bitmap word, bit (31 - i) = (v[i] >= 0).  Four independent funnel-shift
 // chains (mask = (mask << 1) | sign(v)), merged with byte permutes.
