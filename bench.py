@@ -377,14 +377,16 @@ def report(args, u, scene, st, world, value, ms_per_step, k1_avg, rays, tests, f
     alg = FLOP_PER_TEST * scene.n * rays_per_launch / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
     tensor_scan, grid_scan = st["scan_mode"] == 2, st["scan_mode"] == 3
     swept = tensor_scan and scene.n > u.tensor_scan_resident_spheres()
-    kernel_name = "k_render_paths_tc" if tensor_scan else "k_render_paths_grid" if grid_scan else "k_render_paths"
+    self_scan = tensor_scan and st["k1_threads"] == 896      # csrc/tc_self.cuh: 6 shade groups + the issuer warpgroup
+    kernel_name = "k_render_paths_ts" if self_scan else "k_render_paths_tc" if tensor_scan else "k_render_paths_grid" if grid_scan else "k_render_paths"
     scan_desc = ("tensor cores (tcgen05 TF32 x3 split, TMEM accumulators), sphere operand swept through shared memory in 512-row slices" if swept else
-                 "tensor cores (tcgen05 TF32 x3 split, TMEM accumulators)" if tensor_scan else
+                 "tensor cores (tcgen05 TF32 x3 split, TMEM accumulators), self-scan pipeline: every shade warp reads its own rays' accumulators" if self_scan else
+                 "tensor cores (tcgen05 TF32 x3 split, TMEM accumulators), scan-warp pipeline" if tensor_scan else
                  "uniform grid (opt-in spatial index; NOT the brute-force 18 x N x rays figure)" if grid_scan else
                  "FP32 pipe (packed FFMA2 from shared memory)")
     traffic = None                                                            # DRAM bytes per launch exist only for captured (kernel, workload) pairs
     if args.workload == "final":
-        traffic = (traffic_db.get("tensor_scan_r2", traffic_db) if tensor_scan else traffic_db.get("fp32_scan", {}) if not grid_scan else {}).get("dram_bytes_per_launch")
+        traffic = (traffic_db.get("self_scan_r2" if self_scan else "tensor_scan_r1", traffic_db) if tensor_scan else traffic_db.get("fp32_scan", {}) if not grid_scan else {}).get("dram_bytes_per_launch")
     elif args.workload == "dense" and swept:
         traffic = traffic_db.get("swept_scan", {}).get("dram_bytes_per_launch")
     common = {"kernel": kernel_name, "scan": scan_desc, "k1_ms_per_launch": k1_avg, "rays_per_launch": rays_per_launch,

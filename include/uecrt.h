@@ -78,7 +78,16 @@ typedef struct {
 } uecrt_params;
 
 enum {
-  UECRT_FLAG_EXACT_HITS = 1u, /* resolve every closest hit in FP64 (reference-exact index) inside K1 */
+  UECRT_FLAG_EXACT_HITS = 1u, /* resolve every closest hit in FP64 (reference-exact index) inside K1.
+                                 Without it (FAST, the default) the candidates of a ray are compared by
+                                 their FP32 roots and only the WINNER's root is solved again in FP64
+                                 (csrc/closest_hit.cuh refine_winner).  Stated FAST tolerance against
+                                 sphere.hpp:25-48 in double, tested on 810 000 primary and 600 000 random
+                                 rays (tests/test_gpu_hits.py, profiles/fast_accuracy_r2.log): t <= 1e-9
+                                 relative, normal <= 1e-9 absolute, front_face equal, wherever the same
+                                 sphere wins; the winning sphere may differ from the reference's when two
+                                 roots lie within ~1e-6 relative of each other (<= 2e-4 of the rays
+                                 allowed, 0 observed). */
   UECRT_FLAG_NO_COUNTERS = 2u, /* do not count rays/sphere tests (saves two atomics per CTA)         */
   UECRT_FLAG_SCAN_FP32 = 4u,   /* force the FP32-pipe candidate scan (packed FFMA2 from shared memory) */
   UECRT_FLAG_SCAN_TENSOR = 8u, /* force the tensor-core candidate scan (tcgen05 TF32 x3, TMEM), any
@@ -164,7 +173,8 @@ int uecrt_tensor_scan_resident_spheres(void);
  * o_xyz/d_xyz: n_rays*3 floats (direction need not be unit; t is in units of |d| as in
  * sphere.hpp:35).  Outputs: t (double, or -1 on miss), n_xyz (3 doubles), id (-1 on miss),
  * front_face.  exact != 0 uses the FP64-resolved path (reference-exact index); exact == 0
- * is the FP32 fast path K1 uses by default. */
+ * is the fast path K1 uses by default: FP32 comparison of the candidates, the winner's root and
+ * normal in FP64 for the caller's direction (tolerance: see UECRT_FLAG_EXACT_HITS). */
 int uecrt_primary_hits(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz,
                        const float* d_xyz, double t_min, double t_max, int exact, double* t,
                        double* n_xyz, int32_t* id, uint8_t* front_face);
@@ -209,6 +219,19 @@ int uecrt_resolve_device(const float* d_accum, uint32_t width, uint32_t height, 
 int uecrt_ctx_primary_hits(uecrt_ctx* ctx, uint64_t n_rays, const float* o_xyz, const float* d_xyz,
                            double t_min, double t_max, int exact, double* t, double* n_xyz, int32_t* id,
                            uint8_t* front_face);
+/* ---- frame queue: overlap what FOLLOWS the path (source.cpp:221-230: to_color3b, then the PNG write) with the next
+ * frame's path.  uecrt_queue_submit is asynchronous: memset + K1 + K3 go to the queue's compute stream, the RGB image
+ * is copied into pinned host memory by a copy engine on a second stream.  uecrt_queue_next blocks until the OLDEST
+ * submitted frame has landed and returns a pointer to it, valid until the slot is submitted to again (two slots: at
+ * most two frames in flight).  Typical loop: submit(0); for k: submit(k + 1); next(k) -> encode PNG of frame k on a host
+ * thread while K1 of frame k + 1 runs.  cam_or_null changes the camera for this and later frames (no copy: the camera
+ * travels in K1's argument block); the scene is the one given at creation.  One device, the caller's current one. */
+typedef struct uecrt_queue uecrt_queue;
+int uecrt_queue_create(const uecrt_scene* scene, const uecrt_camera* cam, uint32_t width, uint32_t height, uecrt_queue** out);
+void uecrt_queue_destroy(uecrt_queue* q);
+int uecrt_queue_submit(uecrt_queue* q, const uecrt_camera* cam_or_null, const uecrt_params* params, uint64_t frame_id);
+int uecrt_queue_next(uecrt_queue* q, const uint8_t** rgb, uint64_t* frame_id_or_null, float* k1_ms_or_null);
+
 /* statistics of the last uecrt_accumulate_device on ctx (blocks on the stream's events) */
 int uecrt_ctx_stats(uecrt_ctx* ctx, uecrt_stats* out);
 

@@ -139,6 +139,9 @@ def test_fast_path_statistics(u, oracle, name, cam, W):
     assert (i != io).mean() <= 2e-4, f"{(i != io).sum()} of {len(i)} indices differ"
     both = (io >= 0) & (i == io)
     rel = np.abs(t[both] - to[both]) / np.abs(to[both])
-    assert np.percentile(rel, 99) <= 1e-4 and rel.max() <= 5e-3
-    assert np.percentile(np.abs(n[both] - no[both]).max(axis=1), 99) <= 1e-4
-    assert (f[both] != fo[both]).mean() <= 1e-4
+    # stated FAST tolerance (include/uecrt.h UECRT_FLAG_EXACT_HITS): the winner's root and normal are solved in FP64, so
+    # wherever the same sphere wins they agree with the double reference far inside north_star's 1e-5
+    assert rel.max() <= 1e-9, (np.percentile(rel, 99), rel.max())
+    dn = np.abs(n[both] - no[both]).max(axis=1)
+    assert dn.max() <= 1e-9, (np.percentile(dn, 99), dn.max())
+    assert np.array_equal(f[both], fo[both])

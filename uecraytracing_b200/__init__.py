@@ -11,13 +11,13 @@ from ._lib import (  # noqa: F401
     FLAG_SCAN_FP32, FLAG_SCAN_TENSOR, FLAG_SCAN_GRID,
 )
 from .api import (  # noqa: F401
-    Scene, Camera, Context, image_height, render, primary_hits, scatter, philox, resolve_device,
+    Scene, Camera, Context, FrameQueue, image_height, render, primary_hits, scatter, philox, resolve_device,
     write_png, device_count, stats_to_dict, philox_host, set_tile_spheres, set_rays_per_thread, load_scene_file, save_scene_file, write_pfm,
     set_scan_mode, set_tensor_pipeline, tensor_scan_max_spheres, tensor_scan_resident_spheres, tensor_candidates,
 )
 
 __all__ = [
-    "UecrtError", "lib", "lib_path", "Scene", "Camera", "Context", "image_height", "render",
+    "UecrtError", "lib", "lib_path", "Scene", "Camera", "Context", "FrameQueue", "image_height", "render",
     "primary_hits", "scatter", "philox", "resolve_device", "write_png", "device_count",
     "stats_to_dict", "MAT_LAMBERTIAN", "MAT_METAL", "MAT_DIELECTRIC", "FLAG_EXACT_HITS",
     "FLAG_NO_COUNTERS", "FLAG_SCAN_FP32", "FLAG_SCAN_TENSOR", "FLAG_SCAN_GRID", "set_scan_mode", "set_tensor_pipeline", "tensor_scan_max_spheres", "tensor_scan_resident_spheres",

@@ -45,7 +45,7 @@ lib_path = os.environ.get("UECRT_LIB") or os.path.join(os.path.dirname(os.path.a
 EXPORTS = [
     "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_set_scan_mode", "uecrt_set_tensor_pipeline", "uecrt_tensor_scan_max_spheres", "uecrt_tensor_scan_resident_spheres", "uecrt_primary_hits", "uecrt_scatter", "uecrt_debug_tensor_candidates",
     "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_ctx_set_scene", "uecrt_accumulate_device", "uecrt_resolve_device",
-    "uecrt_ctx_stats", "uecrt_ctx_primary_hits", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
+    "uecrt_ctx_stats", "uecrt_ctx_primary_hits", "uecrt_queue_create", "uecrt_queue_destroy", "uecrt_queue_submit", "uecrt_queue_next", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
     "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox", "uecrt_host_scene_file_count", "uecrt_host_scene_file_fill",
     "uecrt_host_scene_file_write", "uecrt_host_last_error", "uecrt_host_write_pfm",
 ]
@@ -87,6 +87,14 @@ def _load():
     L.uecrt_ctx_stats.argtypes = [vp, vp]
     L.uecrt_ctx_primary_hits.argtypes = [vp, u64, vp, vp, dbl, dbl, C.c_int, vp, vp, vp, vp]
     L.uecrt_ctx_primary_hits.restype = C.c_int
+    L.uecrt_queue_create.argtypes = [vp, vp, u32, u32, C.POINTER(vp)]
+    L.uecrt_queue_create.restype = C.c_int
+    L.uecrt_queue_destroy.argtypes = [vp]
+    L.uecrt_queue_destroy.restype = None
+    L.uecrt_queue_submit.argtypes = [vp, vp, vp, u64]
+    L.uecrt_queue_submit.restype = C.c_int
+    L.uecrt_queue_next.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_float)]
+    L.uecrt_queue_next.restype = C.c_int
     L.uecrt_host_scene_count.argtypes = [C.c_char_p, u32, u32]
     L.uecrt_host_scene_count.restype = u32
     L.uecrt_host_scene_fill.argtypes = [C.c_char_p, u32, u32, u32, vp, vp, vp]

@@ -122,6 +122,39 @@ def render(scene, camera, width=400, spp=100, max_depth=50, seed=0, gpus=1, exac
     return rgb, accum, stats_to_dict(st)
 
 
+class FrameQueue:
+    """uecrt_queue_*: K1 of frame k + 1 overlaps the D2H (pinned, copy engine) and the host-side handling of frame k."""
+
+    def __init__(self, scene, camera, width):
+        self.width, self.height = width, image_height(width)
+        self.q = C.c_void_p()
+        sc, cam = scene.struct(), camera.struct()
+        check(lib.uecrt_queue_create(C.byref(sc), C.byref(cam), self.width, self.height, C.byref(self.q)), "uecrt_queue_create")
+
+    def submit(self, frame_id, spp=100, max_depth=50, seed=0, camera=None, exact=False, scan=None):
+        p = _params(self.width, self.height, spp, max_depth, seed, 0, 0, 1, (FLAG_EXACT_HITS if exact else 0) | _SCAN_FLAGS[scan])
+        cam = camera.struct() if camera is not None else None
+        check(lib.uecrt_queue_submit(self.q, C.byref(cam) if cam is not None else None, C.byref(p), int(frame_id)), "uecrt_queue_submit")
+
+    def next(self):
+        """(frame_id, rgb copy (H, W, 3) uint8, K1 ms) of the oldest frame in flight; blocks until its RGB has landed."""
+        ptr, fid, ms = C.c_void_p(), C.c_uint64(), C.c_float()
+        check(lib.uecrt_queue_next(self.q, C.byref(ptr), C.byref(fid), C.byref(ms)), "uecrt_queue_next")
+        buf = (C.c_uint8 * (self.width * self.height * 3)).from_address(ptr.value)
+        return int(fid.value), np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 3).copy(), float(ms.value)
+
+    def close(self):
+        if self.q:
+            lib.uecrt_queue_destroy(self.q)
+            self.q = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def primary_hits(scene, o, d, t_min=0.001, t_max=float("inf"), exact=True):
     o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
     d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)

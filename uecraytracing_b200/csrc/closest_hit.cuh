@@ -296,11 +296,64 @@ struct Hit {
   bool front;
 };
 
-// sphere.hpp:41-45 + hittable.hpp:23-27 for the winning sphere, normal taken from the
-// centre-relative vector (never from the rounded world-space hit point).
+// The WINNER's root and normal in double (sphere.hpp:27-45 for one sphere).  The candidate test (test_fast_g) computes
+// t = -hb -+ sqrt(disc) in FP32, which loses digits by cancellation when the sphere is much larger than the distance to
+// it (the r = 1000 ground seen from 10 units: 5e-4 relative on the final scene's primary rays, 5e-3 on horizon rays).
+// Once per ray, for the sphere that won, the quadratic is solved again in FP64 for the direction vector (vx, vy, vz) the
+// caller wants t measured in (K1: its FP32 unit direction; K2: the caller's original direction) and the SAME root (near
+// or far) as the FP32 test took is returned: t and the normal are then exact for the given ray up to double rounding.  Which sphere wins is
+// still decided by the FP32 roots, identically in every scan mode.  RECIP: a = |v|^2 is 1 +- 1e-7, so 1 / a = 2 - a to
+// 1e-14 (K1); otherwise a true division (K2).
+struct HitD { double t, nx, ny, nz; bool front; };
+template <bool RECIP>
+__device__ __forceinline__ HitD refine_winner(const float4 g, float ox, float oy, float oz, float vx, float vy, float vz, bool near_root) {
+  const double Dx = vx, Dy = vy, Dz = vz, r = g.w;
+  const double ocx = (double)ox - (double)g.x, ocy = (double)oy - (double)g.y, ocz = (double)oz - (double)g.z;      // sphere.hpp:27
+  const double a = fma(Dz, Dz, fma(Dy, Dy, Dx * Dx));                                                             // :28
+  const double hb = fma(ocz, Dz, fma(ocy, Dy, ocx * Dx));                                                         // :29
+  const double c = fma(ocz, ocz, fma(ocy, ocy, fma(ocx, ocx, -r * r)));                                           // :30
+  const double disc = fma(hb, hb, -a * c);                                                                        // :31
+  const double sq = sqrt(fmax(disc, 0.0));                                                                        // :33
+  double r0, r1;
+  if (RECIP) { const double ia = 2.0 - a; r0 = (-hb - sq) * ia; r1 = (-hb + sq) * ia; }
+  else { r0 = (-hb - sq) / a; r1 = (-hb + sq) / a; }                                                              // :35, :37
+  HitD h;
+  h.t = near_root ? r0 : r1;
+  const double ir = RECIP ? (double)__fdividef(1.0f, g.w) : 1.0 / r;
+  h.nx = fma(h.t, Dx, ocx) * ir; h.ny = fma(h.t, Dy, ocy) * ir; h.nz = fma(h.t, Dz, ocz) * ir;                     // :44 (centre-relative)
+  h.front = fma(Dz, h.nz, fma(Dy, h.ny, Dx * h.nx)) < 0.0;                                                        // hittable.hpp:25
+  if (!h.front) { h.nx = -h.nx; h.ny = -h.ny; h.nz = -h.nz; }
+  return h;
+}
+
+// which root test_fast_g took for sphere g: t32 = -hb -+ s with s >= 0 (the self-hit shortcut's -2 hb is the far root),
+// hb recomputed bit-identically from the same FP32 unit direction
+__device__ __forceinline__ bool took_near_root(const float4 g, float ox, float oy, float oz, float dx, float dy, float dz, float t32) {
+  const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
+  const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
+  return t32 <= -hb;      // a zero FP32 discriminant leaves t32 == -hb: the near root, as the reference would take
+}
+
+// K1: hit record of the winning sphere for the FP32 unit direction (dx, dy, dz); h.t holds the FP32 root on entry.
+// Only the root is solved in double (refine_winner's :27-:37 with a = |d|^2 = 1 +- 1e-7 inverted as 2 - a and the
+// square root taken as one FP64 Newton step on MUFU.RSQ: 46 bits); the point and the normal follow in FP32 from the
+// centre-relative vector, exact to 1e-7 once t is.
 __device__ __forceinline__ void finish_hit_fast_g(const float4 g, float ox, float oy, float oz,
                                                   float dx, float dy, float dz, Hit& h) {
   const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
+  const bool near_root = h.t <= -fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));       // took_near_root
+  {
+    const double Dx = dx, Dy = dy, Dz = dz, r = g.w;
+    const double Ocx = (double)ox - (double)g.x, Ocy = (double)oy - (double)g.y, Ocz = (double)oz - (double)g.z;
+    const double a = fma(Dz, Dz, fma(Dy, Dy, Dx * Dx));
+    const double hb = fma(Ocz, Dz, fma(Ocy, Dy, Ocx * Dx));
+    const double c = fma(Ocz, Ocz, fma(Ocy, Ocy, fma(Ocx, Ocx, -r * r)));
+    const double disc = fmax(fma(hb, hb, -a * c), 0.0);
+    double y = (double)rsqrtf(fmaxf((float)disc, 1e-37f));                      // 1 / sqrt(disc) to 2^-23
+    y = fma(0.5 * y, fma(-disc * y, y, 1.0), y);                                // Newton: 2^-45
+    const double sq = disc * y;
+    h.t = (float)((near_root ? -hb - sq : -hb + sq) * (2.0 - a));
+  }
   const float inv_r = __fdividef(1.0f, g.w);
   h.px = fmaf(h.t, dx, ox); h.py = fmaf(h.t, dy, oy); h.pz = fmaf(h.t, dz, oz);
   float nx = fmaf(h.t, dx, ocx) * inv_r, ny = fmaf(h.t, dy, ocy) * inv_r, nz = fmaf(h.t, dz, ocz) * inv_r;

@@ -552,9 +552,10 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
       });
       if (has_ray) resolve_fast(sc.geom, L[0], cnt[0], ox, oy, oz, dx, dy, dz, tmin_w, -1, best);
       if (has_ray && best.id >= 0) {
-        Hit h; h.id = best.id; h.t = best.t;
-        finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
-        id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
+        // the winner's root and normal in double for the CALLER's direction (closest_hit.cuh refine_winner)
+        const float4 gw = __ldg(&sc.geom[best.id]);
+        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, took_near_root(gw, ox, oy, oz, dx, dy, dz, best.t));
+        id = best.id; t = w.t; nx = w.nx; ny = w.ny; nz = w.nz; front = w.front;
       }
     } else {
       const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
@@ -1088,9 +1089,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
           tc::shade_next_pass(sh);
         }
         if (best.id >= 0) {
-          Hit h; h.id = best.id; h.t = best.t;
-          finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
-          id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
+          // the winner's root and normal in double for the CALLER's direction (closest_hit.cuh refine_winner)
+          const float4 gw = __ldg(&sc.geom[best.id]);
+        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, took_near_root(gw, ox, oy, oz, dx, dy, dz, best.t));
+          id = best.id; t = w.t; nx = w.nx; ny = w.ny; nz = w.nz; front = w.front;
         }
       } else {
         const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root
@@ -1227,9 +1229,10 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits_grid(const Device
       grid_walk(sc.grid, ox, oy, oz, dx, dy, dz, [&](int j) { test_fast<false>(sc.geom, j, ox, oy, oz, dx, dy, dz, tmin_w, -1, best); },
                 [&]() { return best.t; }, n_tests);
       if (best.id >= 0) {
-        Hit h; h.id = best.id; h.t = best.t;
-        finish_hit_fast(sc.geom, ox, oy, oz, dx, dy, dz, h);
-        id = h.id; t = (double)(best.t * inv); nx = h.nx; ny = h.ny; nz = h.nz; front = h.front;
+        // the winner's root and normal in double for the CALLER's direction (closest_hit.cuh refine_winner)
+        const float4 gw = __ldg(&sc.geom[best.id]);
+        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, took_near_root(gw, ox, oy, oz, dx, dy, dz, best.t));
+        id = best.id; t = w.t; nx = w.nx; ny = w.ny; nz = w.nz; front = w.front;
       }
     } else {
       const double Ox = ox, Oy = oy, Oz = oz, Dx = rx, Dy = ry, Dz = rz;   // ORIGINAL direction: t == reference root

@@ -261,18 +261,21 @@ void ctx_free(uecrt_ctx* c) {
 }
 
 // (re)load a scene + camera into a context on the current device; buffers are reused when they fit
+// the camera travels by value in K1's argument block: changing it costs no copy
+void ctx_set_camera(uecrt_ctx* c, const uecrt_camera* cam) {
+  for (int i = 0; i < 3; ++i) {
+    c->cam.origin[i] = cam->origin[i]; c->cam.ll[i] = cam->lower_left[i]; c->cam.hor[i] = cam->horizontal[i];
+    c->cam.ver[i] = cam->vertical[i]; c->cam.u[i] = cam->u[i]; c->cam.v[i] = cam->v[i];
+  }
+  c->cam.lens = cam->lens_radius;
+  c->cam.origin_is_zero = (cam->origin[0] == 0.f && cam->origin[1] == 0.f && cam->origin[2] == 0.f) ? 1 : 0;
+}
+
 int ctx_set_scene(uecrt_ctx* c, const uecrt_scene* scene, const uecrt_camera* cam) {
   int rc = validate_scene(scene);
   if (rc) return rc;
   if ((rc = ctx_upload_scene(c, scene))) return rc;
-  if (cam) {
-    for (int i = 0; i < 3; ++i) {
-      c->cam.origin[i] = cam->origin[i]; c->cam.ll[i] = cam->lower_left[i]; c->cam.hor[i] = cam->horizontal[i];
-      c->cam.ver[i] = cam->vertical[i]; c->cam.u[i] = cam->u[i]; c->cam.v[i] = cam->v[i];
-    }
-    c->cam.lens = cam->lens_radius;
-    c->cam.origin_is_zero = (cam->origin[0] == 0.f && cam->origin[1] == 0.f && cam->origin[2] == 0.f) ? 1 : 0;
-  }
+  if (cam) ctx_set_camera(c, cam);
   cudaError_t e;
   if (!c->configured) {
     if ((e = cudaMalloc(&c->d_counters, kCounterWords * sizeof(unsigned long long))) != cudaSuccess ||
@@ -639,6 +642,113 @@ int uecrt_resolve_device(const float* d_accum, uint32_t width, uint32_t height, 
 }
 
 int uecrt_ctx_stats(uecrt_ctx* ctx, uecrt_stats* out) { return ctx_stats(ctx, out); }
+
+// ---- frame queue: what follows the path in the reference (source.cpp:221-230: to_color3b, then the PNG write) overlapped
+// with the NEXT frame's path.  Two slots; per frame the compute stream runs memset, K1, K3 and records an event, the copy
+// stream waits for it and moves the RGB image into PINNED host memory with cudaMemcpyAsync (a copy engine, no SM), so the
+// D2H of frame k and whatever the caller does with it on the host (PNG deflate) run while K1 of frame k + 1 occupies the SMs.
+struct uecrt_queue {
+  uecrt_ctx* ctx = nullptr;
+  int device = 0;
+  uint32_t width = 0, height = 0;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  struct Slot {
+    float* accum = nullptr;
+    uint8_t* d_rgb = nullptr;
+    uint8_t* h_rgb = nullptr;            // pinned
+    cudaEvent_t k1_begin = nullptr, k1_end = nullptr, resolved = nullptr, copied = nullptr;
+    uint64_t frame_id = 0;
+  } slot[2];
+  uint64_t submitted = 0, taken = 0;
+};
+
+static void queue_free(uecrt_queue* q) {
+  if (!q) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(q->device);
+  if (q->compute) cudaStreamSynchronize(q->compute);
+  if (q->copy) cudaStreamSynchronize(q->copy);
+  for (auto& s : q->slot) {
+    cudaFree(s.accum); cudaFree(s.d_rgb);
+    if (s.h_rgb) cudaFreeHost(s.h_rgb);
+    for (cudaEvent_t e : {s.k1_begin, s.k1_end, s.resolved, s.copied}) if (e) cudaEventDestroy(e);
+  }
+  if (q->compute) cudaStreamDestroy(q->compute);
+  if (q->copy) cudaStreamDestroy(q->copy);
+  if (q->ctx) ctx_free(q->ctx);
+  cudaSetDevice(prev);
+  delete q;
+}
+
+int uecrt_queue_create(const uecrt_scene* scene, const uecrt_camera* cam, uint32_t width, uint32_t height, uecrt_queue** out) {
+  if (!out) return fail(UECRT_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!scene || !cam || width == 0 || height == 0) return fail(UECRT_ERR_INVALID, "bad argument");
+  uecrt_queue* q = new uecrt_queue();
+  q->width = width; q->height = height;
+  int rc = ctx_create_on_current_device(scene, cam, &q->ctx);
+  if (rc) { delete q; return rc; }
+  q->device = q->ctx->device;
+  const size_t npx = (size_t)width * height;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaStreamCreateWithFlags(&q->compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&q->copy, cudaStreamNonBlocking));
+    for (auto& s : q->slot) {
+      CUDA_TRY(cudaMalloc(&s.accum, npx * 4 * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&s.d_rgb, npx * 3));
+      CUDA_TRY(cudaHostAlloc(&s.h_rgb, npx * 3, cudaHostAllocDefault));
+      CUDA_TRY(cudaEventCreate(&s.k1_begin)); CUDA_TRY(cudaEventCreate(&s.k1_end));
+      CUDA_TRY(cudaEventCreateWithFlags(&s.resolved, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    }
+    return UECRT_OK;
+  };
+  if ((rc = body())) { queue_free(q); return rc; }
+  *out = q;
+  return UECRT_OK;
+}
+void uecrt_queue_destroy(uecrt_queue* q) { queue_free(q); }
+
+int uecrt_queue_submit(uecrt_queue* q, const uecrt_camera* cam_or_null, const uecrt_params* params, uint64_t frame_id) {
+  if (!q || !params) return fail(UECRT_ERR_INVALID, "null argument");
+  if (params->width != q->width || params->height != q->height) return fail(UECRT_ERR_INVALID, "the queue was created for %u x %u frames", q->width, q->height);
+  if (params->spp == 0) return fail(UECRT_ERR_INVALID, "spp must be > 0");
+  if (q->submitted - q->taken >= 2) return fail(UECRT_ERR_INVALID, "both slots are in flight: call uecrt_queue_next first");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != q->device) return fail(UECRT_ERR_INVALID, "queue lives on device %d, current device is %d", q->device, dev);
+  uecrt_queue::Slot& s = q->slot[q->submitted & 1u];
+  if (cam_or_null) ctx_set_camera(q->ctx, cam_or_null);
+  const size_t npx = (size_t)q->width * q->height;
+  CUDA_TRY(cudaMemsetAsync(s.accum, 0, npx * 4 * sizeof(float), q->compute));
+  CUDA_TRY(cudaEventRecord(s.k1_begin, q->compute));
+  int rc = accumulate(q->ctx, params, s.accum, q->compute);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(s.k1_end, q->compute));
+  uecrt::launch_resolve(reinterpret_cast<const float4*>(s.accum), (uint32_t)npx, params->spp, s.d_rgb, q->compute);   // K3: 0.01 ms
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(s.resolved, q->compute));
+  CUDA_TRY(cudaStreamWaitEvent(q->copy, s.resolved, 0));
+  CUDA_TRY(cudaMemcpyAsync(s.h_rgb, s.d_rgb, npx * 3, cudaMemcpyDeviceToHost, q->copy));
+  CUDA_TRY(cudaEventRecord(s.copied, q->copy));
+  s.frame_id = frame_id;
+  ++q->submitted;
+  return UECRT_OK;
+}
+
+int uecrt_queue_next(uecrt_queue* q, const uint8_t** rgb, uint64_t* frame_id_or_null, float* k1_ms_or_null) {
+  if (!q || !rgb) return fail(UECRT_ERR_INVALID, "null argument");
+  if (q->taken == q->submitted) return fail(UECRT_ERR_INVALID, "no frame in flight");
+  uecrt_queue::Slot& s = q->slot[q->taken & 1u];
+  CUDA_TRY(cudaEventSynchronize(s.copied));
+  if (k1_ms_or_null) CUDA_TRY(cudaEventElapsedTime(k1_ms_or_null, s.k1_begin, s.k1_end));
+  if (frame_id_or_null) *frame_id_or_null = s.frame_id;
+  *rgb = s.h_rgb;
+  ++q->taken;
+  return UECRT_OK;
+}
+
 
 int uecrt_render(const uecrt_scene* scene, const uecrt_camera* cam, const uecrt_params* params, uint8_t* rgb_out,
                  float* accum_out_or_null, uecrt_stats* stats_or_null) {

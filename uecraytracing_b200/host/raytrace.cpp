@@ -3,13 +3,18 @@
 // stdout lines "rendering...", "rendering finished", "write to file : <f>", "success";
 // a failed write prints "error" and exits 1; an unknown option aborts (uncaught exception).
 // New, additive flags (north_star): --width --spp --depth --seed, plus --gpus --scene --dense-n
-// --exact-hits --scan --dump-accum.  Defaults equal the reference's macros (400 / 100 / 50).
+// --exact-hits --scan --dump-accum, and --frames N --orbit DEG: N frames of a camera orbit through the frame queue
+// (K1 of frame k + 1 overlaps the D2H and the PNG write of frame k; files <output stem>_0000.png ...).
+// Defaults equal the reference's macros (400 / 100 / 50).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <random>
+#include <chrono>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "cli_options.hpp"
 #include "png_writer.hpp"
@@ -37,6 +42,8 @@ int main(int argc, char* argv[]) {
       .add(0, "dense-n", "sphere count of --scene dense (default 10000)", true)
       .add(0, "exact-hits", "resolve every closest hit in FP64", false)
       .add(0, "scan", "closest-hit search: auto | fp32 | tensor | grid (default auto: brute force on the tensor cores from 96 spheres up; grid = opt-in spatial index)", true)
+      .add(0, "frames", "render N frames of a camera orbit about the y axis, PNG write of frame k overlapped with frame k + 1 (default 1)", true)
+      .add(0, "orbit", "degrees the camera turns per frame of --frames (default 2)", true)
       .add(0, "dump-accum", "also write the linear float image (.pfm) or the raw W*H*4 f32 accumulation buffer", true);
   options.positional("output");
   options.parse(argc, argv);
@@ -85,6 +92,54 @@ int main(int argc, char* argv[]) {
   else if (scene == "final") { world = yk::scenes::final_scene(scene_seed); cam = yk::scenes::final_camera(); }
   else if (scene == "dense") { world = yk::scenes::dense_scene(dense_n, scene_seed); cam = yk::scenes::dense_camera(); }
   else { std::cout << "unknown scene : " << scene << std::endl; std::exit(EXIT_FAILURE); }
+
+  const std::uint32_t frames = options.count("frames") ? options.as<std::uint32_t>("frames") : 1u;
+  if (frames > 1) {
+    // a sequence: <stem>_0000.png ... ; the PNG of frame k is deflated and written by a host thread while K1 of frame k + 1 runs
+    const double step = options.count("orbit") ? std::stod(options.last("orbit")) : 2.0;
+    std::vector<yk::camera<double>> cams;
+    for (std::uint32_t k = 0; k < frames; ++k) cams.push_back(yk::orbit_y(cam, step * k));
+    const std::size_t dot = filename.rfind('.');
+    const std::string stem = dot == std::string::npos ? filename : filename.substr(0, dot), ext = dot == std::string::npos ? ".png" : filename.substr(dot);
+    const std::uint32_t W = cfg.width, H = yk::constants::height_for(cfg.width);
+    std::vector<std::vector<std::uint8_t>> copies(2, std::vector<std::uint8_t>((std::size_t)W * H * 3));
+    std::thread writer[2];
+    bool write_ok = true;
+    double k1_sum = 0.0;
+    std::cout << "rendering..." << std::endl;
+    double wall = 0.0;
+    try {
+      wall = yk::render_sequence(world, cams, cfg, [&](std::size_t k, const std::uint8_t* rgb, float k1_ms) {
+        std::thread& t = writer[k & 1];
+        if (t.joinable()) t.join();                       // the write of frame k - 2
+        std::copy(rgb, rgb + copies[k & 1].size(), copies[k & 1].begin());
+        k1_sum += k1_ms;
+        char num[16];
+        std::snprintf(num, sizeof num, "_%04zu", k);
+        const std::string path = stem + num + ext;
+        t = std::thread([&, path, k] {
+          if (!uecrt_host::write_png(path.c_str(), (int)W, (int)H, 3, copies[k & 1].data(), (int)(3 * W))) write_ok = false;
+        });
+        if (yk::verbose) std::cout << "frame " << k << ": K1 " << k1_ms << " ms -> " << path << std::endl;
+      });
+    } catch (const std::exception& e) {
+      for (auto& t : writer) if (t.joinable()) t.join();
+      std::cout << "error" << std::endl;
+      std::cerr << e.what() << std::endl;
+      std::exit(EXIT_FAILURE);
+    }
+    const auto tj = std::chrono::steady_clock::now();
+    for (auto& t : writer) if (t.joinable()) t.join();
+    wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tj).count();
+    std::cout << "rendering finished" << std::endl;
+    if (yk::verbose)
+      std::cout << frames << " frames in " << wall * 1e3 << " ms wall-clock incl. PNG (" << wall * 1e3 / frames << " ms per frame; K1 alone " << k1_sum / frames
+                << " ms per frame)" << std::endl;
+    std::cout << "write to file : " << stem << "_0000" << ext << " .. " << frames << " frames" << std::endl;
+    if (!write_ok) { std::cout << "error" << std::endl; std::exit(EXIT_FAILURE); }
+    std::cout << "success" << std::endl;
+    return 0;
+  }
 
   // rendering
   const bool dump = options.count("dump-accum") != 0;

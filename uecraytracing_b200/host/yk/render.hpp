@@ -4,7 +4,10 @@
 // YK_MAX_DEPTH (source.cpp:43-53) and become runtime values, so image_t is a heap vector
 // instead of a stack std::array (source.cpp:70-71 overflows the stack at 3840x2160).
 #pragma once
+#include <chrono>
+#include <cmath>
 #include <cstdint>
+#include <functional>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -80,6 +83,54 @@ inline image_t render(const hittable_list<double>& world, const camera<double>& 
   }
   std::cout << "rendering finished" << std::endl;                 // source.cpp:175
   return img;
+}
+
+// The camera turned by `degrees` about the world's y axis (every frame of an orbit sees the same scene from the
+// same height and distance): all of its points and vectors are rotated, so any camera<T> works, positioned or not.
+template <class T>
+inline camera<T> orbit_y(const camera<T>& c, T degrees) {
+  const T a = degrees * T(3.14159265358979323846) / T(180), cs = std::cos(a), sn = std::sin(a);
+  auto rot = [&](auto& p) { const T x = p.x, z = p.z; p.x = cs * x + sn * z; p.z = -sn * x + cs * z; };
+  camera<T> r = c;
+  rot(r.origin); rot(r.lower_left_corner); rot(r.horizontal); rot(r.vertical); rot(r.u); rot(r.v);
+  return r;
+}
+
+// A sequence of frames of one scene through the frame queue (include/uecrt.h uecrt_queue_*): K1 of frame k + 1 runs while
+// the RGB image of frame k is copied into pinned host memory and handed to on_frame (the caller's PNG write), the overlap
+// SURVEY 8(f)2 asks for after source.cpp:221-230.  on_frame(k, rgb, k1_ms) is called in frame order on the calling thread
+// with the queue's pinned buffer, valid until it returns.  Returns the wall-clock seconds of the whole sequence.
+inline double render_sequence(const hittable_list<double>& world, const std::vector<camera<double>>& cams, const render_config& cfg,
+                              const std::function<void(std::size_t, const std::uint8_t*, float)>& on_frame) {
+  if (cams.empty()) return 0.0;
+  const std::uint32_t width = cfg.width, height = constants::height_for(cfg.width);
+  const uecrt_scene sc = world.flatten();
+  const uecrt_camera c0 = cams[0].flatten();
+  uecrt_queue* q = nullptr;
+  if (uecrt_queue_create(&sc, &c0, width, height, &q) != UECRT_OK) throw std::runtime_error(std::string("uecrt_queue_create: ") + uecrt_last_error());
+  uecrt_params p{};
+  p.width = width; p.height = height; p.spp = cfg.spp; p.max_depth = cfg.max_depth; p.num_gpus = 1;
+  p.flags = (cfg.exact_hits ? UECRT_FLAG_EXACT_HITS : 0u) |
+      (cfg.scan == UECRT_SCAN_FP32 ? UECRT_FLAG_SCAN_FP32 : cfg.scan == UECRT_SCAN_TENSOR ? UECRT_FLAG_SCAN_TENSOR
+       : cfg.scan == UECRT_SCAN_GRID ? UECRT_FLAG_SCAN_GRID : 0u);
+  auto submit = [&](std::size_t k) {
+    const uecrt_camera c = cams[k].flatten();
+    p.seed = cfg.seed + k;                          // independent Philox streams per frame
+    if (uecrt_queue_submit(q, &c, &p, k) != UECRT_OK) { uecrt_queue_destroy(q); throw std::runtime_error(std::string("uecrt_queue_submit: ") + uecrt_last_error()); }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  submit(0);
+  for (std::size_t k = 0; k < cams.size(); ++k) {
+    if (k + 1 < cams.size()) submit(k + 1);
+    const std::uint8_t* rgb = nullptr;
+    std::uint64_t id = 0;
+    float k1_ms = 0.f;
+    if (uecrt_queue_next(q, &rgb, &id, &k1_ms) != UECRT_OK) { uecrt_queue_destroy(q); throw std::runtime_error(std::string("uecrt_queue_next: ") + uecrt_last_error()); }
+    on_frame((std::size_t)id, rgb, k1_ms);
+  }
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  uecrt_queue_destroy(q);
+  return s;
 }
 
 }  // namespace yk
