@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--scan", default="auto", choices=["auto", "fp32", "tensor", "grid"],
                     help="K1 closest-hit search (auto: brute force on the tensor cores when the scene fits; grid: opt-in spatial index, reported separately)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-scans", action="store_true", help="skip the side-by-side FP32-scan and exact-resolve timings after the timed region")
     ap.add_argument("--single-process", action="store_true",
                     help="N GPUs from ONE process: every step is uecrt_render(num_gpus=N) (no torch.distributed)")
     ap.add_argument("--psnr", action="store_true",
@@ -275,8 +276,8 @@ def main():
     k1_avg = sum(ke) / len(ke) if ke else 0.0
     few = max(2, min(args.steps, 3))
     # side by side, same launches: the FP32-pipe scan (the design north_star names) and the FP64-exact resolve
-    fp32_ms = time_k1((flags & ~u.FLAG_SCAN_TENSOR) | u.FLAG_SCAN_FP32, few)[0][1:] if st["scan_mode"] == 2 else []
-    exact_ms = time_k1(flags | u.FLAG_EXACT_HITS, few)[0][1:] if not args.exact_hits else []
+    fp32_ms = time_k1((flags & ~u.FLAG_SCAN_TENSOR) | u.FLAG_SCAN_FP32, few)[0][1:] if st["scan_mode"] == 2 and not args.no_side_scans else []
+    exact_ms = time_k1(flags | u.FLAG_EXACT_HITS, few)[0][1:] if not (args.exact_hits or args.no_side_scans) else []
     fp32_k1 = sum(fp32_ms) / len(fp32_ms) if fp32_ms else 0.0
     exact_k1 = sum(exact_ms) / len(exact_ms) if exact_ms else 0.0
     t = torch.tensor([total_ms, k1_avg, float(rays), float(tests), fp32_k1, exact_k1], dtype=torch.float64, device=dev)

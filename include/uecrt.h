@@ -154,7 +154,8 @@ void uecrt_set_rays_per_thread(int rays);
  * 96 spheres and more, and the FP32 scan for smaller scenes (faster there) and when tiles were forced with
  * uecrt_set_tile_spheres.  Up to uecrt_tensor_scan_resident_spheres() spheres the tensor scan keeps its sphere
  * operand (128 B per sphere) resident in shared memory; above that it sweeps it through shared memory in
- * 512-sphere slices, up to uecrt_tensor_scan_max_spheres() (the scene size limit). */
+ * 512-sphere slices, up to uecrt_tensor_scan_max_spheres() (the scene size limit, 2^22).  The FP32 scan keeps 16-bit
+ * candidate lists and is refused above 65 534 spheres; the automatic mode uses the tensor-core scan there. */
 void uecrt_set_scan_mode(int uecrt_scan_mode);
 /* Which pipeline K1 runs the tensor-core scan with when the sphere operand is resident in shared memory:
  *   UECRT_TENSOR_PIPELINE_SELF      (default) every shade warp reads the TMEM accumulators of its own rays
@@ -195,6 +196,14 @@ int uecrt_scatter(uint64_t n, const uint32_t* mat_type, const uecrt_float4* mat_
  * discriminant (sphere.hpp:27-32, in double on the same float inputs) is >= 0 must be flagged. */
 int uecrt_debug_tensor_candidates(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz,
                                   const float* d_xyz, uint8_t* flags_out, int32_t* spheres_per_flag_out);
+
+/* Test hook for K1's camera rays (source.cpp:162-165 + camera.hpp:29-32 on the device): the ray K1 starts path
+ * (pixel, sample) of a width x height frame with.  The jitter and the lens sample come from the Philox block
+ * (pixel, sample, 0, 0) of `seed`: u = (x + U0) / width, v = (height - 1 - y + U1) / height with pixel = y * width + x,
+ * lens point = lens_radius * sqrt(U2) * (cos 2 pi U3, sin 2 pi U3) in the camera's (u, v) basis.  o_xyz: origin (+ lens
+ * offset); d_xyz: lower_left + u horizontal + v vertical - origin - offset, NOT normalised (K1 normalises it). */
+int uecrt_debug_camera_rays(const uecrt_camera* cam, uint32_t width, uint32_t height, uint64_t seed, uint64_t n,
+                            const uint32_t* pixel, const uint32_t* sample, float* o_xyz, float* d_xyz);
 
 /* Philox4x32-10 block for (key = seed, counter = {c0,c1,c2,c3}), computed on the device. */
 int uecrt_philox(uint64_t n, uint64_t seed, const uint32_t* counters4, uint32_t* out4);

@@ -125,8 +125,9 @@ def test_empty_ragged_and_interval(u, oracle):
     o, d = primary_rays(u.Camera.named("final"), 200, 112)
     for tmin, tmax in ((0.001, 1.2), (1.0, 1.5), (0.5, float("inf"))):
         _check_exact(u.primary_hits(sc, o, d, tmin, tmax), oracle.hits(sc, o.astype(np.float64), d.astype(np.float64), tmin, tmax), f"[{tmin},{tmax}]")
-    with pytest.raises(u.UecrtError):
-        u.primary_hits(u.Scene(np.zeros((70000, 4)), np.zeros(70000), np.zeros((70000, 4))), o, d)
+    with pytest.raises(u.UecrtError):                      # scene size limit (uecrt_tensor_scan_max_spheres)
+        n = u.tensor_scan_max_spheres() + 1
+        u.primary_hits(u.Scene(np.zeros((n, 4)), np.zeros(n), np.zeros((n, 4))), o[:4], d[:4])
 
 
 @pytest.mark.parametrize("name,cam,W", [("ref4", "ref", 400), ("final", "final", 1200)])

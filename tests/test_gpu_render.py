@@ -294,3 +294,27 @@ def test_cli_frames_sequence(u, tmp_path):
     still, _, _ = u.render(u.Scene.named("final", seed=1), u.Camera.named("final"), 240, 8, 50, seed=21)
     assert imgs[0].shape == still.shape and (imgs[0] != still).mean() < 1e-3
     assert (imgs[0] != imgs[2]).mean() > 0.2
+
+
+@pytest.mark.parametrize("cam_name,W", [("ref", 400), ("final", 1200), ("dense", 320)])
+def test_device_camera_rays_match_reference_camera(u, oracle, cam_name, W):
+    """K1's camera rays on caller (pixel, sample) pairs (uecrt_debug_camera_rays) against camera::get_ray (camera.hpp:29-32, through
+    the oracle) fed with the same jitter and lens sample: the Philox block (pixel, sample, 0, 0) read as four uniforms, the
+    unit-disk point taken by the polar map the kernel documents (same distribution as the book's rejection loop)."""
+    cam, H, seed = u.Camera.named(cam_name), u.image_height(W), 0x1234567890abcdef
+    rng = np.random.default_rng(5)
+    pixel = np.concatenate([[0, W - 1, W * (H - 1), W * H - 1], rng.integers(0, W * H, 400)]).astype(np.uint32)   # the four corners first
+    sample = np.concatenate([[0, 1, 2, 3], rng.integers(0, 4096, 400)]).astype(np.uint32)
+    o, d = u.camera_rays(cam, W, seed, pixel, sample)
+    lens = float(cam.s.lens_radius)
+    for k in range(len(pixel)):
+        U = [(x >> 8) / 16777216.0 for x in u.philox_host(seed, (int(pixel[k]), int(sample[k]), 0, 0))]
+        py, px = divmod(int(pixel[k]), W)
+        s, t = (px + U[0]) / W, (H - 1 - py + U[1]) / H
+        r, phi = np.sqrt(U[2]), 2 * np.pi * U[3]
+        ro, rd = oracle.camera_ray(cam, s, t, r * np.cos(phi), r * np.sin(phi))
+        scale = max(1.0, np.abs(rd).max())
+        assert np.abs(o[k] - ro).max() <= 1e-6 * max(1.0, np.abs(ro).max()) + 2e-6 * lens, (k, o[k], ro)
+        assert np.abs(d[k] - rd).max() <= 3e-6 * scale + 4e-6 * lens, (k, d[k], rd)
+    if lens == 0.0:
+        assert np.all(o == np.asarray(cam.s.origin, np.float32))

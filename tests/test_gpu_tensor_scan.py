@@ -176,7 +176,7 @@ def _random_scene(u, n, seed, span=6.0):
 def test_limits_reported(u):
     r = u.tensor_scan_resident_spheres()          # operand + two quad-flag bitmaps + the shade side's tables per sphere row
     assert r % 128 == 0 and 1024 <= r <= 1536
-    assert u.tensor_scan_max_spheres() == 65534
+    assert u.tensor_scan_max_spheres() == 1 << 22       # the scene size limit; the FP32 scan alone stops at 65 534 (16-bit candidate lists)
 
 
 @pytest.mark.parametrize("n", [1025, 2048, 5000])
@@ -208,8 +208,9 @@ def test_swept_operand_hits_identical_to_fp32_scan(u, n, exact):
 
 
 def test_swept_operand_at_the_scene_size_limit(u):
-    """65 534 spheres (the scene size limit): 128 slices of 512 rows, an 8 MB operand streamed from L2."""
-    n = u.tensor_scan_max_spheres()
+    """65 534 spheres (the FP32 scan's limit, so the largest scene on which the two scans can be compared): 128 slices of
+    512 rows, an 8 MB operand streamed from L2."""
+    n = 65534
     sc = _random_scene(u, n, 77, span=40.0)
     rng = np.random.default_rng(78)
     o = rng.uniform(-45, 45, (3000, 3)).astype(np.float32)
@@ -338,3 +339,31 @@ def test_both_tensor_pipelines_trace_the_same_paths(u, name, cam, n, exact):
     assert np.array_equal(aa[..., 3], ab[..., 3]) and np.all(aa[..., 3] == 12)
     assert np.abs(aa[..., :3] - ab[..., :3]).max() <= 1e-4 * 12
     assert (ra != rb).mean() < 1e-4
+
+
+def test_scene_above_the_16_bit_list_limit(u, oracle):
+    """70 000 spheres: more than the FP32 scan's 16-bit candidate lists can index (65 534).  The automatic mode takes the
+    swept tensor scan (candidate bitmaps) and the grid holds 32-bit items: both still return the reference's hits."""
+    n = 70000
+    sc, cam = u.Scene.named("dense", seed=3, n=n), u.Camera.named("dense")
+    assert sc.n == n and u.tensor_scan_max_spheres() >= n
+    rng = np.random.default_rng(17)
+    o = rng.uniform(-60, 60, (1500, 3)).astype(np.float32); o[:, 1] = np.abs(o[:, 1]) * 0.2 + 0.3
+    d = rng.normal(size=(1500, 3)).astype(np.float32)
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    assert (want[2] >= 0).sum() > 300 and want[2].max() > 65535
+    _check_exact(u.primary_hits(sc, o, d), want, "auto (tensor, swept)")
+    u.set_scan_mode("grid")
+    try:
+        _check_exact(u.primary_hits(sc, o, d), want, "grid")
+    finally:
+        u.set_scan_mode("auto")
+    u.set_scan_mode("fp32")
+    try:
+        with pytest.raises(u.UecrtError):
+            u.primary_hits(sc, o, d)                       # forced FP32 scan: refused, not silently wrong
+    finally:
+        u.set_scan_mode("auto")
+    _, _, sa = u.render(sc, cam, 96, 2, 50, seed=4)
+    _, _, sg = u.render(sc, cam, 96, 2, 50, seed=4, scan="grid")
+    assert sa["scan_mode"] == 2 and sg["scan_mode"] == 3 and sa["rays_traced"] == sg["rays_traced"] and sa["paths"] == 96 * u.image_height(96) * 2

@@ -29,4 +29,5 @@ for spp in (16, 64, 256, 500, 1024, 4096):
 out = {'reference': 'mean of two 500-spp renders by the unmodified reference code', 'ref_vs_ref_psnr8_500spp': meta['psnr8_A_vs_B'],
        'ref_linear_mean': meta['linear_mean'], 'rows': rows,
        'note': 'above ~1000 spp the PSNR is limited by the noise of the 1000-spp reference image itself (asymptote ~46.4 dB)'}
-json.dump(out, open('gpurun_out/convergence_r1.json', 'w'), indent=1)
+out['kernel'] = {'scan_mode': st['scan_mode'], 'k1_threads': st['k1_threads'], 'note': 'automatic scan: tensor cores, self-scan pipeline (k_render_paths_ts) when k1_threads == 896'}
+json.dump(out, open('gpurun_out/convergence_r2.json', 'w'), indent=1)

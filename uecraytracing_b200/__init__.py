@@ -13,7 +13,7 @@ from ._lib import (  # noqa: F401
 from .api import (  # noqa: F401
     Scene, Camera, Context, FrameQueue, image_height, render, primary_hits, scatter, philox, resolve_device,
     write_png, device_count, stats_to_dict, philox_host, set_tile_spheres, set_rays_per_thread, load_scene_file, save_scene_file, write_pfm,
-    set_scan_mode, set_tensor_pipeline, tensor_scan_max_spheres, tensor_scan_resident_spheres, tensor_candidates,
+    set_scan_mode, set_tensor_pipeline, tensor_scan_max_spheres, tensor_scan_resident_spheres, tensor_candidates, camera_rays,
 )
 
 __all__ = [

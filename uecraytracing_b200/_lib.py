@@ -43,7 +43,7 @@ lib_path = os.environ.get("UECRT_LIB") or os.path.join(os.path.dirname(os.path.a
 
 # every symbol include/uecrt.h and include/uecrt_host.h declare
 EXPORTS = [
-    "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_set_scan_mode", "uecrt_set_tensor_pipeline", "uecrt_tensor_scan_max_spheres", "uecrt_tensor_scan_resident_spheres", "uecrt_primary_hits", "uecrt_scatter", "uecrt_debug_tensor_candidates",
+    "uecrt_last_error", "uecrt_version", "uecrt_device_count", "uecrt_render", "uecrt_release", "uecrt_set_tile_spheres", "uecrt_set_rays_per_thread", "uecrt_set_scan_mode", "uecrt_set_tensor_pipeline", "uecrt_tensor_scan_max_spheres", "uecrt_tensor_scan_resident_spheres", "uecrt_primary_hits", "uecrt_scatter", "uecrt_debug_tensor_candidates", "uecrt_debug_camera_rays",
     "uecrt_philox", "uecrt_ctx_create", "uecrt_ctx_destroy", "uecrt_ctx_set_scene", "uecrt_accumulate_device", "uecrt_resolve_device",
     "uecrt_ctx_stats", "uecrt_ctx_primary_hits", "uecrt_queue_create", "uecrt_queue_destroy", "uecrt_queue_submit", "uecrt_queue_next", "uecrt_host_scene_count", "uecrt_host_scene_fill", "uecrt_host_camera",
     "uecrt_host_camera_lookat", "uecrt_host_image_height", "uecrt_host_write_png", "uecrt_host_philox", "uecrt_host_scene_file_count", "uecrt_host_scene_file_fill",
@@ -75,6 +75,8 @@ def _load():
     L.uecrt_primary_hits.argtypes = [vp, u64, vp, vp, dbl, dbl, C.c_int, vp, vp, vp, vp]
     L.uecrt_debug_tensor_candidates.argtypes = [vp, u64, vp, vp, vp, vp]
     L.uecrt_debug_tensor_candidates.restype = C.c_int
+    L.uecrt_debug_camera_rays.argtypes = [vp, u32, u32, u64, u64, vp, vp, vp, vp]
+    L.uecrt_debug_camera_rays.restype = C.c_int
     L.uecrt_scatter.argtypes = [u64] + [vp] * 11
     L.uecrt_philox.argtypes = [u64, u64, vp, vp]
     L.uecrt_ctx_create.argtypes = [vp, vp, C.POINTER(vp)]

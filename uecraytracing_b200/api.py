@@ -167,6 +167,17 @@ def primary_hits(scene, o, d, t_min=0.001, t_max=float("inf"), exact=True):
     return t, nrm, idx, ff
 
 
+def camera_rays(camera, width, seed, pixel, sample):
+    """(origins, unnormalised directions) of the camera rays K1 starts paths (pixel, sample) with (uecrt_debug_camera_rays)."""
+    pixel = np.ascontiguousarray(pixel, np.uint32); sample = np.ascontiguousarray(sample, np.uint32)
+    n = len(pixel)
+    o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+    cam = camera.struct()
+    check(lib.uecrt_debug_camera_rays(C.byref(cam), width, image_height(width), int(seed), n, _ptr(pixel), _ptr(sample), _ptr(o), _ptr(d)),
+          "uecrt_debug_camera_rays")
+    return o, d
+
+
 def tensor_candidates(scene, o, d):
     """(flags (n_rays, n_spheres) uint8, spheres_per_flag): the tensor-core scan's verdict alone (uecrt_debug_tensor_candidates)."""
     o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)

@@ -105,7 +105,7 @@ struct CandList {
 // ---------------------------------------------------------------------------------------
 // Phase 2, FAST: FP32 resolve of `cnt` candidates (ascending index order).
 // t is the distance along the UNIT direction; tmin is 0.001*|d| in those units.
-struct FastBest { float t; int id; };
+struct FastBest { float t; int id; bool far_root = false; };   // far_root: the accepted root is -hb + s (refine_winner solves the same one)
 
 // one candidate sphere j against the running best (sphere.hpp:32-39 + hittable_list.hpp:37-44).
 // ORDERED = true: candidates arrive in ascending index order, so accepting t <= best is the reference's
@@ -117,6 +117,7 @@ __device__ __forceinline__ void test_fast_g(const float4 g, int j, float ox, flo
   const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
   const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
   float t;
+  bool far_root = true;
   if (j == self_id) {
     // the ray starts ON this sphere: the roots are exactly 0 and -2*hb (reference: the
     // ~1e-16 self-hit is below t_min = 0.001 and only the far root can be accepted)
@@ -128,12 +129,13 @@ __device__ __forceinline__ void test_fast_g(const float4 g, int j, float ox, flo
     if (disc < 0.0f) return;                         // sphere.hpp:32
     const float s = sqrt_fast(disc);
     t = -hb - s;                                      // sphere.hpp:35
-    if (t < tmin) {                                   // sphere.hpp:36-39 (t_max test below)
+    far_root = t < tmin;
+    if (far_root) {                                   // sphere.hpp:36-39 (t_max test below)
       t = -hb + s;
       if (t < tmin) return;
     }
   }
-  if (ORDERED ? (t <= best.t) : (t < best.t || (t == best.t && j > best.id))) { best.t = t; best.id = j; }   // closed interval: later index wins ties
+  if (ORDERED ? (t <= best.t) : (t < best.t || (t == best.t && j > best.id))) { best.t = t; best.id = j; best.far_root = far_root; }   // closed interval: later index wins ties
 }
 template <bool ORDERED = true>
 __device__ __forceinline__ void test_fast(const float4* __restrict__ geom, int j, float ox, float oy, float oz, float dx,
@@ -301,7 +303,7 @@ struct Hit {
 // it (the r = 1000 ground seen from 10 units: 5e-4 relative on the final scene's primary rays, 5e-3 on horizon rays).
 // Once per ray, for the sphere that won, the quadratic is solved again in FP64 for the direction vector (vx, vy, vz) the
 // caller wants t measured in (K1: its FP32 unit direction; K2: the caller's original direction) and the SAME root (near
-// or far) as the FP32 test took is returned: t and the normal are then exact for the given ray up to double rounding.  Which sphere wins is
+// or far, FastBest::far_root) as the FP32 test took is returned: t and the normal are then exact for the given ray up to double rounding.  Which sphere wins is
 // still decided by the FP32 roots, identically in every scan mode.  RECIP: a = |v|^2 is 1 +- 1e-7, so 1 / a = 2 - a to
 // 1e-14 (K1); otherwise a true division (K2).
 struct HitD { double t, nx, ny, nz; bool front; };
@@ -326,33 +328,23 @@ __device__ __forceinline__ HitD refine_winner(const float4 g, float ox, float oy
   return h;
 }
 
-// which root test_fast_g took for sphere g: t32 = -hb -+ s with s >= 0 (the self-hit shortcut's -2 hb is the far root),
-// hb recomputed bit-identically from the same FP32 unit direction
-__device__ __forceinline__ bool took_near_root(const float4 g, float ox, float oy, float oz, float dx, float dy, float dz, float t32) {
-  const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
-  const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
-  return t32 <= -hb;      // a zero FP32 discriminant leaves t32 == -hb: the near root, as the reference would take
-}
-
-// K1: hit record of the winning sphere for the FP32 unit direction (dx, dy, dz); h.t holds the FP32 root on entry.
-// Only the root is solved in double (refine_winner's :27-:37 with a = |d|^2 = 1 +- 1e-7 inverted as 2 - a and the
-// square root taken as one FP64 Newton step on MUFU.RSQ: 46 bits); the point and the normal follow in FP32 from the
-// centre-relative vector, exact to 1e-7 once t is.
+// K1: hit record of the winning sphere for the FP32 unit direction (dx, dy, dz); far_root: which root the FP32 test took.
+// Only the root is solved in double (refine_winner's :27-:37 with |d|^2 taken as 1: K1's directions are normalised in
+// FP32, |d|^2 = 1 +- 1.2e-7, which bounds what that costs; the square root is one FP64 Newton step on MUFU.RSQ, 46 bits);
+// the point and the normal follow in FP32 from the centre-relative vector, exact to 1e-7 once t is.
 __device__ __forceinline__ void finish_hit_fast_g(const float4 g, float ox, float oy, float oz,
-                                                  float dx, float dy, float dz, Hit& h) {
+                                                  float dx, float dy, float dz, bool far_root, Hit& h) {
   const float ocx = ox - g.x, ocy = oy - g.y, ocz = oz - g.z;
-  const bool near_root = h.t <= -fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));       // took_near_root
   {
     const double Dx = dx, Dy = dy, Dz = dz, r = g.w;
     const double Ocx = (double)ox - (double)g.x, Ocy = (double)oy - (double)g.y, Ocz = (double)oz - (double)g.z;
-    const double a = fma(Dz, Dz, fma(Dy, Dy, Dx * Dx));
     const double hb = fma(Ocz, Dz, fma(Ocy, Dy, Ocx * Dx));
     const double c = fma(Ocz, Ocz, fma(Ocy, Ocy, fma(Ocx, Ocx, -r * r)));
-    const double disc = fmax(fma(hb, hb, -a * c), 0.0);
+    const double disc = fmax(fma(hb, hb, -c), 0.0);
     double y = (double)rsqrtf(fmaxf((float)disc, 1e-37f));                      // 1 / sqrt(disc) to 2^-23
     y = fma(0.5 * y, fma(-disc * y, y, 1.0), y);                                // Newton: 2^-45
     const double sq = disc * y;
-    h.t = (float)((near_root ? -hb - sq : -hb + sq) * (2.0 - a));
+    h.t = (float)(far_root ? sq - hb : -hb - sq);
   }
   const float inv_r = __fdividef(1.0f, g.w);
   h.px = fmaf(h.t, dx, ox); h.py = fmaf(h.t, dy, oy); h.pz = fmaf(h.t, dz, oz);
@@ -364,8 +356,8 @@ __device__ __forceinline__ void finish_hit_fast_g(const float4 g, float ox, floa
   h.nx = h.front ? nx : -nx; h.ny = h.front ? ny : -ny; h.nz = h.front ? nz : -nz;
 }
 __device__ __forceinline__ void finish_hit_fast(const float4* __restrict__ geom, float ox, float oy, float oz,
-                                                float dx, float dy, float dz, Hit& h) {
-  finish_hit_fast_g(__ldg(&geom[h.id]), ox, oy, oz, dx, dy, dz, h);
+                                                float dx, float dy, float dz, bool far_root, Hit& h) {
+  finish_hit_fast_g(__ldg(&geom[h.id]), ox, oy, oz, dx, dy, dz, far_root, h);
 }
 
 }  // namespace uecrt

@@ -214,7 +214,7 @@ __device__ __forceinline__ void closest_hits(const DeviceScene& sc, const ulongl
       if (best[r].id >= 0) {
         h[r].id = best[r].id;
         h[r].t = best[r].t;
-        finish_hit_fast(sc.geom, q[r].ox, q[r].oy, q[r].oz, q[r].dx, q[r].dy, q[r].dz, h[r]);
+        finish_hit_fast(sc.geom, q[r].ox, q[r].oy, q[r].oz, q[r].dx, q[r].dy, q[r].dz, best[r].far_root, h[r]);
       }
     }
   } else {
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits(const DeviceScene
       if (has_ray && best.id >= 0) {
         // the winner's root and normal in double for the CALLER's direction (closest_hit.cuh refine_winner)
         const float4 gw = __ldg(&sc.geom[best.id]);
-        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, took_near_root(gw, ox, oy, oz, dx, dy, dz, best.t));
+        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, !best.far_root);
         id = best.id; t = w.t; nx = w.nx; ny = w.ny; nz = w.nz; front = w.front;
       }
     } else {
@@ -644,7 +644,7 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
-      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, best.far_root, h);
     }
   } else {
     ExactBest best{(double)CUDART_INF, -1};
@@ -700,7 +700,7 @@ __device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_qua
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
-      finish_hit_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)best.id), q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+      finish_hit_fast_g(tc::lds_f4(s_geom + 16u * (uint32_t)best.id), q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, best.far_root, h);
     }
   } else {
     ExactBest best{(double)CUDART_INF, -1};
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_primary_hits_tc(const Devic
         if (best.id >= 0) {
           // the winner's root and normal in double for the CALLER's direction (closest_hit.cuh refine_winner)
           const float4 gw = __ldg(&sc.geom[best.id]);
-        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, took_near_root(gw, ox, oy, oz, dx, dy, dz, best.t));
+        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, !best.far_root);
           id = best.id; t = w.t; nx = w.nx; ny = w.ny; nz = w.nz; front = w.front;
         }
       } else {
@@ -1146,7 +1146,7 @@ __device__ __forceinline__ void grid_closest_hit(const DeviceScene& sc, const Ra
     if (best.id >= 0) {
       h.id = best.id;
       h.t = best.t;
-      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, h);
+      finish_hit_fast(sc.geom, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, best.far_root, h);
     }
   } else {
     ExactBest best{(double)CUDART_INF, -1};
@@ -1231,7 +1231,7 @@ __global__ void __launch_bounds__(kHitsThreads) k_primary_hits_grid(const Device
       if (best.id >= 0) {
         // the winner's root and normal in double for the CALLER's direction (closest_hit.cuh refine_winner)
         const float4 gw = __ldg(&sc.geom[best.id]);
-        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, took_near_root(gw, ox, oy, oz, dx, dy, dz, best.t));
+        const HitD w = refine_winner<false>(gw, ox, oy, oz, rx, ry, rz, !best.far_root);
         id = best.id; t = w.t; nx = w.nx; ny = w.ny; nz = w.nz; front = w.front;
       }
     } else {
@@ -1522,6 +1522,22 @@ void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4
                     float* att, float* o_out, float* d_out, cudaStream_t st) {
   k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, mat_type, mat_param, d_in, p, nrm, ff, uniforms4, scattered,
                                                         att, o_out, d_out);
+}
+
+// Probe: the camera ray K1 starts path (pixel, sample) with -- slot_start_path itself on caller (pixel, sample) pairs
+__global__ void k_camera_rays(const RenderArgs a, unsigned long long n, const uint32_t* __restrict__ pixel, const uint32_t* __restrict__ sample,
+                              float* __restrict__ o_out, float* __restrict__ d_out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PathState p{};
+  p.pixel = pixel[i]; p.sample = sample[i]; p.valid = true;
+  unsigned n_paths = 0;
+  slot_start_path(p, a, true, 1.0f / (float)a.width, 1.0f / (float)a.height, n_paths);
+  o_out[3 * i] = p.ox; o_out[3 * i + 1] = p.oy; o_out[3 * i + 2] = p.oz;
+  d_out[3 * i] = p.dx * p.dlen; d_out[3 * i + 1] = p.dy * p.dlen; d_out[3 * i + 2] = p.dz * p.dlen;   // the unnormalised direction
+}
+void launch_camera_rays(const RenderArgs& a, unsigned long long n, const uint32_t* pixel, const uint32_t* sample, float* o, float* d, cudaStream_t st) {
+  k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, pixel, sample, o, d);
 }
 
 void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st) {

@@ -69,6 +69,7 @@ void launch_resolve(const float4* accum, uint32_t n_pixels, uint32_t spp, uint8_
 void launch_scatter(unsigned long long n, const uint32_t* mat_type, const float4* mat_param, const float* d_in,
                     const float* p, const float* nrm, const uint8_t* ff, const float* uniforms4,
                     uint8_t* scattered, float* att, float* o_out, float* d_out, cudaStream_t st);
+void launch_camera_rays(const RenderArgs& a, unsigned long long n, const uint32_t* pixel, const uint32_t* sample, float* o, float* d, cudaStream_t st);
 void launch_philox(unsigned long long n, uint32_t k0, uint32_t k1, const uint32_t* ctr4, uint32_t* out4, cudaStream_t st);
 cudaError_t configure_kernels(int* regs_render, int* max_blocks_per_sm, size_t smem_render, bool tiled, int rays);
 

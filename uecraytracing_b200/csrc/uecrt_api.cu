@@ -92,9 +92,13 @@ int require_device() {
   return UECRT_OK;
 }
 
+// The FP32 scan's per-thread candidate lists hold 16-bit sphere indices: scenes above kFp32ScanMaxSpheres run on the
+// tensor-core scan (candidate bitmaps, swept operand) or the uniform grid (32-bit items), which have no such limit.
+constexpr uint32_t kFp32ScanMaxSpheres = 65534u, kMaxSceneSpheres = 1u << 22;
+
 int validate_scene(const uecrt_scene* s) {
   if (!s) return fail(UECRT_ERR_INVALID, "scene is null");
-  if (s->n > 65534u) return fail(UECRT_ERR_INVALID, "scene has %u spheres; the candidate lists hold 16-bit indices (max 65534)", s->n);
+  if (s->n > kMaxSceneSpheres) return fail(UECRT_ERR_INVALID, "scene has %u spheres (max %u)", s->n, kMaxSceneSpheres);
   if (s->n && (!s->geom || !s->mat_type || !s->mat_param)) return fail(UECRT_ERR_INVALID, "scene arrays are null");
   for (uint32_t i = 0; i < s->n; ++i) {
     if (s->mat_type[i] > UECRT_MAT_DIELECTRIC) return fail(UECRT_ERR_INVALID, "sphere %u: unknown material type %u", i, s->mat_type[i]);
@@ -405,6 +409,10 @@ int rc_mode(uint32_t flags, const uecrt_ctx* ctx, int* out) {
   // and below ~100 spheres the FP32 scan is faster (one 128-column MMA chunk per tile is the tensor scan's floor;
   // measured crossover between 64 and 128 spheres, profiles/README.md)
   if (want == UECRT_SCAN_AUTO) want = (g_tile_spheres.load() || ctx->n < kTensorScanMinSpheres || (!kAutoSweep && ctx->sc.tc_npasses > 1)) ? UECRT_SCAN_FP32 : UECRT_AUTO_SCAN;
+  if (want == UECRT_SCAN_FP32 && ctx->n > kFp32ScanMaxSpheres) {
+    if (forced) return fail(UECRT_ERR_INVALID, "the FP32 scan holds 16-bit candidate indices (max %u spheres); this scene has %u: use the tensor-core scan or the grid", kFp32ScanMaxSpheres, ctx->n);
+    want = UECRT_SCAN_TENSOR;
+  }
   if (want == UECRT_SCAN_TENSOR && !ctx->sc.tc_rows) {
     if (forced) return fail(UECRT_ERR_INVALID, "tensor-core scan requested but no operand was built for this scene (%u spheres)", ctx->n);
     want = UECRT_SCAN_FP32;
@@ -872,7 +880,7 @@ void uecrt_release(void) { release_workspaces(); }
 void uecrt_set_tile_spheres(uint32_t spheres_per_tile) { g_tile_spheres.store(spheres_per_tile); }
 void uecrt_set_tensor_pipeline(int p) { uecrt::tc_set_pipeline(p); }
 void uecrt_set_scan_mode(int m) { g_scan_mode.store((m == UECRT_SCAN_FP32 || m == UECRT_SCAN_TENSOR || m == UECRT_SCAN_GRID) ? m : UECRT_SCAN_AUTO); }
-int uecrt_tensor_scan_max_spheres(void) { return 65534; }
+int uecrt_tensor_scan_max_spheres(void) { return (int)kMaxSceneSpheres; }
 int uecrt_tensor_scan_resident_spheres(void) { return uecrt::tc_resident_max_spheres(); }
 void uecrt_set_rays_per_thread(int rays) { g_rays_per_thread.store((rays == 2 && uecrt::max_rays_per_thread() == 2) ? 2 : 1); }
 
@@ -924,6 +932,36 @@ int uecrt_ctx_primary_hits(uecrt_ctx* ctx, uint64_t n_rays, const float* o_xyz, 
 
 // Test hook: the tensor-core pre-filter's verdict on caller rays, before any resolve.  flags_out[i * n + j] = 1 iff the
 // scan flagged sphere j for ray i (with one bit per quad: iff it flagged j's quad).
+int uecrt_debug_camera_rays(const uecrt_camera* cam, uint32_t width, uint32_t height, uint64_t seed, uint64_t n,
+                            const uint32_t* pixel, const uint32_t* sample, float* o_xyz, float* d_xyz) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (n == 0) return UECRT_OK;
+  if (!cam || !pixel || !sample || !o_xyz || !d_xyz || width == 0 || height == 0) return fail(UECRT_ERR_INVALID, "bad argument");
+  uecrt_ctx tmp;                                       // only its camera conversion is used
+  ctx_set_camera(&tmp, cam);
+  uecrt::RenderArgs a{};
+  a.cam = tmp.cam; a.width = width; a.height = height; a.max_depth = 1;
+  a.key0 = (uint32_t)(seed & 0xffffffffull); a.key1 = (uint32_t)(seed >> 32);
+  uint32_t *d_p = nullptr, *d_s = nullptr;
+  float *d_o = nullptr, *d_d = nullptr;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_p, n * 4)); CUDA_TRY(cudaMalloc(&d_s, n * 4));
+    CUDA_TRY(cudaMalloc(&d_o, n * 12)); CUDA_TRY(cudaMalloc(&d_d, n * 12));
+    CUDA_TRY(cudaMemcpy(d_p, pixel, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_s, sample, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+    uecrt::launch_camera_rays(a, n, d_p, d_s, d_o, d_d, 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(o_xyz, d_o, n * 12, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(d_xyz, d_d, n * 12, cudaMemcpyDeviceToHost));
+    return UECRT_OK;
+  };
+  rc = body();
+  cudaFree(d_p); cudaFree(d_s); cudaFree(d_o); cudaFree(d_d);
+  return rc;
+}
+
 int uecrt_debug_tensor_candidates(const uecrt_scene* scene, uint64_t n_rays, const float* o_xyz, const float* d_xyz,
                                   uint8_t* flags_out, int32_t* spheres_per_flag_out) {
   int rc = require_device();
