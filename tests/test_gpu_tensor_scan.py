@@ -367,3 +367,26 @@ def test_scene_above_the_16_bit_list_limit(u, oracle):
     _, _, sa = u.render(sc, cam, 96, 2, 50, seed=4)
     _, _, sg = u.render(sc, cam, 96, 2, 50, seed=4, scan="grid")
     assert sa["scan_mode"] == 2 and sg["scan_mode"] == 3 and sa["rays_traced"] == sg["rays_traced"] and sa["paths"] == 96 * u.image_height(96) * 2
+
+
+def test_self_scan_pipeline_stress(u):
+    """The self-scan pipeline's barrier protocol (lanes, per-lane termination, a work queue shorter or longer than the
+    launch) over many small launches: 1 to 9 chunks, images from a few pixels (most groups never get a path) to ragged
+    sizes, 1 to 5 spp, depth 0 to 50.  Every launch must end (the test would hang otherwise), count every sample exactly
+    once and trace exactly the rays the FP32 scan traces.  (compute-sanitizer is closed on the pool; this is the race check.)"""
+    rng = np.random.default_rng(2026)
+    cam = u.Camera.named("dense")
+    for k in range(36):
+        n = int(rng.choice([96, 127, 128, 129, 255, 300, 512, 513, 777, 1024, 1100, 1152]))
+        W = int(rng.choice([8, 16, 33, 64, 100, 177]))
+        spp = int(rng.integers(1, 6))
+        depth = int(rng.choice([0, 1, 2, 7, 50]))
+        sc = u.Scene.named("dense", seed=10 + k, n=n)
+        exact = bool(k % 3 == 0)
+        _, a, sa = u.render(sc, cam, W, spp, depth, seed=k, exact=exact, return_accum=True, scan="tensor")
+        _, b, sb = u.render(sc, cam, W, spp, depth, seed=k, exact=exact, return_accum=True, scan="fp32")
+        tag = (n, W, spp, depth, exact)
+        assert sa["k1_threads"] == 896 and sa["scan_mode"] == 2, tag
+        assert np.all(a[..., 3] == spp) and sa["paths"] == sb["paths"] == W * u.image_height(W) * spp, tag
+        assert sa["rays_traced"] == sb["rays_traced"], tag
+        assert np.abs(a[..., :3] - b[..., :3]).max() <= 1e-4 * spp, tag

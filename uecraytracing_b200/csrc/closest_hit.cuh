@@ -155,9 +155,12 @@ __device__ __forceinline__ void resolve_fast(const float4* __restrict__ geom, co
 // reference's root; the unit direction inside K1).
 struct ExactBest { double t; int id; };
 
+// self_id (K1 only): the sphere the ray starts ON.  The origin is the hit point rounded to FP32, so its near root on that
+// sphere is not the reference's ~1e-16 but up to ~1e-3 at grazing angles on a large sphere (r = 1000 ground): above t_min,
+// a false self-hit the double reference cannot have.  As in the FAST test, only the far root of that sphere may be accepted.
 template <bool ORDERED = true>
 __device__ __forceinline__ void test_exact_g(const float4 g, int j, double ox, double oy, double oz, double dx,
-                                             double dy, double dz, double a, double tmin, ExactBest& best) {
+                                             double dy, double dz, double a, double tmin, ExactBest& best, int self_id = -1) {
   const double cx = g.x, cy = g.y, cz = g.z, r = g.w;
   const double ocx = __dsub_rn(ox, cx), ocy = __dsub_rn(oy, cy), ocz = __dsub_rn(oz, cz);     // sphere.hpp:27
   const double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));  // :29
@@ -167,7 +170,7 @@ __device__ __forceinline__ void test_exact_g(const float4 g, int j, double ox, d
   if (disc < 0.0) return;                                                                       // :32
   const double sqrtd = __dsqrt_rn(disc);                                                        // :33
   double root = __ddiv_rn(__dsub_rn(-half_b, sqrtd), a);                                       // :35
-  if (root < tmin || best.t < root) {                                                           // :36
+  if (j == self_id || root < tmin || best.t < root) {                                           // :36
     root = __ddiv_rn(__dadd_rn(-half_b, sqrtd), a);                                            // :37
     if (root < tmin || best.t < root) return;                                                   // :38
   }
@@ -177,15 +180,15 @@ __device__ __forceinline__ void test_exact_g(const float4 g, int j, double ox, d
 }
 template <bool ORDERED = true>
 __device__ __forceinline__ void test_exact(const float4* __restrict__ geom, int j, double ox, double oy, double oz, double dx,
-                                           double dy, double dz, double a, double tmin, ExactBest& best) {
-  test_exact_g<ORDERED>(__ldg(&geom[j]), j, ox, oy, oz, dx, dy, dz, a, tmin, best);
+                                           double dy, double dz, double a, double tmin, ExactBest& best, int self_id = -1) {
+  test_exact_g<ORDERED>(__ldg(&geom[j]), j, ox, oy, oz, dx, dy, dz, a, tmin, best, self_id);
 }
 
 template <int STRIDE>
 __device__ __forceinline__ void resolve_exact(const float4* __restrict__ geom, const CandList<STRIDE>& L, int cnt,
                                               double ox, double oy, double oz, double dx, double dy, double dz,
-                                              double a, double tmin, ExactBest& best) {
-  for (int e = 0; e < cnt; ++e) test_exact(geom, L.base[e * STRIDE], ox, oy, oz, dx, dy, dz, a, tmin, best);
+                                              double a, double tmin, ExactBest& best, int self_id = -1) {
+  for (int e = 0; e < cnt; ++e) test_exact(geom, L.base[e * STRIDE], ox, oy, oz, dx, dy, dz, a, tmin, best, self_id);
 }
 // ---------------------------------------------------------------------------------------
 // Phase 1: the scan.  pairs: shared memory, 2 x 16 B per sphere pair

@@ -144,9 +144,9 @@ __device__ __noinline__ void fold_full_fast(const float4* geom, uint16_t* base, 
 template <int STRIDE>
 __device__ __noinline__ void fold_full_exact(const float4* geom, uint16_t* base, int cnt, double ox,
                                              double oy, double oz, double dx, double dy, double dz, double a,
-                                             double tmin, ExactBest* best) {
+                                             double tmin, ExactBest* best, int self_id = -1) {
   CandList<STRIDE> L{base};
-  resolve_exact(geom, L, cnt, ox, oy, oz, dx, dy, dz, a, tmin, *best);
+  resolve_exact(geom, L, cnt, ox, oy, oz, dx, dy, dz, a, tmin, *best, self_id);
 }
 
 // Candidate collection over the whole scene for the R rays of a thread.  RESIDENT: one call of the
@@ -231,13 +231,13 @@ __device__ __forceinline__ void closest_hits(const DeviceScene& sc, const ulongl
       for (int k = 0; k < R; ++k)
         if (k == r)
           fold_full_exact<STRIDE>(sc.geom, L[k].base, c, (double)q[k].ox, (double)q[k].oy, (double)q[k].oz, (double)q[k].dx,
-                                  (double)q[k].dy, (double)q[k].dz, a[k], (double)q[k].tmin, &best[k]);
+                                  (double)q[k].dy, (double)q[k].dz, a[k], (double)q[k].tmin, &best[k], q[k].self_id);
     });
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (!q[r].live) continue;
       const double Ox = q[r].ox, Oy = q[r].oy, Oz = q[r].oz, Dx = q[r].dx, Dy = q[r].dy, Dz = q[r].dz;
-      resolve_exact(sc.geom, L[r], cnt[r], Ox, Oy, Oz, Dx, Dy, Dz, a[r], (double)q[r].tmin, best[r]);
+      resolve_exact(sc.geom, L[r], cnt[r], Ox, Oy, Oz, Dx, Dy, Dz, a[r], (double)q[r].tmin, best[r], q[r].self_id);
       if (best[r].id >= 0) {
         const float4 g = __ldg(&sc.geom[best[r].id]);
         const double px = Ox + Dx * best[r].t, py = Oy + Dy * best[r].t, pz = Oz + Dz * best[r].t;   // ray.hpp:16-19
@@ -348,52 +348,53 @@ __device__ __forceinline__ void slot_refill_pooled(PathState& p, WorkPool& wp, c
   slot_start_path(p, a, need, inv_w, inv_h, n_paths);
 }
 
+// the camera ray of a fresh path from its Philox block (pixel, sample, 0, 0) (source.cpp:154-165, camera.hpp:29-32)
+__device__ __forceinline__ void slot_camera_ray(PathState& p, const RenderArgs& a, const philox_out r, float inv_w, float inv_h, unsigned& n_paths) {
+  // pixel -> (row, column) without the ~20-instruction runtime integer divide: float reciprocal
+  // estimate (exact to +-1 for pixel < 2^24 * width) and one fix-up step each way
+  uint32_t py = (uint32_t)__fmul_rz((float)p.pixel, inv_w);
+  uint32_t px = p.pixel - py * a.width;
+  if ((int32_t)px < 0) { --py; px += a.width; }
+  if (px >= a.width) { ++py; px -= a.width; }
+  const float u = ((float)px + uecrt_u01(r.x)) * inv_w;
+  const float v = ((float)(a.height - py - 1u) + uecrt_u01(r.y)) * inv_h;
+  float tx = fmaf(v, a.cam.ver[0], fmaf(u, a.cam.hor[0], a.cam.ll[0]));
+  float ty = fmaf(v, a.cam.ver[1], fmaf(u, a.cam.hor[1], a.cam.ll[1]));
+  float tz = fmaf(v, a.cam.ver[2], fmaf(u, a.cam.hor[2], a.cam.ll[2]));
+  p.ox = a.cam.origin[0]; p.oy = a.cam.origin[1]; p.oz = a.cam.origin[2];
+  if (a.cam.lens > 0.f) {
+    // uniform point in the unit disk from the block's last two uniforms (polar map: r = sqrt(u),
+    // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop of the
+    // book (and of the CPU checker), but exactly two uniforms and no divergent retry loop.
+    const float rr = sqrt_fast(uecrt_u01(r.z)), phi = 6.28318530717958647692f * uecrt_u01(r.w);
+    const float rx = rr * __cosf(phi), ry = rr * __sinf(phi);
+    const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;
+    const float offx = fmaf(ly, a.cam.v[0], lx * a.cam.u[0]);
+    const float offy = fmaf(ly, a.cam.v[1], lx * a.cam.u[1]);
+    const float offz = fmaf(ly, a.cam.v[2], lx * a.cam.u[2]);
+    tx = tx - p.ox - offx; ty = ty - p.oy - offy; tz = tz - p.oz - offz;
+    p.ox += offx; p.oy += offy; p.oz += offz;
+  } else if (!a.cam.origin_is_zero) {
+    tx -= p.ox; ty -= p.oy; tz -= p.oz;
+  }
+  const float len2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+  const float inv = rsqrt_nr(len2);
+  p.dlen = len2 * inv;
+  p.dx = tx * inv; p.dy = ty * inv; p.dz = tz * inv;
+  p.thr_r = p.thr_g = p.thr_b = 1.f;
+  p.depth_left = a.max_depth;
+  p.self_id = -1;
+  p.bounce = 0;
+  p.active = p.depth_left > 0;
+  if (!p.active) {                               // depth 0: black (raytracer.hpp:26)
+    red_add_v4(a.accum + p.pixel, 0.f, 0.f, 0.f, 1.f);
+    ++n_paths;
+  }
+}
+
 __device__ __forceinline__ void slot_start_path(PathState& p, const RenderArgs& a, bool need, float inv_w, float inv_h,
                                                 unsigned& n_paths) {
-  // start the path: camera ray (source.cpp:154-165, camera.hpp:29-32)
-  if (need && !p.done && p.valid) {
-    // pixel -> (row, column) without the ~20-instruction runtime integer divide: float reciprocal
-    // estimate (exact to +-1 for pixel < 2^24 * width) and one fix-up step each way
-    uint32_t py = (uint32_t)__fmul_rz((float)p.pixel, inv_w);
-    uint32_t px = p.pixel - py * a.width;
-    if ((int32_t)px < 0) { --py; px += a.width; }
-    if (px >= a.width) { ++py; px -= a.width; }
-    const philox_out r = philox4x32_10(p.pixel, p.sample, 0u, 0u, a.key0, a.key1);
-    const float u = ((float)px + uecrt_u01(r.x)) * inv_w;
-    const float v = ((float)(a.height - py - 1u) + uecrt_u01(r.y)) * inv_h;
-    float tx = fmaf(v, a.cam.ver[0], fmaf(u, a.cam.hor[0], a.cam.ll[0]));
-    float ty = fmaf(v, a.cam.ver[1], fmaf(u, a.cam.hor[1], a.cam.ll[1]));
-    float tz = fmaf(v, a.cam.ver[2], fmaf(u, a.cam.hor[2], a.cam.ll[2]));
-    p.ox = a.cam.origin[0]; p.oy = a.cam.origin[1]; p.oz = a.cam.origin[2];
-    if (a.cam.lens > 0.f) {
-      // uniform point in the unit disk from the block's last two uniforms (polar map: r = sqrt(u),
-      // phi = 2*pi*v).  Same distribution as the RTIOW random_in_unit_disk rejection loop of the
-      // book (and of the CPU checker), but exactly two uniforms and no divergent retry loop.
-      const float rr = sqrt_fast(uecrt_u01(r.z)), phi = 6.28318530717958647692f * uecrt_u01(r.w);
-      const float rx = rr * __cosf(phi), ry = rr * __sinf(phi);
-      const float lx = a.cam.lens * rx, ly = a.cam.lens * ry;
-      const float offx = fmaf(ly, a.cam.v[0], lx * a.cam.u[0]);
-      const float offy = fmaf(ly, a.cam.v[1], lx * a.cam.u[1]);
-      const float offz = fmaf(ly, a.cam.v[2], lx * a.cam.u[2]);
-      tx = tx - p.ox - offx; ty = ty - p.oy - offy; tz = tz - p.oz - offz;
-      p.ox += offx; p.oy += offy; p.oz += offz;
-    } else if (!a.cam.origin_is_zero) {
-      tx -= p.ox; ty -= p.oy; tz -= p.oz;
-    }
-    const float len2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-    const float inv = rsqrt_nr(len2);
-    p.dlen = len2 * inv;
-    p.dx = tx * inv; p.dy = ty * inv; p.dz = tz * inv;
-    p.thr_r = p.thr_g = p.thr_b = 1.f;
-    p.depth_left = a.max_depth;
-    p.self_id = -1;
-    p.bounce = 0;
-    p.active = p.depth_left > 0;
-    if (!p.active) {                               // depth 0: black (raytracer.hpp:26)
-      red_add_v4(a.accum + p.pixel, 0.f, 0.f, 0.f, 1.f);
-      ++n_paths;
-    }
-  }
+  if (need && !p.done && p.valid) slot_camera_ray(p, a, philox4x32_10(p.pixel, p.sample, 0u, 0u, a.key0, a.key1), inv_w, inv_h, n_paths);
 }
 
 // one path segment after its closest hit is known: scatter or terminate (raytracer.hpp:27-36)
@@ -432,6 +433,82 @@ __device__ __forceinline__ void slot_shade(PathState& p, const Hit& h, const Ren
                (rad_b == rad_b) ? rad_b : 0.f, 1.f);
     ++n_paths;
     p.active = false;
+  }
+}
+
+// Shade + refill of one slot with ONE Philox block per round (self-scan K1).  slot_shade draws the scatter's uniforms and
+// slot_refill_pooled / slot_start_path the camera ray's in two separately diverged regions (each ran with ~14 of 32 lanes
+// and 70 instructions of Philox4x32-10).  Path ends that need no random number -- a miss, or a hit with no depth left --
+// are known before the draw, so those lanes take their next work item first and the block is computed once for both kinds
+// of lanes: counter (pixel, sample, bounce) for a scattering lane, (pixel', sample', 0) for a fresh one.  Same counters,
+// same paths; a lane whose scatter is absorbed (metal below the surface) is refilled one round later.  WARP-CONVERGENT.
+__device__ __forceinline__ void slot_shade_refill_fused(PathState& p, const Hit& h, const RenderArgs& a, WorkPool& wp, unsigned lane,
+                                                        unsigned long long n_pixels, double inv_np, float inv_w, float inv_h,
+                                                        unsigned& n_rays, unsigned& n_paths) {
+  bool scatter_lane = false;
+  if (p.active) {
+    ++n_rays;
+    if (h.id < 0) {                                                // raytracer.hpp:35: the sky
+      const float t = 0.5f * (p.dy + 1.0f), w0 = 1.0f - t;
+      const float rr = p.thr_r * fmaf(t, 0.5f, w0), rg = p.thr_g * fmaf(t, 0.7f, w0), rb = p.thr_b * (w0 + t);
+      red_add_v4(a.accum + p.pixel, (rr == rr) ? rr : 0.f, (rg == rg) ? rg : 0.f, (rb == rb) ? rb : 0.f, 1.f);
+      ++n_paths;
+      p.active = false;
+    } else if (p.depth_left <= 1u) {                               // depth - 1 == 0 returns black whatever the scatter does (raytracer.hpp:26)
+      red_add_v4(a.accum + p.pixel, 0.f, 0.f, 0.f, 1.f);
+      ++n_paths;
+      p.active = false;
+    } else {
+      scatter_lane = true;
+    }
+  }
+  // lanes without a path take the next work items together (slot_refill_pooled)
+  const bool need = !p.active && !p.done;
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+  if (need_mask) {
+    const unsigned n = __popc(need_mask), k = __popc(need_mask & ((1u << lane) - 1u));
+    const unsigned long long avail = wp.end - wp.next;
+    const unsigned long long w = k < avail ? wp.next + k : wp.nxt + (k - avail);
+    if (n <= avail) {
+      wp.next += n;
+    } else {
+      wp.next = wp.nxt + (n - avail);
+      wp.end = wp.nxt + WorkPool::kBatch;
+      unsigned long long b = 0;
+      if (lane == 0) b = atomicAdd(a.counters, (unsigned long long)WorkPool::kBatch);
+      wp.nxt = __shfl_sync(0xffffffffu, b, 0);
+    }
+    if (need) slot_assign(p, a, w, n_pixels, inv_np);
+  }
+  const bool fresh = need && !p.done && p.valid;
+  uint32_t mt = 0;
+  float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scatter_lane) {
+    ++p.bounce;
+    mt = __ldg(&a.sc.mat_type[h.id]);
+    mp = __ldg(&a.sc.mat_param[h.id]);
+  }
+  philox_out r{0u, 0u, 0u, 0u};
+  if (fresh || (scatter_lane && (mt != UECRT_MAT_METAL || mp.w > 0.f)))
+    r = philox4x32_10(p.pixel, p.sample, fresh ? 0u : p.bounce, 0u, a.key0, a.key1);
+  if (fresh) {
+    slot_camera_ray(p, a, r, inv_w, inv_h, n_paths);
+  } else if (scatter_lane) {
+    const ScatterOut s = scatter_material(mt, mp, p.dx, p.dy, p.dz, h.nx, h.ny, h.nz, h.front, uecrt_u01(r.x), uecrt_u01(r.y), uecrt_u01(r.z), uecrt_u01(r.w));
+    if (s.ok) {
+      p.thr_r *= s.ar; p.thr_g *= s.ag; p.thr_b *= s.ab;
+      p.ox = h.px; p.oy = h.py; p.oz = h.pz;
+      const float len2 = fmaf(s.dz, s.dz, fmaf(s.dy, s.dy, s.dx * s.dx));
+      const float inv = rsqrt_nr(len2);
+      p.dlen = len2 * inv;
+      p.dx = s.dx * inv; p.dy = s.dy * inv; p.dz = s.dz * inv;
+      p.self_id = h.id;
+      --p.depth_left;
+    } else {                                                       // absorbed: black; the lane is refilled next round
+      red_add_v4(a.accum + p.pixel, 0.f, 0.f, 0.f, 1.f);
+      ++n_paths;
+      p.active = false;
+    }
   }
 }
 
@@ -654,7 +731,7 @@ __device__ __forceinline__ void tc_closest_hit(tc::Shade& sh, uint32_t& m, uint3
       tc::shade_wait(sh, m++);
       UECRT_TCP(prof, 3)
       tc::for_each_flag(sh, SWEEP ? 0u : ((m - 1u) & 1u), q.live, [&](int k) {
-        auto test = [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); };
+        auto test = [&](int j) { test_exact(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best, q.self_id); };
         if (tc::kQuad == 4) tc_quad(sc, (int)base + k, qr, test); else test((int)base + k);
       });
       if (!SWEEP || ++p == npasses) break;
@@ -707,7 +784,7 @@ __device__ __forceinline__ void tc_collect_hit_with(ForEach&& fe, uint32_t s_qua
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
     fe([&](int k) {
-      auto test = [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); };
+      auto test = [&](int j) { test_exact_g(tc::lds_f4(s_geom + 16u * (uint32_t)j), j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best, q.self_id); };
       if (tc::kQuad == 4) tc_quad_s(s_quads, plane, k, qr, test); else test(k);
     });
     if (best.id >= 0) {
@@ -926,6 +1003,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   tc::cta_teardown(tmem_base);
 }
 
+#ifndef UECRT_TS_FUSED_SHADE
+#define UECRT_TS_FUSED_SHADE 0  // 1: one Philox block per round for the scatter and the next path's camera ray (slot_shade_refill_fused); same paths, measured SLOWER (17.55 against 17.35 ms at 100 spp)
+#endif
 #ifndef UECRT_TS_PLANAR
 #define UECRT_TS_PLANAR 0      // 1: planar copy of the quad table in shared memory (fewer bank conflicts, measured SLOWER: 17.05 against 16.65 ms at 100 spp)
 #endif
@@ -972,6 +1052,10 @@ __device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned ch
     Hit h;
     tc_collect_hit_with<EXACT>([&](auto&& f) { ts::for_each_flag(sh, q.live, f); }, s_quads, UECRT_TS_PLANAR ? (uint32_t)nchunks * (ts::kNC * 4u) : 0u, s_geom, q, h);
     UECRT_TCP(prof, 4)
+#if UECRT_TS_FUSED_SHADE
+    slot_shade_refill_fused(st, h, a, pool, lane, n_pixels, inv_np, inv_w, inv_h, n_rays, n_paths);   // shade, and the next path's camera ray, on one Philox block
+    UECRT_TCP(prof, 5)
+#else
     if (st.active) {
       ++n_rays;
       slot_shade(st, h, a, n_paths);
@@ -979,6 +1063,7 @@ __device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned ch
     UECRT_TCP(prof, 5)
     slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);   // a path that ended: the next one's camera ray
     UECRT_TCP(prof, 1)
+#endif
 #ifdef UECRT_TC_PROFILE
     prof.t[6] += prof.last - pc_start;
     ++pc_rounds;
@@ -1153,7 +1238,7 @@ __device__ __forceinline__ void grid_closest_hit(const DeviceScene& sc, const Ra
     const double Ox = q.ox, Oy = q.oy, Oz = q.oz, Dx = q.dx, Dy = q.dy, Dz = q.dz;
     const double a = __dadd_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(Dy, Dy)), __dmul_rn(Dz, Dz));
     grid_walk(sc.grid, q.ox, q.oy, q.oz, q.dx, q.dy, q.dz,
-              [&](int j) { test_exact<false>(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best); },
+              [&](int j) { test_exact<false>(sc.geom, j, Ox, Oy, Oz, Dx, Dy, Dz, a, (double)q.tmin, best, q.self_id); },
               [&]() { return (float)best.t; }, n_tests);
     if (best.id >= 0) {
       const float4 g = __ldg(&sc.geom[best.id]);
