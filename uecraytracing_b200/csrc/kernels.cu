@@ -1043,9 +1043,9 @@ __device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned ch
     ts::submit(sh, T, make_scan_ray(st.ox, st.oy, st.oz, st.dx, st.dy, st.dz), st.active);
     UECRT_TCP(prof, 2)
 #ifdef UECRT_TC_PROFILE
-    ts::scan_tile(sh, T, &prof.t[0]);
+    ts::scan_tile(sh, T, UECRT_TS_IDLE_SKIP && !__any_sync(0xffffffffu, st.active), &prof.t[0]);
 #else
-    ts::scan_tile(sh, T);
+    ts::scan_tile(sh, T, UECRT_TS_IDLE_SKIP && !__any_sync(0xffffffffu, st.active));
 #endif
     UECRT_TCP(prof, 3)
     const RayQuery q{st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, 0.001f * st.dlen, st.self_id, st.active};
