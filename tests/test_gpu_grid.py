@@ -122,3 +122,38 @@ def test_render_traces_the_same_paths_as_brute_force(u, name, cam, W, spp, other
     assert np.array_equal(aa[..., 3], ab[..., 3])
     assert np.abs(aa[..., :3] - ab[..., :3]).max() <= 1e-4 * spp
     assert 0 < sa["sphere_tests"] < sb["sphere_tests"] or sc.n <= 8          # the grid tests fewer spheres than N per ray
+
+
+def _mixed_scene(u, seed=4):
+    """8000 pebbles, 200 boulders 20 - 40 x their size and the ground: one cell size cannot serve all three."""
+    rng = np.random.default_rng(seed)
+    r_small, r_big = rng.uniform(0.1, 0.3, 8000), rng.uniform(3.0, 6.0, 200)
+    geom = [[0, -1000, 0, 1000]]
+    geom += [[x, r, z, r] for x, z, r in zip(rng.uniform(-60, 60, 8000), rng.uniform(-60, 60, 8000), r_small)]
+    geom += [[x, r, z, r] for x, z, r in zip(rng.uniform(-60, 60, 200), rng.uniform(-60, 60, 200), r_big)]
+    geom = np.array(geom, np.float32)
+    n = len(geom)
+    mats = rng.integers(0, 3, n).astype(np.uint32); mats[0] = 0
+    par = np.concatenate([rng.uniform(0.2, 0.9, (n, 3)), np.where(mats[:, None] == 2, 1.5, rng.uniform(0, 0.3, (n, 1)))], axis=1).astype(np.float32)
+    return u.Scene(geom, mats, par)
+
+
+def test_two_level_grid_mixed_radii(grid, oracle):
+    """Scenes whose radii span orders of magnitude get a second, coarse grid level over the spheres too large for the fine one
+    (csrc/grid_build.hpp build_grids; the host test checks the level structure).  Same contract: the oracle's hits bit for bit,
+    and a render traces exactly the rays the brute-force scan traces."""
+    u = grid
+    sc = _mixed_scene(u)
+    cam = u.Camera.lookat((20, 3, 8), (0, 0.5, 0), vfov=50.0)
+    o, d = primary_rays(cam, 480, u.image_height(480))
+    want = oracle.hits(sc, o.astype(np.float64), d.astype(np.float64))
+    assert (want[2] > 8000).sum() > 2000 and ((want[2] > 0) & (want[2] <= 8000)).sum() > 2000        # boulders and pebbles are both seen
+    _check_exact(u.primary_hits(sc, o, d, exact=True), want, "mixed radii grid")
+    rng = np.random.default_rng(12)
+    o2 = rng.uniform(-65, 65, (50000, 3)).astype(np.float32); o2[:, 1] = np.abs(o2[:, 1]) * 0.15 + 0.05
+    d2 = rng.normal(size=(50000, 3)).astype(np.float32)
+    _check_exact(u.primary_hits(sc, o2, d2, exact=True), oracle.hits(sc, o2.astype(np.float64), d2.astype(np.float64)), "mixed radii grid, random rays")
+    _, _, sg = u.render(sc, cam, 200, 4, 50, seed=6, scan="grid")
+    _, _, st = u.render(sc, cam, 200, 4, 50, seed=6, scan="tensor")
+    assert sg["scan_mode"] == 3 and st["scan_mode"] == 2 and sg["rays_traced"] == st["rays_traced"]
+    assert sg["sphere_tests"] / sg["rays_traced"] < 40          # with the boulders in the always-list it would be > 200

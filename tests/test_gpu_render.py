@@ -318,3 +318,28 @@ def test_device_camera_rays_match_reference_camera(u, oracle, cam_name, W):
         assert np.abs(d[k] - rd).max() <= 3e-6 * scale + 4e-6 * lens, (k, d[k], rd)
     if lens == 0.0:
         assert np.all(o == np.asarray(cam.s.origin, np.float32))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")), reason="binary not built")
+def test_cli_verbose_levels_print_the_reference_progress_lines(tmp_path):
+    """-l 1 / -l 2 (source.cpp:128-152): "(row,col) : (y,x)" per pixel and "(row,col,sam) : (y,x,s)" per sample, in loop order,
+    field widths ceil(log10(extent)) - 1, between "rendering..." and "rendering finished"."""
+    import math
+    exe = os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")
+    W, S = 128, 12
+    H = int(W / (16.0 / 9.0))
+    wy, wx, ws = (max(0, math.ceil(math.log10(v)) - 1) for v in (H, W, S))
+    for level in (1, 2):
+        r = subprocess.run([exe, "-l", str(level), "--width", str(W), "--spp", str(S), "--seed", "3", str(tmp_path / "v.png")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.split("\n")
+        assert lines[0] == "rendering..." and "rendering finished" in lines and lines[-2] == "success"
+        body = lines[1:lines.index("rendering finished")]
+        want = []
+        for y in range(H):
+            for x in range(W):
+                want.append(f"(row,col) : ({y:>{wy}},{x:>{wx}})")
+                if level > 1:
+                    want += [f"(row,col,sam) : ({y:>{wy}},{x:>{wx}},{s:>{ws}})" for s in range(S)]
+        assert body[:len(want)] == want                      # then the -v timing line of this implementation
+        assert len(body) == len(want) + 1 and body[-1].startswith("K1 render_paths")

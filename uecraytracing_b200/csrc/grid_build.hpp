@@ -28,23 +28,26 @@ struct HostGrid {
   std::vector<uint32_t> always;       // spheres tested for every ray (too large for the grid), ascending
 };
 
-inline HostGrid build_grid(const uecrt_scene& sc) {
+// One grid level over the spheres `subset` (ascending indices).  Spheres of the subset whose radius exceeds 8 x the
+// subset's median radius would be listed in a huge number of cells: they are returned in g.always instead.  With
+// grow_to_fit (the last level) that limit is raised until at most 64 spheres are left over.
+inline HostGrid build_grid_level(const uecrt_scene& sc, const std::vector<uint32_t>& subset, bool grow_to_fit) {
   HostGrid g;
-  const uint32_t n = sc.n;
+  const uint32_t n = (uint32_t)subset.size();
   g.cell_start.assign(2, 0);
   if (n == 0) return g;
-  std::vector<float> radii(n);
-  for (uint32_t i = 0; i < n; ++i) radii[i] = std::fabs(sc.geom[i].w);
-  std::vector<float> sorted = radii;
+  std::vector<float> radii(sc.n, 0.f);
+  std::vector<float> sorted;
+  sorted.reserve(n);
+  for (uint32_t i : subset) { radii[i] = std::fabs(sc.geom[i].w); sorted.push_back(radii[i]); }
   std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
   const float r_med = std::max(sorted[n / 2], 1e-6f);
-  // spheres far larger than the typical one would be listed in a huge number of cells: test them always
   float big = 8.0f * r_med;
   std::vector<uint32_t> small;
   for (int attempt = 0; attempt < 8; ++attempt) {
     small.clear(); g.always.clear();
-    for (uint32_t i = 0; i < n; ++i) (radii[i] <= big ? small : g.always).push_back(i);
-    if (g.always.size() <= 64) break;
+    for (uint32_t i : subset) (radii[i] <= big ? small : g.always).push_back(i);
+    if (!grow_to_fit || g.always.size() <= 64) break;
     big *= 4.0f;
   }
   if (small.empty()) return g;           // everything is in the always-list: one empty cell
@@ -103,6 +106,39 @@ inline HostGrid build_grid(const uecrt_scene& sc) {
     }
   }
   return g;
+}
+
+// TWO levels: a fine grid over the typical spheres, and -- when more than kCoarseMin spheres are too large for it -- a
+// coarse grid over those, sized by THEIR median radius; what is too large even for that one (the r = 1000 ground) is
+// tested for every ray.  One cell size cannot serve a scene whose radii span orders of magnitude: a medium sphere in
+// the fine grid is listed in thousands of cells, in the always-list it costs every ray a test.
+constexpr size_t kCoarseMin = 8;
+struct HostGrids {
+  HostGrid fine, coarse;             // coarse.items empty: one level only
+  std::vector<uint32_t> always;      // ascending
+};
+inline HostGrids build_grids(const uecrt_scene& sc) {
+  HostGrids G;
+  std::vector<uint32_t> all(sc.n);
+  for (uint32_t i = 0; i < sc.n; ++i) all[i] = i;
+  HostGrid one = build_grid_level(sc, all, /*grow_to_fit=*/false);
+  if (one.always.size() <= kCoarseMin) {
+    G.fine = build_grid_level(sc, all, true);        // a handful of large spheres: the single level with its always-list
+    G.always = G.fine.always;
+    G.coarse.cell_start.assign(2, 0);
+  } else {
+    G.coarse = build_grid_level(sc, one.always, true);
+    G.always = G.coarse.always;
+    G.fine = std::move(one);
+  }
+  G.fine.always.clear(); G.coarse.always.clear();
+  return G;
+}
+// the single-level form (round 1), kept for its host test
+inline HostGrid build_grid(const uecrt_scene& sc) {
+  std::vector<uint32_t> all(sc.n);
+  for (uint32_t i = 0; i < sc.n; ++i) all[i] = i;
+  return build_grid_level(sc, all, true);
 }
 
 }  // namespace uecrt

@@ -2,7 +2,8 @@
 // the point where the ray enters the grid box, testing the spheres listed in every cell it passes with the
 // SAME per-sphere test as the brute-force scans (closest_hit.cuh test_fast / test_exact, unordered tie rule),
 // and stopping once the closest hit so far lies before the exit of the current cell.  Spheres too large
-// for the grid (the `always` list: e.g. the r = 1000 ground) are tested first for every ray.
+// for any level (the `always` list: e.g. the r = 1000 ground) are tested first for every ray; with two levels the coarse
+// one is walked before the fine one, and the order-independent tie rule makes the order immaterial to the result.
 //
 // Why no hit is lost: a sphere is listed in every cell its bounding box, inflated by eps = 1e-4 x scene extent,
 // overlaps; the ray's true path through the grid and the DDA's FP32 cell sequence differ only within
@@ -18,11 +19,10 @@
 
 namespace uecrt {
 
-// test(j) runs the per-sphere test; best_t() returns the current closest distance along the UNIT direction
+// one level: test(j) runs the per-sphere test; best_t() returns the current closest distance along the UNIT direction
 template <class Test, class BestT>
-__device__ __forceinline__ void grid_walk(const DeviceGrid& G, float ox, float oy, float oz, float dx, float dy, float dz,
-                                          Test&& test, BestT&& best_t, unsigned& n_tests) {
-  for (int e = 0; e < G.n_always; ++e) { test((int)__ldg(&G.always[e])); ++n_tests; }
+__device__ __forceinline__ void grid_walk_level(const DeviceGridLevel& G, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                Test&& test, BestT&& best_t, unsigned& n_tests) {
   if (!G.cell_start) return;
   const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
   // slab test against the grid box
@@ -80,6 +80,15 @@ __device__ __forceinline__ void grid_walk(const DeviceGrid& G, float ox, float o
     c += (uint32_t)(sx ? stride[0] : sy ? stride[1] : stride[2]);
     tmax[0] += sx ? tdelta[0] : 0.0f; tmax[1] += sy ? tdelta[1] : 0.0f; tmax[2] += sz ? tdelta[2] : 0.0f;
   }
+}
+
+// the always-list, then the coarse level (few, large spheres: an early bound on the closest hit), then the fine level
+template <class Test, class BestT>
+__device__ __forceinline__ void grid_walk(const DeviceGrid& G, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          Test&& test, BestT&& best_t, unsigned& n_tests) {
+  for (int e = 0; e < G.n_always; ++e) { test((int)__ldg(&G.always[e])); ++n_tests; }
+  grid_walk_level(G.lvl[1], ox, oy, oz, dx, dy, dz, test, best_t, n_tests);
+  grid_walk_level(G.lvl[0], ox, oy, oz, dx, dy, dz, test, best_t, n_tests);
 }
 
 }  // namespace uecrt

@@ -5,13 +5,17 @@
 
 namespace uecrt {
 
-// uniform grid over the spheres (grid_build.hpp): cell (x, y, z) lists items[cell_start[c] .. cell_start[c+1]),
-// c = (z * dim[1] + y) * dim[0] + x; `always` spheres are tested for every ray
-struct DeviceGrid {
+// uniform grid over the spheres (grid_build.hpp): per level, cell (x, y, z) lists items[cell_start[c] .. cell_start[c+1]),
+// c = (z * dim[1] + y) * dim[0] + x.  Two levels (fine: the typical spheres; coarse: the ones too large for it, empty when
+// there are only a few); `always` spheres are tested for every ray.
+struct DeviceGridLevel {
   float org[3], cell[3], inv_cell[3];
   int dim[3];
-  const uint32_t* cell_start;     // null: no grid uploaded
+  const uint32_t* cell_start;     // null: level not present
   const uint32_t* items;
+};
+struct DeviceGrid {
+  DeviceGridLevel lvl[2];         // [0] fine, [1] coarse
   const uint32_t* always;
   int n_always;
 };

@@ -144,8 +144,8 @@ struct uecrt_ctx {
   int regs_tc = 0;
   // uniform grid (grid_build.hpp): built and uploaded on first use of UECRT_SCAN_GRID with the current scene
   std::vector<uecrt_float4> h_geom;
-  void *d_cell_start = nullptr, *d_items = nullptr, *d_always = nullptr;
-  size_t cap_cells = 0, cap_items = 0, cap_always = 0;
+  void *d_cell_start[2] = {nullptr, nullptr}, *d_items[2] = {nullptr, nullptr}, *d_always = nullptr;   // [0] fine, [1] coarse level
+  size_t cap_cells[2] = {0, 0}, cap_items[2] = {0, 0}, cap_always = 0;
   bool grid_ready = false;
   int regs_grid = 0, blocks_grid[2] = {0, 0};
   int last_scan_mode = UECRT_SCAN_FP32, last_threads = uecrt::kRenderThreads, last_regs = 0;
@@ -257,7 +257,8 @@ void ctx_free(uecrt_ctx* c) {
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   cudaFree(c->d_pairs); cudaFree(c->d_geom); cudaFree(c->d_mat_type); cudaFree(c->d_mat_param); cudaFree(c->d_counters); cudaFree(c->d_tc); cudaFree(c->d_quads); cudaFree(c->d_hits);
-  cudaFree(c->d_cell_start); cudaFree(c->d_items); cudaFree(c->d_always);
+  for (int l = 0; l < 2; ++l) { cudaFree(c->d_cell_start[l]); cudaFree(c->d_items[l]); }
+  cudaFree(c->d_always);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   cudaSetDevice(prev);
@@ -370,7 +371,7 @@ void release_workspaces() {
 int ctx_ensure_grid(uecrt_ctx* c) {
   if (c->grid_ready) return UECRT_OK;
   uecrt_scene sc{c->n, c->h_geom.data(), nullptr, nullptr};
-  const uecrt::HostGrid g = uecrt::build_grid(sc);
+  const uecrt::HostGrids G = uecrt::build_grids(sc);
   auto up = [&](void*& dptr, size_t& cap, const std::vector<uint32_t>& v) -> int {
     const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(uint32_t);
     if (bytes > cap) {
@@ -382,16 +383,21 @@ int ctx_ensure_grid(uecrt_ctx* c) {
     return UECRT_OK;
   };
   int rc;
-  if ((rc = up(c->d_cell_start, c->cap_cells, g.cell_start)) || (rc = up(c->d_items, c->cap_items, g.items)) ||
-      (rc = up(c->d_always, c->cap_always, g.always)))
-    return rc;
+  const uecrt::HostGrid* level[2] = {&G.fine, &G.coarse};
+  for (int l = 0; l < 2; ++l)
+    if ((rc = up(c->d_cell_start[l], c->cap_cells[l], level[l]->cell_start)) || (rc = up(c->d_items[l], c->cap_items[l], level[l]->items))) return rc;
+  if ((rc = up(c->d_always, c->cap_always, G.always))) return rc;
   CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));      // as in ctx_upload_scene: the grid is complete before any launch reads it
   uecrt::DeviceGrid& d = c->sc.grid;
-  for (int a = 0; a < 3; ++a) { d.org[a] = g.org[a]; d.cell[a] = g.cell[a]; d.inv_cell[a] = g.inv_cell[a]; d.dim[a] = g.dim[a]; }
-  d.cell_start = g.items.empty() ? nullptr : static_cast<const uint32_t*>(c->d_cell_start);
-  d.items = static_cast<const uint32_t*>(c->d_items);
+  for (int l = 0; l < 2; ++l) {
+    const uecrt::HostGrid& g = *level[l];
+    uecrt::DeviceGridLevel& dl = d.lvl[l];
+    for (int a = 0; a < 3; ++a) { dl.org[a] = g.org[a]; dl.cell[a] = g.cell[a]; dl.inv_cell[a] = g.inv_cell[a]; dl.dim[a] = g.dim[a]; }
+    dl.cell_start = g.items.empty() ? nullptr : static_cast<const uint32_t*>(c->d_cell_start[l]);
+    dl.items = static_cast<const uint32_t*>(c->d_items[l]);
+  }
   d.always = static_cast<const uint32_t*>(c->d_always);
-  d.n_always = (int)g.always.size();
+  d.n_always = (int)G.always.size();
   cudaError_t e = uecrt::configure_kernels_grid(&c->regs_grid, c->blocks_grid);
   if (e != cudaSuccess || c->blocks_grid[0] < 1 || c->blocks_grid[1] < 1)
     return fail(UECRT_ERR_CUDA, "grid kernel configuration failed: %s", cudaGetErrorString(e));

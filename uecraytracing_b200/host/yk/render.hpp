@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <functional>
+#include <iomanip>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -57,6 +58,24 @@ struct image_t {
   const std::uint8_t* data() const { return reinterpret_cast<const std::uint8_t*>(pixels.data()); }
 };
 
+// The reference's verbose levels 1 and 2 (source.cpp:128-152): one "(row,col) : (y,x)" line per pixel and, at level 2,
+// one "(row,col,sam) : (y,x,s)" line per sample, in loop order, with its field widths.  They carry no result, so the
+// re-hosted render() prints them up front (the pixels are no longer visited one at a time).  Level 3's per-ray lines
+// (raytracer.hpp:21-25) exist on the host mirror's ray_color only: K1's rays live on the device.
+inline void print_progress_lines(std::uint32_t width, std::uint32_t height, std::uint32_t spp) {
+  if (!verbose) return;
+  const int wy = (int)std::ceil(std::log10((double)height)) - 1, wx = (int)std::ceil(std::log10((double)width)) - 1,
+            ws = (int)std::ceil(std::log10((double)spp)) - 1;
+  for (std::uint32_t y = 0; y < height; ++y)
+    for (std::uint32_t x = 0; x < width; ++x) {
+      std::cout << "(row,col) : (" << std::setw(wy) << y << ',' << std::setw(wx) << x << ")\n";
+      if (verbose > 1)
+        for (std::uint32_t k = 0; k < spp; ++k)
+          std::cout << "(row,col,sam) : (" << std::setw(wy) << y << ',' << std::setw(wx) << x << ',' << std::setw(ws) << k << ")\n";
+    }
+  std::cout.flush();
+}
+
 inline image_t render(const hittable_list<double>& world, const camera<double>& cam, const render_config& cfg, bool keep_accum = false) {
   image_t img;
   img.width = cfg.width;
@@ -64,6 +83,7 @@ inline image_t render(const hittable_list<double>& world, const camera<double>& 
   img.pixels.resize((std::size_t)img.width * img.height);
   if (keep_accum) img.accum.resize((std::size_t)img.width * img.height * 4);
   std::cout << "rendering..." << std::endl;                      // source.cpp:114
+  print_progress_lines(img.width, img.height, cfg.spp);
   const uecrt_scene sc = world.flatten();
   const uecrt_camera c = cam.flatten();
   uecrt_params p{};
