@@ -1003,6 +1003,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_render_paths_tc(const Rende
   tc::cta_teardown(tmem_base);
 }
 
+#ifndef UECRT_TS_PIN
+#define UECRT_TS_PIN 1      // loop-invariant shared addresses pinned in registers (17.33 -> 17.03 ms at 100 spp)
+#endif
 #ifndef UECRT_TS_FUSED_SHADE
 #define UECRT_TS_FUSED_SHADE 0  // 1: one Philox block per round for the scatter and the next path's camera ray (slot_shade_refill_fused); same paths, measured SLOWER (17.55 against 17.35 ms at 100 spp)
 #endif
@@ -1016,8 +1019,18 @@ __device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned ch
   ts::Header* hdr = reinterpret_cast<ts::Header*>(smem_raw);
   ts::Shade sh = ts::make_shade(smem_raw, tmem_base, nchunks);
   const ts::Layout lay = ts::make_layout((uint32_t)nchunks * ts::kNC);
-  const uint32_t s_quads = tc::smem_addr(smem_raw + lay.quads), s_geom = tc::smem_addr(smem_raw + lay.geom);
-  const unsigned lane = threadIdx.x & 31u;
+  uint32_t s_quads = tc::smem_addr(smem_raw + lay.quads), s_geom = tc::smem_addr(smem_raw + lay.geom);
+#if UECRT_TS_PIN
+  // keep the loop-invariant shared addresses in registers: ptxas otherwise re-derives them from S2UR SR_CgaCtaId inside the
+  // resolve loop (3 % of the executed instructions, ncu line attribution of __cvta_generic_to_shared)
+  tc::pin(s_quads); tc::pin(s_geom); tc::pin(sh.words); tc::pin(sh.full); tc::pin(sh.empty0); tc::pin(sh.lane_taddr);
+  tc::pin(sh.a_ready0); tc::pin(sh.a_free0); tc::pin(sh.is_lane0);
+#endif
+  uint32_t flags0 = tc::smem_addr(&hdr->done_flags[0][0]), my_flag0 = flags0 + (threadIdx.x >> 5), my_lane = sh.g % (uint32_t)ts::kLanes;
+  unsigned lane = threadIdx.x & 31u;
+#if UECRT_TS_PIN
+  tc::pin(flags0); tc::pin(my_flag0); tc::pin(my_lane); tc::pin(lane);
+#endif
   const unsigned long long n_pixels = a.n_slots;
   const double inv_np = 1.0 / (double)n_pixels;
   const float inv_w = 1.0f / (float)a.width, inv_h = 1.0f / (float)a.height;
@@ -1033,13 +1046,13 @@ __device__ __forceinline__ void shade_role_self(const RenderArgs& a, unsigned ch
   st.dz = 1.f; st.dlen = 1.f; st.self_id = -1;
   slot_refill_pooled(st, pool, a, lane, n_pixels, inv_np, inv_w, inv_h, n_paths);
   uint32_t T = sh.g;                              // this group's tile of the round: T = round * kGroups + group
-  for (uint32_t r = 0; ts::round_continues(hdr, sh.g % (uint32_t)ts::kLanes, r); ++r, T += (uint32_t)ts::kGroups) {
+  for (uint32_t r = 0; ts::round_continues_s(flags0, my_lane, r); ++r, T += (uint32_t)ts::kGroups) {
 #ifdef UECRT_TC_PROFILE
     const long long pc_start = prof.last;
 #endif
     // termination vote (tc_self.cuh): this warp's flag of this round, stored before its a_ready arrive
     const bool warp_done = __all_sync(0xffffffffu, st.done);
-    if (lane == 0) hdr->done_flags[r & 7u][threadIdx.x >> 5] = warp_done ? 1 : 0;
+    if (lane == 0) ts::vote_s(my_flag0, r, warp_done);
     ts::submit(sh, T, make_scan_ray(st.ox, st.oy, st.oz, st.dx, st.dy, st.dz), st.active);
     UECRT_TCP(prof, 2)
 #ifdef UECRT_TC_PROFILE

@@ -160,6 +160,23 @@ __device__ __forceinline__ bool lane_done_at(const Header* h, uint32_t lane, uin
   return all == 0x01010101u;
 }
 __device__ __forceinline__ bool round_continues(const Header* h, uint32_t lane, uint32_t r) { return !(r >= 2u && lane_done_at(h, lane, r - 2u)); }
+// the same through a SHARED address kept in a register (flags0 = shared address of done_flags[0][0]): the generic-pointer
+// form makes ptxas re-derive the shared window base from S2UR SR_CgaCtaId in every round
+__device__ __forceinline__ bool round_continues_s(uint32_t flags0, uint32_t lane, uint32_t r) {
+  if (r < 2u) return true;
+  const uint32_t row = flags0 + 32u * ((r - 2u) & 7u) + 4u * lane;
+  uint32_t all = 0x01010101u;
+#pragma unroll
+  for (int g = 0; g < kGroups; g += kLanes) {
+    uint32_t f;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(f) : "r"(row + 4u * (uint32_t)g));
+    all &= f;
+  }
+  return all != 0x01010101u;
+}
+__device__ __forceinline__ void vote_s(uint32_t my_flag0, uint32_t r, bool warp_done) {   // my_flag0 = flags0 + warp index; one lane calls it
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(my_flag0 + 32u * (r & 7u)), "r"(warp_done ? 1u : 0u) : "memory");
+}
 
 // ISSUER of lane `lane`: the whole warp runs the loop and waits convergently, one elected lane issues (tc_scan.cuh issuer_role)
 __device__ __forceinline__ void issuer_role(unsigned char* smem_raw, uint32_t tmem_base, int nchunks, uint32_t lane, unsigned long long* prof_counters = nullptr) {
@@ -227,6 +244,7 @@ struct Shade {
   uint32_t g;
   int nchunks;
   uint32_t gparity = 0;                          // parity of the group's next chunk
+  uint32_t is_lane0;                             // 1 in lane 0 of the warp (kept in a register: SR_TID is ~25 cycles away)
 };
 __device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tmem_base, int nchunks) {
   Header* h = reinterpret_cast<Header*>(smem_raw);
@@ -238,6 +256,7 @@ __device__ __forceinline__ Shade make_shade(unsigned char* smem_raw, uint32_t tm
   s.lane_taddr = tmem_base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16);
   s.words = tc::smem_addr(smem_raw + lay.words) + threadIdx.x * 4u;
   s.nchunks = nchunks;
+  s.is_lane0 = (threadIdx.x & 31u) == 0u ? 1u : 0u;
   return s;
 }
 
@@ -257,14 +276,14 @@ __device__ __forceinline__ void submit(const Shade& s, uint32_t T, const ScanRay
   tc::tmem_st_wait();
   tc::fence_before_sync();
   __syncwarp();
-  if ((threadIdx.x & 31u) == 0u) tc::mbar_arrive(s.a_ready0 + 8u * aslot);
+  if (s.is_lane0) tc::mbar_arrive(s.a_ready0 + 8u * aslot);
 }
 
 // SHADE: read the accumulators of this thread's ray for every chunk of tile T as the MMAs complete and leave one
 // flag word per chunk (bit 31 - k = some sphere of quad k of the chunk may be hit) in the thread's private words.
 __device__ __forceinline__ void scan_tile(Shade& s, uint32_t T, bool warp_idle, long long* prof_wait = nullptr) {
   const uint32_t slot = T % (uint32_t)kLanes;
-  const bool lane0 = (threadIdx.x & 31u) == 0u;
+  const bool lane0 = s.is_lane0 != 0u;
   for (int j = 0; j < s.nchunks; ++j) {
 #ifdef UECRT_TC_PROFILE
     const long long pw0 = clock64();
