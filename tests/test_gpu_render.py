@@ -217,7 +217,7 @@ def test_cli_scan_flag_three_searches_one_image(tmp_path):
     imgs = {}
     for mode in ("fp32", "tensor", "grid"):
         out = tmp_path / f"{mode}.png"
-        r = subprocess.run([exe, "-v", "--scene", "final", "--width", "240", "--spp", "16", "--seed", "7", "--scan", mode, str(out)],
+        r = subprocess.run([exe, "--stats", "--scene", "final", "--width", "240", "--spp", "16", "--seed", "7", "--scan", mode, str(out)],
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "success" in r.stdout, r.stdout + r.stderr
         assert {"fp32": "FP32-pipe scan", "tensor": "tensor-core scan", "grid": "uniform grid"}[mode] in r.stdout
@@ -286,7 +286,7 @@ def test_cli_frames_sequence(u, tmp_path):
     """--frames N --orbit DEG: N PNGs through the frame queue; frame 0 is the still image of the same seed."""
     exe = os.path.join(ROOT, "uecraytracing_b200", "bin", "raytrace")
     out = tmp_path / "seq.png"
-    r = subprocess.run([exe, "-v", "--scene", "final", "--width", "240", "--spp", "8", "--seed", "21", "--frames", "3", "--orbit", "10", str(out)],
+    r = subprocess.run([exe, "--stats", "--scene", "final", "--width", "240", "--spp", "8", "--seed", "21", "--frames", "3", "--orbit", "10", str(out)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("success"), r.stdout + r.stderr
     assert "3 frames in" in r.stdout and "ms per frame" in r.stdout

@@ -11,8 +11,8 @@ python bench.py --workload ref4 --steps 20 --no-cpu-baseline > $O/bench_r2_ref4.
 python tools/psnr_gate.py > $O/psnr_gate_r2.json 2> $O/psnr_gate_r2.err
 python tools/convergence_sweep.py > $O/convergence_r2.log 2>&1
 python tools/fast_accuracy.py > $O/fast_accuracy_r2.log 2>&1
-./uecraytracing_b200/bin/raytrace -v --scene final --width 3840 --spp 64 --seed 3 --frames 8 --orbit 3 /tmp/seq.png > $O/frames_4k_r2.log 2>&1
-./uecraytracing_b200/bin/raytrace -v --scene final --width 3840 --spp 64 --seed 3 /tmp/one.png >> $O/frames_4k_r2.log 2>&1
+./uecraytracing_b200/bin/raytrace --stats --scene final --width 3840 --spp 64 --seed 3 --frames 8 --orbit 3 /tmp/seq.png > $O/frames_4k_r2.log 2>&1
+./uecraytracing_b200/bin/raytrace --stats --scene final --width 3840 --spp 64 --seed 3 /tmp/one.png >> $O/frames_4k_r2.log 2>&1
 # profiler passes LAST (numbers printed under ncu are never bench values)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launch_r2.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_render_paths_ts -s 2 -c 1 -o $O/k1_ts_r2 -f python tools/profile_k1.py tensor > $O/ncu_k1_ts_r2.log 2>&1

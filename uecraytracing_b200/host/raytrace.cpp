@@ -3,7 +3,7 @@
 // stdout lines "rendering...", "rendering finished", "write to file : <f>", "success";
 // a failed write prints "error" and exits 1; an unknown option aborts (uncaught exception).
 // New, additive flags (north_star): --width --spp --depth --seed, plus --gpus --scene --dense-n
-// --exact-hits --scan --dump-accum, and --frames N --orbit DEG: N frames of a camera orbit through the frame queue
+// --exact-hits --scan --dump-accum --stats, and --frames N --orbit DEG: N frames of a camera orbit through the frame queue
 // (K1 of frame k + 1 overlaps the D2H and the PNG write of frame k; files <output stem>_0000.png ...).
 // Defaults equal the reference's macros (400 / 100 / 50).
 #include <cstdint>
@@ -31,6 +31,7 @@ int main(int argc, char* argv[]) {
       .add('v', "verbose", "verbose output", false)
       .add('o', "output", "filename of output", true)
       .add('l', "verbose-level", "set verbose level", true)
+      .add(0, "stats", "print the kernel timing line (K1 / reduce / K3 ms, samples/s) without the per-pixel lines of -v", false)
       .add(0, "width", "image width (default 400; height = width*9/16)", true)
       .add(0, "spp", "samples per pixel (default 100)", true)
       .add(0, "depth", "maximum bounce depth (default 50)", true)
@@ -53,6 +54,7 @@ int main(int argc, char* argv[]) {
   }
   if (options.count("verbose") && !yk::verbose) ++yk::verbose;
   if (options.count("verbose-level")) yk::verbose = options.as<std::uint32_t>("verbose-level");
+  yk::stats = options.count("stats") != 0;
 
   const std::string filename = options.last("output");
 
@@ -120,7 +122,7 @@ int main(int argc, char* argv[]) {
         t = std::thread([&, path, k] {
           if (!uecrt_host::write_png(path.c_str(), (int)W, (int)H, 3, copies[k & 1].data(), (int)(3 * W))) write_ok = false;
         });
-        if (yk::verbose) std::cout << "frame " << k << ": K1 " << k1_ms << " ms -> " << path << std::endl;
+        if (yk::verbose || yk::stats) std::cout << "frame " << k << ": K1 " << k1_ms << " ms -> " << path << std::endl;
       });
     } catch (const std::exception& e) {
       for (auto& t : writer) if (t.joinable()) t.join();
@@ -132,7 +134,7 @@ int main(int argc, char* argv[]) {
     for (auto& t : writer) if (t.joinable()) t.join();
     wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tj).count();
     std::cout << "rendering finished" << std::endl;
-    if (yk::verbose)
+    if (yk::verbose || yk::stats)
       std::cout << frames << " frames in " << wall * 1e3 << " ms wall-clock incl. PNG (" << wall * 1e3 / frames << " ms per frame; K1 alone " << k1_sum / frames
                 << " ms per frame)" << std::endl;
     std::cout << "write to file : " << stem << "_0000" << ext << " .. " << frames << " frames" << std::endl;

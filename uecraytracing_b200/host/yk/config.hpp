@@ -3,4 +3,5 @@
 #include <cstdint>
 namespace yk {
 inline std::uint32_t verbose = 0;
+inline bool stats = false;          // print the kernel timing line(s) without the reference's per-pixel progress lines (raytrace --stats)
 }

@@ -94,7 +94,7 @@ inline image_t render(const hittable_list<double>& world, const camera<double>& 
   static_assert(sizeof(color3b) == 3, "color3b must be 3 packed bytes");
   if (uecrt_render(&sc, &c, &p, reinterpret_cast<std::uint8_t*>(img.pixels.data()), keep_accum ? img.accum.data() : nullptr, &img.stats) != UECRT_OK)
     throw std::runtime_error(std::string("uecrt_render: ") + uecrt_last_error());
-  if (verbose) {
+  if (verbose || stats) {
     const double samples = (double)img.width * img.height * cfg.spp;
     std::cout << "K1 render_paths (" << (img.stats.scan_mode == UECRT_SCAN_TENSOR ? "tensor-core scan" : img.stats.scan_mode == UECRT_SCAN_GRID ? "uniform grid" : "FP32-pipe scan") << ") "
               << img.stats.kernel_ms << " ms, reduce " << img.stats.reduce_ms << " ms, K3 resolve "
