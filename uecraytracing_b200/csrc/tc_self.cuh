@@ -85,7 +85,7 @@ __host__ __device__ inline Layout make_layout(uint32_t rows) {
   Layout l;
   l.b = kHeaderBytes;
   l.words = l.b + rows * 128u;
-  l.quads = l.words + (rows / (uint32_t)kNC) * (uint32_t)kShadeThreads * 4u;
+  l.quads = l.words + (rows / (uint32_t)kNC) * (uint32_t)tc::kWordsPerChunk * (uint32_t)kShadeThreads * 4u;
   l.geom = l.quads + rows * 16u;
   l.total = l.geom + rows * 16u;
   return l;
@@ -324,6 +324,26 @@ __device__ __forceinline__ void scan_tile(Shade& s, uint32_t T, bool warp_idle, 
     c3 = tc::quad_signs(p);
 #else
     int v[32], q[8];
+    if (tc::kQuad == 1) {                          // one flag per SPHERE (-DUECRT_TC_QUAD=1): four words per chunk, no quad re-test in the resolve
+      tc::tmem_ld32(t0, v);
+      tc::tmem_ld_wait();
+      c0 = tc::sign_word(v);
+      tc::tmem_ld32(t0 + 32, v);
+      tc::tmem_ld_wait();
+      c1 = tc::sign_word(v);
+      tc::tmem_ld32(t0 + 64, v);
+      tc::tmem_ld_wait();
+      c2 = tc::sign_word(v);
+      tc::tmem_ld32(t0 + 96, v);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane0) tc::mbar_arrive(s.empty0 + 8u * slot);
+      c3 = tc::sign_word(v);
+      const uint32_t o = s.words + 4u * (uint32_t)j * (kShadeThreads * 4u);
+      tc::sts32(o, c0); tc::sts32(o + kShadeThreads * 4u, c1); tc::sts32(o + 2u * kShadeThreads * 4u, c2); tc::sts32(o + 3u * kShadeThreads * 4u, c3);
+      continue;
+    }
     tc::tmem_ld32(t0, v);
     tc::tmem_ld_wait();
     tc::quad_max(v, q);
@@ -357,15 +377,16 @@ __device__ __forceinline__ void scan_tile(Shade& s, uint32_t T, bool warp_idle, 
 #endif
 template <class F>
 __device__ __forceinline__ void for_each_flag(const Shade& s, bool live, F&& f) {
-  if (UECRT_TS_UNIFORM_TRIPS && s.nchunks <= 4) {
+  const int nwords = s.nchunks * tc::kWordsPerChunk;
+  if (UECRT_TS_UNIFORM_TRIPS && nwords <= 4) {
     // up to four flag words: all loaded at once (independent loads), the trip count is the warp's maximum of the
     // lanes' flag counts (one REDUX), and every trip pops the lane's next flag from registers
     uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
     if (live) {
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s.words));
-      if (s.nchunks > 1) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s.words + 1u * (kShadeThreads * 4u)));
-      if (s.nchunks > 2) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(s.words + 2u * (kShadeThreads * 4u)));
-      if (s.nchunks > 3) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(s.words + 3u * (kShadeThreads * 4u)));
+      if (nwords > 1) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s.words + 1u * (kShadeThreads * 4u)));
+      if (nwords > 2) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(s.words + 2u * (kShadeThreads * 4u)));
+      if (nwords > 3) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(s.words + 3u * (kShadeThreads * 4u)));
     }
     const int trips = __reduce_max_sync(0xffffffffu, __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3));
     for (int t = 0; t < trips; ++t) {
@@ -382,9 +403,9 @@ __device__ __forceinline__ void for_each_flag(const Shade& s, bool live, F&& f) 
     return;
   }
   uint32_t m = 0u;
-  int w = live ? -1 : s.nchunks;
+  int w = live ? -1 : nwords;
   for (;;) {
-    while (m == 0u && w + 1 < s.nchunks) {
+    while (m == 0u && w + 1 < nwords) {
       ++w;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(s.words + (uint32_t)w * (kShadeThreads * 4u)));
     }
