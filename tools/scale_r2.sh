@@ -13,9 +13,11 @@ nvidia-smi -L | wc -l > $O/scale_r2_gpus.txt
 timeout 300 python -m pytest tests/test_gpu_render.py -q -k "multi_gpu_single_process" > $O/multigpu_test_r2.log 2>&1; tail -2 $O/multigpu_test_r2.log
 for N in 1 2 4 8; do
   run $N scale_r2_n$N --steps 10 --warmup 3 --no-cpu-baseline --no-side-scans
+  [ -n "$SCALE_ONLY_FINAL" ] && continue
   run $N scale_r2_4k_n$N --workload final4k --steps 2 --warmup 3 --no-cpu-baseline --no-side-scans
   run $N scale_r2_conv4096_n$N --workload final4096 --steps 2 --warmup 3 --no-cpu-baseline --no-side-scans --psnr
 done
+[ -n "$SCALE_ONLY_FINAL" ] && { timeout 300 python bench.py --gpus 8 --single-process --steps 5 --warmup 3 --no-cpu-baseline > $O/scale_r2_sp_n8.json 2> $O/scale_r2_sp_n8.err; exit 0; }
 for N in 2 8; do
   timeout 300 python bench.py --gpus $N --single-process --steps 5 --warmup 3 --no-cpu-baseline > $O/scale_r2_sp_n$N.json 2> $O/scale_r2_sp_n$N.err
 done
