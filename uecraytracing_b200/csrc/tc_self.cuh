@@ -2,7 +2,7 @@
 // its own 32 rays ("self-scan" pipeline; resident sphere operand, K1 only).
 //
 // The warp-specialised pipeline of tc_scan.cuh / tc_collect.cuh funnels all 128 x 512 accumulators of a tile
-// through ONE scan warp per SM sub-partition.  That warp is latency-bound (tcgen05.ld round trip ~170 cycles,
+// through ONE scan warp per SM sub-partition.  That warp is latency-bound (tcgen05.ld round trip ~190 cycles,
 // tcgen05.wait::ld waits for all of a thread's loads; 2.3 k cycles per tile at ~0.2 instructions per cycle) and
 // closes a loop with the four shade groups that wait for it: the kernel ran at 0.45 useful instructions per
 // cycle and sub-partition with 37 % of all executed instructions being barrier polls (profiles/README.md,
@@ -12,6 +12,8 @@
 //     dependent chains overlap each other (thread-level parallelism instead of one pacing warp),
 //   * the quad flags never leave the thread: no bitmap hand-off, no scan_done barrier,
 //   * the scan warpgroup's registers go to more shade groups (6 x 128 paths at 80 registers).
+// Final scene, 1200 x 675 x 500 spp on one B200: 83.5 ms per frame against 88.7 with the scan-warp pipeline of round 2's
+// start and 91.9 in round 1; what bounds it now is the length of a group's serial round, see DESIGN.md.
 // Roles of a CTA (kThreads = kGroups * 128 + 128, one CTA per SM):
 //   SHADE   kGroups groups x 128 threads, one path per thread.  Per round: lifted ray -> row of an A tile in
 //           TMEM, then for every 128-sphere chunk wait for its MMAs, read the 128 accumulators of the own ray
@@ -94,17 +96,19 @@ __host__ __device__ inline Layout make_layout(uint32_t rows) {
 #ifdef __CUDACC__
 __device__ __forceinline__ bool is_issuer_thread() { return (int)threadIdx.x >= kShadeThreads; }
 
-// Wait with a timer back-off for hand-offs that are known to take long: a warp in tc::mbar_wait re-polls on every
-// wake-up of NANOSLEEP.SYNCS (5 instructions each; 27 % of all executed instructions of the first self-scan build),
-// and those polls come out of the issue slots of the five other warps of the sub-partition.  NS = 0: tc::mbar_wait.
+// Tuning knobs (each measured in a same-call A/B on the final scene, 100 spp; DESIGN.md section 4 has the numbers).
 #ifndef UECRT_TS_LD64
-#define UECRT_TS_LD64 0
+#define UECRT_TS_LD64 0            // 1: two tcgen05.ld of 32 columns in flight (no difference: the reads are issue-bound, not round-trip-bound)
 #endif
 #ifndef UECRT_TS_IDLE_SKIP
-#define UECRT_TS_IDLE_SKIP 0      // 1: tiles / warps without a live ray skip the MMAs / the accumulator reads; takes 25 us off the drain of a launch and adds 1.2 % to every round (vote + branch on the chain): measured slower at 63 and at 500 spp
+#define UECRT_TS_IDLE_SKIP 0       // 1: tiles / warps without a live ray skip the MMAs / the reads: 25 us off the drain of a launch, 1.2 % onto every round
 #endif
+// How each hand-off is waited for.  0: tc::mbar_wait (try_wait + NANOSLEEP.SYNCS: the warp re-polls with 5 instructions on
+// every wake-up; a quarter of all executed instructions are such polls); -1: spin on test_wait (no hardware suspend);
+// N > 0: test_wait with a timer sleep of N ns in between.  The issuer spins on "slot read" (16.8 against 17.3 ms with the
+// suspending wait, 17.0 - 17.1 with 20 - 100 ns sleeps); every other variant of every other wait was slower.
 #ifndef UECRT_TS_SLEEP_EMPTY
-#define UECRT_TS_SLEEP_EMPTY -1    // the issuer spins on "slot read" (16.8 against 17.3 ms with the suspending wait, 100 spp)
+#define UECRT_TS_SLEEP_EMPTY -1
 #endif
 #ifndef UECRT_TS_SLEEP_READY
 #define UECRT_TS_SLEEP_READY 0
